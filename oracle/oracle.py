@@ -92,6 +92,12 @@ def lib():
         L.orc_rollout_random.restype = C.c_int64
         L.orc_rollout_random.argtypes = [C.POINTER(OrcCfg), C.c_int32, C.c_int64, C.c_uint64, C.c_uint64,
                                          C.c_int32, C.c_int32, dp]
+        L.orc_batch_create.restype = C.c_void_p
+        L.orc_batch_create.argtypes = [C.POINTER(OrcCfg), C.c_int32, C.c_uint64, C.c_int32, C.c_int32]
+        L.orc_batch_destroy.argtypes = [C.c_void_p]
+        L.orc_batch_step_random.restype = C.c_double
+        L.orc_batch_step_random.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32]
+        L.orc_max_threads.restype = C.c_int32
         _lib = L
     return _lib
 
@@ -245,3 +251,27 @@ def rollout_random(cfg, num_envs, steps, seed=42, action_seed=1, reset_episodes=
     n = lib().orc_rollout_random(C.byref(cfg), num_envs, steps, seed, action_seed, reset_episodes, threads,
                                  C.byref(chk))
     return int(n), chk.value
+
+
+class OracleBatch:
+    """Persistent batch of independent oracle envs stepped with the Bernoulli action stream on
+    OpenMP threads (the timed CPU arm of bench.py)."""
+
+    def __init__(self, cfg, num_envs, seed=42, reset_episodes=200, threads=0):
+        self.num_envs, self.threads = num_envs, threads
+        self._h = C.c_void_p(lib().orc_batch_create(C.byref(cfg), num_envs, seed, reset_episodes, threads))
+
+    def step_random(self, step, action_seed=1):
+        return lib().orc_batch_step_random(self._h, action_seed, step, self.threads)
+
+    def close(self):
+        if self._h:
+            lib().orc_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+def max_threads():
+    return int(lib().orc_max_threads())

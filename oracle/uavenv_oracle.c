@@ -533,3 +533,71 @@ int64_t orc_rollout_random(const orc_cfg *c, int32_t num_envs, int64_t steps, ui
     if (checksum) *checksum = sum;
     return total;
 }
+
+/* ------------------------------------------------------------------ persistent batch (bench --impl reference) */
+
+struct orc_batch {
+    int32_t E, reset_episodes;
+    uint64_t seed;
+    orc_env **envs;
+    uint32_t *episode, *scene;
+};
+
+orc_batch *orc_batch_create(const orc_cfg *c, int32_t num_envs, uint64_t seed, int32_t reset_episodes, int32_t threads) {
+    orc_batch *B = (orc_batch *)calloc(1, sizeof(orc_batch));
+    B->E = num_envs; B->seed = seed; B->reset_episodes = reset_episodes;
+    B->envs = (orc_env **)calloc((size_t)num_envs, sizeof(orc_env *));
+    B->episode = (uint32_t *)calloc((size_t)num_envs, sizeof(uint32_t));
+    B->scene = (uint32_t *)calloc((size_t)num_envs, sizeof(uint32_t));
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#pragma omp parallel for schedule(static)
+#endif
+    for (int32_t b = 0; b < num_envs; ++b) {
+        float obs[ORC_SEQ_LEN * ORC_STATE_DIM];
+        B->envs[b] = orc_create(c);
+        B->episode[b] = 1;
+        orc_generate_scene(B->envs[b], seed, (uint32_t)b, 0);
+        orc_reset(B->envs[b], obs);
+    }
+    (void)threads;
+    return B;
+}
+
+void orc_batch_destroy(orc_batch *B) {
+    if (!B) return;
+    for (int32_t b = 0; b < B->E; ++b) orc_destroy(B->envs[b]);
+    free(B->envs); free(B->episode); free(B->scene); free(B);
+}
+
+/* one reference-algorithm step of every env with the Bernoulli action stream; returns sum of rewards */
+double orc_batch_step_random(orc_batch *B, uint64_t action_seed, uint64_t step, int32_t threads) {
+    double sum = 0.0;
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#pragma omp parallel for schedule(static) reduction(+ : sum)
+#endif
+    for (int32_t b = 0; b < B->E; ++b) {
+        float obs[ORC_SEQ_LEN * ORC_STATE_DIM];
+        double reward; int32_t done, rows; orc_info info;
+        orc_env *e = B->envs[b];
+        orc_step(e, orc_random_action(action_seed, step, (uint32_t)b), obs, &rows, &reward, &done, &info);
+        sum += reward;
+        if (done) {                                   /* main_train.py:79 schedule */
+            ++B->episode[b];
+            if (B->reset_episodes > 0 && B->episode[b] % (uint32_t)B->reset_episodes == 0)
+                orc_generate_scene(e, B->seed, (uint32_t)b, ++B->scene[b]);
+            orc_reset(e, obs);
+        }
+    }
+    (void)threads;
+    return sum;
+}
+
+int32_t orc_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}

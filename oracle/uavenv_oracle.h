@@ -114,6 +114,13 @@ int64_t orc_rollout_random(const orc_cfg *c, int32_t num_envs, int64_t steps, ui
                            uint64_t action_seed, int32_t reset_episodes, int32_t threads,
                            double *checksum);
 
+/* persistent batch of independent envs for the timed reference arm (bench.py --impl reference) */
+typedef struct orc_batch orc_batch;
+orc_batch *orc_batch_create(const orc_cfg *c, int32_t num_envs, uint64_t seed, int32_t reset_episodes, int32_t threads);
+void orc_batch_destroy(orc_batch *b);
+double orc_batch_step_random(orc_batch *b, uint64_t action_seed, uint64_t step, int32_t threads);
+int32_t orc_max_threads(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,208 @@
+// uavenv_device.cuh - device-side records and scalar building blocks of the batched
+// UAV->target allocation environment (sm_100a).
+//
+// Reference semantics: envs/mechanics.py:11-241 (scores, observation row), envs/entities.py:13-61
+// (entity state).  All score arithmetic is fp64 in the reference's operation order (this file is
+// compiled with -fmad=false) because the Eq.21 accept test `new_r >= prev_r`
+// (envs/uav_env.py:317) has to come out bit-identical to the reference's fp64 decision.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace uavk {
+
+constexpr int kStateDim = 14;  // configs/config.py:61
+constexpr int kSeqLen = 5;     // configs/config.py:62
+constexpr int kObsFloats = kStateDim * kSeqLen;
+
+// ------------------------------------------------------------------------------------------------
+// HBM layout.  Entities are 64-byte records, contiguous per env ("the env's tile"): a pointer pair
+// (k, m) costs one 64 B gather per record, and the cooperative reset / scene generation /
+// score-matrix paths stream the tile with fully coalesced accesses.
+
+struct __align__(64) UavRec {  // envs/entities.py:13-36 (live fields) + two per-scene derived values
+    double x, y, vx, vy;       // sector 0: kinematics
+    double load, cost;         // sector 1
+    double p_pen;              //   calc_penetration_prob(uav): target-independent (mechanics.py:118-163)
+    double speed;              //   ||velocity||
+};
+
+struct __align__(64) TgtRec {  // envs/entities.py:39-49 + velocity norm (uav_env.py:141, mechanics.py:100)
+    double x, y, speed, value; // sector 0: static
+    double nh;                 // sector 1: prod(1 - p_final) over the lock list  ("target health")
+    double nh_pure;            //           prod(1 - p_damage)
+    double lock_cost;          //           sum of costs of the UAVs locked on it (chi_mc numerator)
+    int32_t lock_cnt;          //           len(locked_by_uavs); covered ("kill flag") <=> lock_cnt > 0
+    int32_t id;                //           Target.id (list position != id after the shuffle, uav_env.py:173)
+};
+static_assert(sizeof(UavRec) == 64 && sizeof(TgtRec) == 64, "records must be one 64 B line half");
+
+struct NfzRec { double x, y, radius; };            // envs/entities.py:52-55
+struct IntRec { double x, y, vx, vy; };            // envs/entities.py:58-61 + velocity (uav_env.py:168)
+
+// Scalar per-env state, structure-of-arrays over B (thread-per-env accesses are fully coalesced).
+struct Header {
+    int32_t *k, *m;             // uav_idx / target_idx                    envs/uav_env.py:33-34
+    int32_t *n_assigned;        // number of locked (UAV,target) pairs A
+    int32_t *n_covered;         // N0                                      envs/uav_env.py:278-282
+    int32_t *age;               // valid rows of the observation window (0..5)
+    int32_t *episode;           // 1-based episode counter                 main_train.py:77
+    int32_t *scene_idx;         // scenes generated so far
+    uint8_t *finished;          // auto_reset = 0 only
+    double *rev;                // sum_m (1 - nh_m) * value_m              envs/uav_env.py:264-265
+    double *cost_sum;           // sum of costs of assigned UAVs           envs/uav_env.py:262 / :195
+    double *covered_val;        // sum of values of covered targets        envs/uav_env.py:199
+    double *sum_pd, *sum_pf;    // sums over locked pairs                  envs/uav_env.py:370-408
+    double *total_val;          // sum of target values (per scene)        envs/uav_env.py:198
+    double *total_cost;         // total_swarm_cost (per scene)            envs/uav_env.py:118
+    double *cur_pf, *cur_pd;    // calc_advantage of the CURRENT pointer pair (computed with its obs row)
+};
+
+struct Params {
+    int32_t B, N, M, K1, K2;
+    int32_t reset_episodes, auto_reset;
+    double zeta_d, k, c1, c2, c3, c4, omega;
+    double weather_speed, weather_load;
+    double map_w, map_h, uav_x_lo, uav_x_hi, tgt_x_lo, tgt_x_hi, intercept_rad;
+    uint32_t seed_lo, seed_hi;
+    uint32_t env_id_base;
+    // device arrays
+    UavRec *uav;        // [B][N]
+    TgtRec *tgt;        // [B][M]
+    int32_t *assigned;  // [B][N]  target id or -1     envs/entities.py:30
+    int32_t *uav_type;  // [B][N]  cold
+    double2 *tgt_vel;   // [B][M]  cold
+    NfzRec *nfz;        // [B][K1]
+    IntRec *intc;       // [B][K2]
+    float2 *hist;       // [5][7][B] observation ring (two features per element)
+    uint32_t *step_ctr; // [0] = ring head (steps taken), [1] = blocks-finished counter
+    Header hd;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. SC'11): counter = (element, stream, scene index, global env id),
+// key = seed.  (tests cross-check raw blocks and whole scenes against an independent CPU implementation)
+
+__device__ __forceinline__ uint4 philox4x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2,
+                                            uint32_t c3) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {  // uniform [0,1) on the 2^-53 grid
+    return (double)((((uint64_t)hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0);
+}
+
+enum Stream : uint32_t {  // draw list of envs/uav_env.py:65-173
+    S_UAV_TYPE = 1, S_UAV_POS = 2, S_UAV_DYN = 3, S_N2 = 4, S_TGT_VAL = 5, S_TGT_POS = 6, S_TGT_VEL = 7,
+    S_NFZ_A = 8, S_NFZ_B = 9, S_INT_A = 10, S_INT_B = 11, S_TGT_LIST = 12
+};
+
+// ------------------------------------------------------------------------------------------------
+// Scores (fp64, reference operation order)
+
+__device__ __forceinline__ double clip01(double v) { return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v); }
+
+// envs/mechanics.py:11-57 calc_angle_score (Eq.1); `speed` = ||v|| precomputed, `dist` returned
+__device__ __forceinline__ double angle_score(double ux, double uy, double vx, double vy, double speed, double tx,
+                                              double ty, double &dist) {
+    const double dx = tx - ux, dy = ty - uy;
+    dist = sqrt(dx * dx + dy * dy);
+    if (dist < 1e-6) return 1.0;                                   // :23
+    const double nx = dx / dist, ny = dy / dist;                   // :28
+    double wx = 1.0, wy = 0.0;                                     // :32-34
+    if (!(speed < 1e-6)) { wx = vx / speed; wy = vy / speed; }     // :36
+    double c = nx * wx + ny * wy;                                  // :39
+    c = c < -1.0 ? -1.0 : (c > 1.0 ? 1.0 : c);
+    const double sigma = acos(c);                                  // :40
+    double b = 0.002 * dist;                                       // :44
+    if (b < 1e-6) b = 1e-6;                                        // :51
+    const double q = sigma / (b * 3.141592653589793);
+    return exp(-(q * q));                                          // :55-56
+}
+
+// envs/mechanics.py:61-68 calc_speed_score (Eq.2)
+__device__ __forceinline__ double speed_score(double kparam, double uav_speed, double tgt_speed) {
+    if (uav_speed < 1e-6) return 0.0;
+    return clip01(1.0 - (kparam * tgt_speed / uav_speed));
+}
+
+// envs/mechanics.py:72-89 calc_dist_score (Eq.3), D_mid = 0
+__device__ __forceinline__ double dist_score(double dist, double zeta) {
+    const double q = (dist - 0.0) / zeta;
+    return exp(-(q * q));
+}
+
+// envs/mechanics.py:93-114 calc_damage_prob (Eq.4)
+__device__ __forceinline__ double damage_prob(const Params &P, double ux, double uy, double vx, double vy,
+                                              double speed, double load, double tx, double ty, double tspeed) {
+    double dist;
+    const double e_angle = angle_score(ux, uy, vx, vy, speed, tx, ty, dist);
+    const double e_dist = dist_score(dist, P.zeta_d);
+    const double e_speed = speed_score(P.k, speed, tspeed);
+    const double term = P.c1 * e_dist + P.c2 * e_speed;            // :111
+    return clip01(e_angle * term * load);                          // :112-114
+}
+
+// envs/mechanics.py:118-163 calc_penetration_prob (Eq.5-6): depends on the UAV only
+__device__ __forceinline__ double penetration_prob(const Params &P, int b, double ux, double uy, double vx,
+                                                   double vy, double speed) {
+    double p = 1.0;
+    const NfzRec *Z = P.nfz + (size_t)b * P.K1;
+    for (int i = 0; i < P.K1; ++i) {                               // :130-141
+        double dist;
+        const double ea = angle_score(ux, uy, vx, vy, speed, Z[i].x, Z[i].y, dist);
+        const double ed = dist_score(dist, 10.0);
+        p *= clip01((1.0 - ea) * (1.0 - ed));
+    }
+    const IntRec *I = P.intc + (size_t)b * P.K2;
+    for (int i = 0; i < P.K2; ++i) {                               // :144-161
+        double dist;
+        const double ea = angle_score(ux, uy, vx, vy, speed, I[i].x, I[i].y, dist);
+        const double ed = dist_score(dist, 10.0);
+        const double ispeed = sqrt(I[i].vx * I[i].vx + I[i].vy * I[i].vy);
+        const double es = speed_score(P.k, speed, ispeed);
+        const double term = P.c3 * (1.0 - ed) + P.c4 * es;
+        p *= clip01((1.0 - ea) * term);
+    }
+    return p;
+}
+
+// envs/mechanics.py:185-241 get_state_vector (Eq.15): fp64 features, cast to f32, then the power-of-two
+// scalings applied in f32 exactly as the reference does (:235-239).
+__device__ __forceinline__ void state_vector(double cost, double value, double chi_c, double chi_v, double chi_mc,
+                                             double p_km, double p_km_dmg, double prev_joint_p, double prev_revenue,
+                                             double prev_joint_p_pure, float *o) {
+    const double hat_p = 1.0 - (1.0 - prev_joint_p) * (1.0 - p_km);            // :196
+    const double hat_p_pure = 1.0 - (1.0 - prev_joint_p_pure) * (1.0 - p_km_dmg);  // :199
+    const double hat_G = hat_p * value;                                        // :201
+    o[0] = (float)cost * 0.5f;
+    o[1] = (float)value * 0.0625f;
+    o[2] = (float)chi_c;
+    o[3] = (float)chi_v;
+    o[4] = (float)chi_mc;
+    o[5] = (float)p_km;
+    o[6] = (float)prev_joint_p;
+    o[7] = (float)hat_p;
+    o[8] = (float)prev_revenue * 0.0625f;
+    o[9] = (float)hat_G * 0.0625f;
+    o[10] = (float)(p_km_dmg - p_km);                                          // :204
+    o[11] = (float)(hat_p_pure - hat_p);                                       // :205
+    o[12] = (float)((hat_p_pure * value) - hat_G) * 0.0625f;                   // :206
+    o[13] = 1.0f;  // float(uav.available): the pointer UAV is always unassigned (uav_env.py:317-324)
+}
+
+// envs/uav_env.py:271-293 _calculate_paper_reward (Eq.19) from the running aggregates
+__device__ __forceinline__ double paper_reward(double J, int n0, int M) {
+    return (n0 == M) ? 2.0 * J : J * ((double)n0 / (double)M);
+}
+
+}  // namespace uavk
