@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""Benchmark of the rollout hot path: env-steps/s of the fused step kernel (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c5] [--impl ours|reference]
+
+One "step" = one uavenv_step launch over the whole env batch of this GPU with synthetic Bernoulli(1/2)
+actions.  Prints ONE JSON line (rank 0).  N > 1: launched by torchrun, one rank per GPU,
+env batch sharded by global env id, no data-path collective (weak scaling: the per-GPU batch is fixed).
+
+Timing: W (>= 3) warm-up steps, then exactly K timed steps; every timed step is bracketed by CUDA events on
+the launching stream and preceded by an L2 flush (a 256 MiB write) outside the bracket; per-rank time = sum
+of the K brackets; job time = max over ranks.  `value` has the actions resident in HBM; `e2e` drives the same
+step through the host-buffer entry point (uavenv_step_host): actions host->device and reward/done
+device->host inside each bracket.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# BASELINE.json configs.  c3 is the configuration the 1/2/4/8-GPU env-steps/s metric is quoted on and the
+# default; c2 (4096 default-size envs, the bit-exact parity config) and c5 (large swarm) are selectable.
+WORKLOADS = {
+    "c2": dict(name="configs[1]: 4096 envs x (30 UAVs x 10 targets), env step only", envs_per_gpu=4096, N=30, M=10),
+    "c3": dict(name="configs[2]: 65536 envs x (64 UAVs x 64 targets), env step only", envs_per_gpu=65536, N=64, M=64),
+    "c5": dict(name="configs[4]: 8192 envs/GPU x (256 UAVs x 256 targets), auto-reset", envs_per_gpu=8192, N=256,
+               M=256),
+}
+ACTION_SEED = 1
+SCENE_SEED = 42          # configs/config.py:85 SEED
+BURN_IN_STEPS = 300      # untimed: de-synchronises the envs' decision pointers (episodes are ~2N steps long)
+POOL = 64                # pre-generated action vectors cycled through the timed steps
+L2_FLUSH_BYTES = 256 << 20
+
+# Algorithmic bytes per env-step of THIS design (DESIGN.md §4 derives each term): actions 8, reward 4, done 1,
+# info 21, scalar state read 92 / write 76, window ring read 224 / write 56, window out 280, records of the new
+# pointer pair 128, accept path (p=1/2) 0.5*(64+32+32+4).
+ALGO_BYTES_PER_ENV_STEP = 8 + 4 + 1 + 21 + 92 + 76 + 224 + 56 + 280 + 128 + 0.5 * (64 + 32 + 32 + 4)
+
+
+def survey_bytes(M):     # SURVEY.md §8d traffic model (re-sums J over all M targets every step)
+    return 665 + 20 * M
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_config(ub, w, reset_episodes=200):
+    return ub.Config(NUM_UAVS=w["N"], NUM_TARGETS=w["M"], RESET_EPISODES=reset_episodes)
+
+
+def run_reference(args, w, rank, world):
+    """The reference's CPU algorithm (oracle port: the reference itself is Python and cannot travel to the GPU
+    box) on all host threads.  A step = one reference-algorithm step of a bounded sample of the workload's envs."""
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    ocfg = orc.make_cfg(NUM_UAVS=w["N"], NUM_TARGETS=w["M"])
+    threads = orc.max_threads()
+    sample = max(threads * 8, min(w["envs_per_gpu"], 2048 if w["N"] <= 64 else 256))
+    batch = orc.OracleBatch(ocfg, sample, seed=SCENE_SEED, reset_episodes=200, threads=threads)
+    for s in range(args.warmup):
+        batch.step_random(s, ACTION_SEED)
+    t0 = time.perf_counter()
+    for s in range(args.warmup, args.warmup + args.steps):
+        batch.step_random(s, ACTION_SEED)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    desc = "%d of the workload's envs, %d steps each, reference algorithm (C port, OpenMP)" % (sample, args.steps)
+    print(json.dumps({
+        "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["name"], "num_uavs": w["N"], "num_targets": w["M"], "sample_envs": sample,
+                   "actions": "Bernoulli(0.5) counter RNG", "reset_schedule": "full reset every 200 episodes"},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def cpu_baseline(w, seconds=12.0):
+    from oracle import oracle as orc
+    ocfg = orc.make_cfg(NUM_UAVS=w["N"], NUM_TARGETS=w["M"])
+    threads = orc.max_threads()
+    sample = max(threads * 8, 1024 if w["N"] <= 64 else 128)
+    batch = orc.OracleBatch(ocfg, sample, seed=SCENE_SEED, reset_episodes=200, threads=threads)
+    for s in range(3):
+        batch.step_random(s, ACTION_SEED)
+    t0, s = time.perf_counter(), 3
+    while time.perf_counter() - t0 < seconds:
+        batch.step_random(s, ACTION_SEED)
+        s += 1
+    dt = time.perf_counter() - t0
+    n = s - 3
+    return {"value": sample * n / dt, "unit": "env-steps/s", "cores": threads, "kind": "port",
+            "sample": "%d envs x %d steps of the same workload, reference algorithm (C port of envs/uav_env.py, "
+                      "OpenMP over envs), %.1f s" % (sample, n, dt)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs-per-gpu", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="diagnostic only: keep L2 warm between steps")
+    ap.add_argument("--reset-episodes", type=int, default=200, help="diagnostic only: cfg.RESET_EPISODES (200)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    w = dict(WORKLOADS[args.workload])
+    if args.envs_per_gpu:
+        w["envs_per_gpu"] = args.envs_per_gpu
+
+    rank, local_rank, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
+    if args.impl == "reference":
+        run_reference(args, w, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import uavenv_b200 as ub
+    from target_allocation_ppo_transformer_b200 import parallel
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the env has no CPU fallback")
+    rank, local_rank, world = parallel.init("nccl")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B = w["envs_per_gpu"]
+    K, W = args.steps, args.warmup
+    env = ub.UAVEnvBatched(B, device=dev, seed=SCENE_SEED, env_id_base=rank * B, config=make_config(ub, w, args.reset_episodes))
+    env.reset(full_reset=True)
+    # steady state of the main_train.py:79 schedule: after long training the envs sit at different phases of
+    # the 200-episode regeneration cycle; start them staggered so regenerations are amortised into the timing
+    gid = np.arange(rank * B, (rank + 1) * B, dtype=np.uint64)
+    env.set_episode_counters((1 + (gid * np.uint64(2654435761) >> np.uint64(7)) % np.uint64(200)).astype(np.int32))
+    for s in range(BURN_IN_STEPS):
+        env.step(env.random_actions(s, ACTION_SEED))
+    pool = torch.empty(POOL, B, dtype=torch.int64, device=dev)
+    for i in range(POOL):
+        env.random_actions(BURN_IN_STEPS + i, ACTION_SEED, out=pool[i])
+    pool_host = pool.cpu().pin_memory()
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def timed(step_fn, n_warm, n_timed):
+        for i in range(n_warm):
+            step_fn(i)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_timed)]
+        parallel.barrier()
+        torch.cuda.synchronize(dev)
+        for i in range(n_timed):
+            if not args.no_flush:
+                flush.fill_(i & 0xff)          # L2 flush, outside the bracket
+            ev[i][0].record(stream)
+            step_fn(n_warm + i)
+            ev[i][1].record(stream)
+        torch.cuda.synchronize(dev)
+        parallel.barrier()
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        return parallel.reduce_scalar(ms, "max", dev)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # --- device-resident inputs: the fused kernel alone --------------------------------------------------
+    ms_dev = timed(lambda i: env.step(pool[i % POOL]), W, K)
+    # --- end to end through the host-buffer entry point ----------------------------------------------------
+    ms_e2e = timed(lambda i: env.step_host(pool_host[i % POOL]), W, K)
+    clocks = sampler.stop() if rank == 0 else None
+    drift = env.recompute_objective()
+    drift = parallel.reduce_scalar(drift, "max", dev)
+
+    if rank == 0:
+        total_envs = B * world
+        value = total_envs * K / (ms_dev * 1e-3)
+        e2e_value = total_envs * K / (ms_e2e * 1e-3)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        per_launch_s = ms_dev * 1e-3 / K
+        achieved = ALGO_BYTES_PER_ENV_STEP * B / per_launch_s / 1e9
+        surv = survey_bytes(w["M"]) * B / per_launch_s / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json"))).get(args.workload)
+        except Exception:
+            pass
+        out = {
+            "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["name"], "envs_per_gpu": B, "num_uavs": w["N"], "num_targets": w["M"],
+                       "actions": "Bernoulli(0.5), counter RNG keyed (seed=1, step, global env id), resident in HBM",
+                       "auto_reset": True, "reset_schedule": "full reset every %d episodes, staggered steady state" % args.reset_episodes,
+                       "burn_in_steps": BURN_IN_STEPS, "l2": "flushed between timed steps (256 MiB write)"
+                       if not args.no_flush else "NOT flushed (diagnostic)",
+                       "timing": "CUDA events per step on the launching stream, summed; max over ranks",
+                       "pair_evals_per_sec": value, "objective_drift_max_abs": drift,
+                       "parallelism": "env-sharded x%d, no rollout collective" % world},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "uavk::step_kernel",
+                         "bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650",
+                         "survey_model": {"bytes_per_env_step": survey_bytes(w["M"]), "achieved": surv,
+                                          "frac": surv / peak,
+                                          "note": "SURVEY §8d counts a 20*M B re-read of all target products per "
+                                                  "step; this kernel carries the objective incrementally and does "
+                                                  "not move those bytes"}},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "ms_per_step": ms_e2e / K,
+                    "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": B * 5,
+                    "api": "UAVEnvBatched.step_host -> uavenv_step_host (pinned host actions in; reward, done out; "
+                           "observation window stays in HBM for the policy)"},
+            "gpu_launches": K, "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(w)
+        print(json.dumps(out))
+    env.close()
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

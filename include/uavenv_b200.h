@@ -143,6 +143,11 @@ int uavenv_load_scene(uavenv_t *h, const uavenv_scene_t *scene, int32_t first_en
 int uavenv_get_scene(uavenv_t *h, uavenv_scene_t *scene, int32_t first_env, int32_t count);
 int uavenv_get_state(uavenv_t *h, uavenv_state_t *state, int32_t first_env, int32_t count);
 
+/* restores the 1-based per-env episode counters that drive the main_train.py:79 regeneration
+ * schedule (resume of a run; staggered steady state for benchmarks).  h_episode[count] is a HOST
+ * array.  Synchronous. */
+int uavenv_set_episode_counters(uavenv_t *h, const int32_t *h_episode, int32_t first_env, int32_t count);
+
 /* replaces the double loop over mechanics.calc_advantage of main.py:38-45 (mechanics.py:167-181):
  * p_final / p_damage for every (env, UAV, target), [B,N,M] list order.  Either pair may be NULL. */
 int uavenv_score_matrix(uavenv_t *h, float *d_p_final, float *d_p_damage, void *stream);

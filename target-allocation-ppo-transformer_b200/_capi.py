@@ -101,6 +101,8 @@ def load():
     L.uavenv_load_scene.argtypes = [vp, C.POINTER(UavenvScene), i32, i32, vp]
     L.uavenv_get_scene.argtypes = [vp, C.POINTER(UavenvScene), i32, i32]
     L.uavenv_get_state.argtypes = [vp, C.POINTER(UavenvState), i32, i32]
+    L.uavenv_set_episode_counters.argtypes = [vp, vp, i32, i32]
+    L.uavenv_set_episode_counters.restype = C.c_int
     L.uavenv_score_matrix.argtypes = [vp, vp, vp, vp]
     L.uavenv_score_matrix_f64.argtypes = [vp, vp, vp, vp]
     L.uavenv_recompute_objective.argtypes = [vp, c_f64p, vp]

@@ -93,7 +93,7 @@ static int create_impl(uavenv *h) {
     std::memset(&P, 0, sizeof P);
     P.B = h->B; P.N = c.num_uavs; P.M = c.num_targets; P.K1 = c.num_nfz; P.K2 = c.num_interceptors;
     P.reset_episodes = c.reset_episodes; P.auto_reset = c.auto_reset ? 1 : 0;
-    P.zeta_d = c.param_zeta_d; P.k = c.param_k; P.c1 = c.param_c1; P.c2 = c.param_c2; P.c3 = c.param_c3;
+    P.zeta_d = c.param_zeta_d; P.inv_zeta_d = 1.0 / c.param_zeta_d; P.k = c.param_k; P.c1 = c.param_c1; P.c2 = c.param_c2; P.c3 = c.param_c3;
     P.c4 = c.param_c4; P.omega = c.cost_weight_omega;
     P.weather_speed = c.weather_speed_factor; P.weather_load = c.weather_load_factor;
     P.map_w = c.map_width; P.map_h = c.map_height;
@@ -105,29 +105,26 @@ static int create_impl(uavenv *h) {
     CU_TRY(h, dev_alloc(h, &P.tgt, B * M));
     CU_TRY(h, dev_alloc(h, &P.assigned, B * N));
     CU_TRY(h, dev_alloc(h, &P.uav_type, B * N));
+    CU_TRY(h, dev_alloc(h, &P.uav_vel, B * N));
     CU_TRY(h, dev_alloc(h, &P.tgt_vel, B * M));
     CU_TRY(h, dev_alloc(h, &P.nfz, B * K1));
     CU_TRY(h, dev_alloc(h, &P.intc, B * K2));
-    CU_TRY(h, dev_alloc(h, &P.hist, (size_t)kSeqLen * (kStateDim / 2) * B));
+    const size_t tiles = (B + 31) / 32;
+    CU_TRY(h, dev_alloc(h, &P.hist, tiles * kRingTileElems));
     CU_TRY(h, dev_alloc(h, &P.step_ctr, 2));
-    Header &H = P.hd;
-    int32_t **ifields[] = {&H.k, &H.m, &H.n_assigned, &H.n_covered, &H.age, &H.episode, &H.scene_idx};
-    for (auto f : ifields) { CU_TRY(h, dev_alloc(h, f, B)); CU_TRY(h, cudaMemset(*f, 0, B * sizeof(int32_t))); }
-    CU_TRY(h, dev_alloc(h, &H.finished, B));
-    CU_TRY(h, cudaMemset(H.finished, 0, B));
-    double **dfields[] = {&H.rev, &H.cost_sum, &H.covered_val, &H.sum_pd, &H.sum_pf, &H.total_val, &H.total_cost,
-                          &H.cur_pf, &H.cur_pd};
-    for (auto f : dfields) { CU_TRY(h, dev_alloc(h, f, B)); CU_TRY(h, cudaMemset(*f, 0, B * sizeof(double))); }
+    CU_TRY(h, dev_alloc(h, &P.hdr, tiles * kHdrTileBytes));
+    CU_TRY(h, cudaMemset(P.hdr, 0, tiles * kHdrTileBytes));
     CU_TRY(h, cudaMemset(P.step_ctr, 0, 2 * sizeof(uint32_t)));
-    CU_TRY(h, cudaMemset(P.hist, 0, (size_t)kSeqLen * (kStateDim / 2) * B * sizeof(float2)));
+    CU_TRY(h, cudaMemset(P.hist, 0, tiles * kRingTileElems * sizeof(float2)));
     CU_TRY(h, cudaMemset(P.assigned, 0xff, B * N * sizeof(int32_t)));
     CU_TRY(h, dev_alloc(h, &h->obs_buf, B * kObsFloats));
     CU_TRY(h, dev_alloc(h, &h->d_actions, B));
     CU_TRY(h, dev_alloc(h, &h->d_reward, B));
     CU_TRY(h, dev_alloc(h, &h->d_done, B));
     CU_TRY(h, dev_alloc(h, &h->d_scratch, 1));
-    h->reset_smem = (32 + M) * sizeof(double) + std::max(N, M) * sizeof(uint32_t);
-    if (h->reset_smem > 40 * 1024) {
+    // per-warp scratch of the scene generator: M doubles + max(N,M) keys, for the 4 warps of a CTA
+    h->reset_smem = (size_t)kWarpsPerCta * (M * sizeof(double) + std::max(N, M) * sizeof(uint32_t));
+    if (h->reset_smem > 8 * 1024) {
         CU_TRY(h, cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->reset_smem));
         CU_TRY(h, cudaFuncSetAttribute(reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->reset_smem));
     }
@@ -188,7 +185,7 @@ extern "C" int uavenv_reset(uavenv_t *h, int32_t full_reset, const uint8_t *d_en
     if (d_env_mask && !h->ready)
         return fail(h, UAVENV_ESTATE, "uavenv_reset: the first reset must cover every env (d_env_mask = NULL)");
     CU_TRY(h, cudaSetDevice(h->device));
-    const int grid = std::min(h->B, 148 * 16);
+    const int grid = std::min((h->B + 3) / 4, 148 * 16);
     reset_kernel<<<grid, kResetThreads, h->reset_smem, (cudaStream_t)stream>>>(h->P, full_reset ? 1 : 0, d_env_mask, 0,
                                                                               h->B, d_obs);
     int rc = launch_check(h, "reset_kernel");
@@ -269,7 +266,7 @@ extern "C" int uavenv_load_scene(uavenv_t *h, const uavenv_scene_t *sc, int32_t 
     S(sc->int_x, k2, &s.int_x); S(sc->int_y, k2, &s.int_y); S(sc->int_vx, k2, &s.int_vx); S(sc->int_vy, k2, &s.int_vy);
     int rc = UAVENV_OK;
     if (e == cudaSuccess) {
-        const int grid = std::min(count, 148 * 16);
+        const int grid = std::min((count + 3) / 4, 148 * 16);
         pack_scene_kernel<<<grid, kResetThreads>>>(P, s, first_env, count);
         reset_kernel<<<grid, kResetThreads, h->reset_smem>>>(P, 2, nullptr, first_env, count, d_obs ? d_obs : h->obs_buf);
         e = cudaDeviceSynchronize();
@@ -294,19 +291,20 @@ extern "C" int uavenv_get_scene(uavenv_t *h, uavenv_scene_t *sc, int32_t first_e
     CU_TRY(h, cudaSetDevice(h->device));
     CU_TRY(h, cudaDeviceSynchronize());
     const size_t n = (size_t)count * P.N, m = (size_t)count * P.M, k1 = (size_t)count * P.K1, k2 = (size_t)count * P.K2;
-    std::vector<UavRec> U; std::vector<TgtRec> T; std::vector<int32_t> ty; std::vector<double2> tv;
+    std::vector<UavRec> U; std::vector<TgtRec> T; std::vector<int32_t> ty; std::vector<double2> tv, uv;
     std::vector<NfzRec> Z; std::vector<IntRec> I;
     CU_TRY(h, fetch(U, P.uav + (size_t)first_env * P.N, n));
     CU_TRY(h, fetch(T, P.tgt + (size_t)first_env * P.M, m));
     CU_TRY(h, fetch(ty, P.uav_type + (size_t)first_env * P.N, n));
     CU_TRY(h, fetch(tv, P.tgt_vel + (size_t)first_env * P.M, m));
+    CU_TRY(h, fetch(uv, P.uav_vel + (size_t)first_env * P.N, n));
     CU_TRY(h, fetch(Z, P.nfz + (size_t)first_env * P.K1, k1));
     CU_TRY(h, fetch(I, P.intc + (size_t)first_env * P.K2, k2));
     for (size_t i = 0; i < n; ++i) {
         if (sc->uav_x) sc->uav_x[i] = U[i].x;
         if (sc->uav_y) sc->uav_y[i] = U[i].y;
-        if (sc->uav_vx) sc->uav_vx[i] = U[i].vx;
-        if (sc->uav_vy) sc->uav_vy[i] = U[i].vy;
+        if (sc->uav_vx) sc->uav_vx[i] = uv[i].x;
+        if (sc->uav_vy) sc->uav_vy[i] = uv[i].y;
         if (sc->uav_load) sc->uav_load[i] = U[i].load;
         if (sc->uav_cost) sc->uav_cost[i] = U[i].cost;
         if (sc->uav_type) sc->uav_type[i] = ty[i];
@@ -344,12 +342,20 @@ extern "C" int uavenv_get_state(uavenv_t *h, uavenv_state_t *st, int32_t first_e
     auto D2H = [&](void *dst, const void *src, size_t bytes) -> cudaError_t {
         return dst ? cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) : cudaSuccess;
     };
-    CU_TRY(h, D2H(st->uav_idx, P.hd.k + f, c * 4));
-    CU_TRY(h, D2H(st->target_idx, P.hd.m + f, c * 4));
     CU_TRY(h, D2H(st->assigned_target_id, P.assigned + f * P.N, c * P.N * 4));
-    CU_TRY(h, D2H(st->episode, P.hd.episode + f, c * 4));
-    CU_TRY(h, D2H(st->scene_index, P.hd.scene_idx + f, c * 4));
-    CU_TRY(h, D2H(st->finished, P.hd.finished + f, c));
+    // header tiles covering [first_env, first_env + count)
+    const size_t t0 = f / 32, t1 = (f + c + 31) / 32;
+    std::vector<unsigned char> tiles;
+    CU_TRY(h, fetch(tiles, P.hdr + t0 * kHdrTileBytes, (t1 - t0) * kHdrTileBytes));
+    for (size_t i = 0; i < c; ++i) {
+        const Hdr hv = header_at(tiles.data(), (int)(f + i - t0 * 32));
+        if (st->uav_idx) st->uav_idx[i] = hv.n(I_K);
+        if (st->target_idx) st->target_idx[i] = hv.n(I_M);
+        if (st->episode) st->episode[i] = hv.n(I_EPISODE);
+        if (st->scene_index) st->scene_index[i] = hv.n(I_SCENE);
+        if (st->finished) st->finished[i] = (uint8_t)(hv.n(I_FINISHED) != 0);
+        if (st->J_val) st->J_val[i] = hv.f(F_REV) - (P.omega * hv.f(F_COST_SUM));
+    }
     if (st->lock_count || st->not_hit || st->not_hit_pure) {
         std::vector<TgtRec> T;
         CU_TRY(h, fetch(T, P.tgt + f * P.M, c * P.M));
@@ -359,12 +365,23 @@ extern "C" int uavenv_get_state(uavenv_t *h, uavenv_state_t *st, int32_t first_e
             if (st->not_hit_pure) st->not_hit_pure[j] = T[j].nh_pure;
         }
     }
-    if (st->J_val) {
-        std::vector<double> rev, cost;
-        CU_TRY(h, fetch(rev, P.hd.rev + f, c));
-        CU_TRY(h, fetch(cost, P.hd.cost_sum + f, c));
-        for (size_t i = 0; i < c; ++i) st->J_val[i] = rev[i] - (P.omega * cost[i]);
-    }
+    return UAVENV_OK;
+}
+
+extern "C" int uavenv_set_episode_counters(uavenv_t *h, const int32_t *h_episode, int32_t first_env, int32_t count) {
+    if (!h || !h_episode) return UAVENV_EINVAL;
+    if (first_env < 0 || count <= 0 || first_env + count > h->B)
+        return fail(h, UAVENV_EINVAL, "uavenv_set_episode_counters: env range outside [0,%d)", h->B);
+    for (int32_t i = 0; i < count; ++i)
+        if (h_episode[i] < 1) return fail(h, UAVENV_EINVAL, "uavenv_set_episode_counters: counters are 1-based");
+    const Params &P = h->P;
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaDeviceSynchronize());
+    const size_t f = (size_t)first_env, c = (size_t)count, t0 = f / 32, t1 = (f + c + 31) / 32;
+    std::vector<unsigned char> tiles;
+    CU_TRY(h, fetch(tiles, P.hdr + t0 * kHdrTileBytes, (t1 - t0) * kHdrTileBytes));
+    for (size_t i = 0; i < c; ++i) header_at(tiles.data(), (int)(f + i - t0 * 32)).n(I_EPISODE) = h_episode[i];
+    CU_TRY(h, cudaMemcpy(P.hdr + t0 * kHdrTileBytes, tiles.data(), tiles.size(), cudaMemcpyHostToDevice));
     return UAVENV_OK;
 }
 

@@ -21,11 +21,12 @@ constexpr int kObsFloats = kStateDim * kSeqLen;
 // (k, m) costs one 64 B gather per record, and the cooperative reset / scene generation /
 // score-matrix paths stream the tile with fully coalesced accesses.
 
-struct __align__(64) UavRec {  // envs/entities.py:13-36 (live fields) + two per-scene derived values
-    double x, y, vx, vy;       // sector 0: kinematics
+struct __align__(64) UavRec {  // envs/entities.py:13-36 (live fields) + per-scene derived values
+    double x, y;               // sector 0: position
+    double wx, wy;             //   unit heading velocity/||velocity||, (1,0) when ||velocity|| < 1e-6 (mechanics.py:31-36)
     double load, cost;         // sector 1
     double p_pen;              //   calc_penetration_prob(uav): target-independent (mechanics.py:118-163)
-    double speed;              //   ||velocity||
+    double inv_speed;          //   1/||velocity||, or -1 when ||velocity|| < 1e-6 (mechanics.py:65)
 };
 
 struct __align__(64) TgtRec {  // envs/entities.py:39-49 + velocity norm (uav_env.py:141, mechanics.py:100)
@@ -41,28 +42,58 @@ static_assert(sizeof(UavRec) == 64 && sizeof(TgtRec) == 64, "records must be one
 struct NfzRec { double x, y, radius; };            // envs/entities.py:52-55
 struct IntRec { double x, y, vx, vy; };            // envs/entities.py:58-61 + velocity (uav_env.py:168)
 
-// Scalar per-env state, structure-of-arrays over B (thread-per-env accesses are fully coalesced).
-struct Header {
-    int32_t *k, *m;             // uav_idx / target_idx                    envs/uav_env.py:33-34
-    int32_t *n_assigned;        // number of locked (UAV,target) pairs A
-    int32_t *n_covered;         // N0                                      envs/uav_env.py:278-282
-    int32_t *age;               // valid rows of the observation window (0..5)
-    int32_t *episode;           // 1-based episode counter                 main_train.py:77
-    int32_t *scene_idx;         // scenes generated so far
-    uint8_t *finished;          // auto_reset = 0 only
-    double *rev;                // sum_m (1 - nh_m) * value_m              envs/uav_env.py:264-265
-    double *cost_sum;           // sum of costs of assigned UAVs           envs/uav_env.py:262 / :195
-    double *covered_val;        // sum of values of covered targets        envs/uav_env.py:199
-    double *sum_pd, *sum_pf;    // sums over locked pairs                  envs/uav_env.py:370-408
-    double *total_val;          // sum of target values (per scene)        envs/uav_env.py:198
-    double *total_cost;         // total_swarm_cost (per scene)            envs/uav_env.py:118
-    double *cur_pf, *cur_pd;    // calc_advantage of the CURRENT pointer pair (computed with its obs row)
+// Scalar per-env state.  Tile-major structure-of-arrays: the 32 envs of a warp own one contiguous
+// 4.75 KB tile [field][32 lanes] (f64 fields first, then i32 fields), so a warp reads its whole header
+// with fully coalesced loads at immediate offsets from ONE base pointer, out of one DRAM neighbourhood.
+enum F64Field {
+    F_REV,            // sum_m (1 - nh_m) * value_m              envs/uav_env.py:264-265
+    F_COST_SUM,       // sum of costs of assigned UAVs           envs/uav_env.py:262 / :195
+    F_COVERED_VAL,    // sum of values of covered targets        envs/uav_env.py:199
+    F_SUM_PD, F_SUM_PF,  // sums over locked pairs               envs/uav_env.py:370-408
+    F_TOTAL_VAL,      // sum of target values (per scene)        envs/uav_env.py:198
+    F_TOTAL_COST,     // total_swarm_cost (per scene)            envs/uav_env.py:118
+    // the CURRENT pointer pair (k,m), captured when its observation row was computed, so that the
+    // accept rule of the next step needs no gather:
+    F_CUR_PF, F_CUR_PD,    // calc_advantage(uav_k, target_m)    mechanics.py:167-181
+    F_CUR_VALUE,           // target_m.value
+    F_CUR_NH, F_CUR_NHP,   // target_m products before this decision
+    F_CUR_LOCK_COST,       // target_m lock cost
+    F_CUR_UCOST,           // uav_k.cost
+    NF64
 };
+enum I32Field {
+    I_K, I_M,         // uav_idx / target_idx                    envs/uav_env.py:33-34
+    I_NASSIGNED,      // number of locked (UAV,target) pairs A
+    I_NCOVERED,       // N0                                      envs/uav_env.py:278-282
+    I_AGE,            // valid rows of the observation window (0..5)
+    I_EPISODE,        // 1-based episode counter                 main_train.py:77
+    I_SCENE,          // scenes generated so far
+    I_CUR_LOCK_CNT,   // target_m lock count
+    I_CUR_TID,        // target_m.id
+    I_FINISHED,       // auto_reset = 0 only
+    NI32
+};
+constexpr size_t kHdrTileBytes = (size_t)NF64 * 32 * sizeof(double) + (size_t)NI32 * 32 * sizeof(int32_t);
+constexpr int kRingTileElems = 5 * 7 * 32;  // float2 elements of one warp tile of the observation ring
+
+struct Hdr {  // view of one env's header: field x lives at d[x*32] / i[x*32]
+    double *d;
+    int32_t *i;
+    __host__ __device__ __forceinline__ double &f(int x) const { return d[x * 32]; }
+    __host__ __device__ __forceinline__ int32_t &n(int x) const { return i[x * 32]; }
+};
+__host__ __device__ __forceinline__ Hdr header_at(unsigned char *base, int b) {
+    unsigned char *tile = base + (size_t)(b >> 5) * kHdrTileBytes;
+    Hdr h;
+    h.d = reinterpret_cast<double *>(tile) + (b & 31);
+    h.i = reinterpret_cast<int32_t *>(tile + (size_t)NF64 * 32 * sizeof(double)) + (b & 31);
+    return h;
+}
 
 struct Params {
     int32_t B, N, M, K1, K2;
     int32_t reset_episodes, auto_reset;
-    double zeta_d, k, c1, c2, c3, c4, omega;
+    double zeta_d, inv_zeta_d, k, c1, c2, c3, c4, omega;
     double weather_speed, weather_load;
     double map_w, map_h, uav_x_lo, uav_x_hi, tgt_x_lo, tgt_x_hi, intercept_rad;
     uint32_t seed_lo, seed_hi;
@@ -72,12 +103,16 @@ struct Params {
     TgtRec *tgt;        // [B][M]
     int32_t *assigned;  // [B][N]  target id or -1     envs/entities.py:30
     int32_t *uav_type;  // [B][N]  cold
+    double2 *uav_vel;   // [B][N]  cold (the records keep heading + speed)
     double2 *tgt_vel;   // [B][M]  cold
     NfzRec *nfz;        // [B][K1]
     IntRec *intc;       // [B][K2]
-    float2 *hist;       // [5][7][B] observation ring (two features per element)
-    uint32_t *step_ctr; // [0] = ring head (steps taken), [1] = blocks-finished counter
-    Header hd;
+    float2 *hist;       // [B/32][5 slots][7 feature pairs][32 lanes] observation ring, warp-tile major
+    uint32_t *step_ctr; // [0] = ring head (mod 5), [1] = CTA arrival counter of the running step
+    unsigned char *hdr; // [B/32] header tiles (kHdrTileBytes each)
+    __host__ __device__ __forceinline__ Hdr header(int b) const { return header_at(hdr, b); }
+    // ring element (slot, feature pair f) of env b: ring(b)[slot * 224 + f * 32]
+    __host__ __device__ __forceinline__ float2 *ring(int b) const { return hist + (size_t)(b >> 5) * kRingTileElems + (b & 31); }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -111,16 +146,14 @@ enum Stream : uint32_t {  // draw list of envs/uav_env.py:65-173 (SURVEY.md §3.
 
 __device__ __forceinline__ double clip01(double v) { return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v); }
 
-// envs/mechanics.py:11-57 calc_angle_score (Eq.1); `speed` = ||v|| precomputed, `dist` returned
-__device__ __forceinline__ double angle_score(double ux, double uy, double vx, double vy, double speed, double tx,
-                                              double ty, double &dist) {
+// envs/mechanics.py:11-57 calc_angle_score (Eq.1) with the UAV's unit heading (wx,wy) precomputed.
+// cos(sigma) is formed as (d . w)/|d| (one division) instead of (d/|d|) . w: <= 2 ulp apart.
+__device__ __forceinline__ double angle_score(double ux, double uy, double wx, double wy, double tx, double ty,
+                                              double &dist) {
     const double dx = tx - ux, dy = ty - uy;
     dist = sqrt(dx * dx + dy * dy);
     if (dist < 1e-6) return 1.0;                                   // :23
-    const double nx = dx / dist, ny = dy / dist;                   // :28
-    double wx = 1.0, wy = 0.0;                                     // :32-34
-    if (!(speed < 1e-6)) { wx = vx / speed; wy = vy / speed; }     // :36
-    double c = nx * wx + ny * wy;                                  // :39
+    double c = (dx * wx + dy * wy) / dist;                         // :28-39
     c = c < -1.0 ? -1.0 : (c > 1.0 ? 1.0 : c);
     const double sigma = acos(c);                                  // :40
     double b = 0.002 * dist;                                       // :44
@@ -129,51 +162,57 @@ __device__ __forceinline__ double angle_score(double ux, double uy, double vx, d
     return exp(-(q * q));                                          // :55-56
 }
 
-// envs/mechanics.py:61-68 calc_speed_score (Eq.2)
-__device__ __forceinline__ double speed_score(double kparam, double uav_speed, double tgt_speed) {
-    if (uav_speed < 1e-6) return 0.0;
-    return clip01(1.0 - (kparam * tgt_speed / uav_speed));
+// envs/mechanics.py:61-68 calc_speed_score (Eq.2); inv_speed < 0 encodes uav_speed < 1e-6
+__device__ __forceinline__ double speed_score(double kparam, double inv_speed, double tgt_speed) {
+    if (inv_speed < 0.0) return 0.0;
+    return clip01(1.0 - (kparam * tgt_speed * inv_speed));
 }
 
 // envs/mechanics.py:72-89 calc_dist_score (Eq.3), D_mid = 0
-__device__ __forceinline__ double dist_score(double dist, double zeta) {
-    const double q = (dist - 0.0) / zeta;
+__device__ __forceinline__ double dist_score(double dist, double inv_zeta) {
+    const double q = dist * inv_zeta;
     return exp(-(q * q));
 }
 
 // envs/mechanics.py:93-114 calc_damage_prob (Eq.4)
-__device__ __forceinline__ double damage_prob(const Params &P, double ux, double uy, double vx, double vy,
-                                              double speed, double load, double tx, double ty, double tspeed) {
+__device__ __forceinline__ double damage_prob(const Params &P, const UavRec &u, double tx, double ty, double tspeed) {
     double dist;
-    const double e_angle = angle_score(ux, uy, vx, vy, speed, tx, ty, dist);
-    const double e_dist = dist_score(dist, P.zeta_d);
-    const double e_speed = speed_score(P.k, speed, tspeed);
+    const double e_angle = angle_score(u.x, u.y, u.wx, u.wy, tx, ty, dist);
+    const double e_dist = dist_score(dist, P.inv_zeta_d);
+    const double e_speed = speed_score(P.k, u.inv_speed, tspeed);
     const double term = P.c1 * e_dist + P.c2 * e_speed;            // :111
-    return clip01(e_angle * term * load);                          // :112-114
+    return clip01(e_angle * term * u.load);                        // :112-114
 }
 
 // envs/mechanics.py:118-163 calc_penetration_prob (Eq.5-6): depends on the UAV only
-__device__ __forceinline__ double penetration_prob(const Params &P, int b, double ux, double uy, double vx,
-                                                   double vy, double speed) {
+__device__ __forceinline__ double penetration_prob(const Params &P, int b, const UavRec &u) {
     double p = 1.0;
     const NfzRec *Z = P.nfz + (size_t)b * P.K1;
     for (int i = 0; i < P.K1; ++i) {                               // :130-141
         double dist;
-        const double ea = angle_score(ux, uy, vx, vy, speed, Z[i].x, Z[i].y, dist);
-        const double ed = dist_score(dist, 10.0);
+        const double ea = angle_score(u.x, u.y, u.wx, u.wy, Z[i].x, Z[i].y, dist);
+        const double qd = dist / 10.0, ed = exp(-(qd * qd));       // zeta = 10 for obstacles (:78)
         p *= clip01((1.0 - ea) * (1.0 - ed));
     }
     const IntRec *I = P.intc + (size_t)b * P.K2;
     for (int i = 0; i < P.K2; ++i) {                               // :144-161
         double dist;
-        const double ea = angle_score(ux, uy, vx, vy, speed, I[i].x, I[i].y, dist);
-        const double ed = dist_score(dist, 10.0);
+        const double ea = angle_score(u.x, u.y, u.wx, u.wy, I[i].x, I[i].y, dist);
+        const double qd = dist / 10.0, ed = exp(-(qd * qd));
         const double ispeed = sqrt(I[i].vx * I[i].vx + I[i].vy * I[i].vy);
-        const double es = speed_score(P.k, speed, ispeed);
+        const double es = speed_score(P.k, u.inv_speed, ispeed);
         const double term = P.c3 * (1.0 - ed) + P.c4 * es;
         p *= clip01((1.0 - ea) * term);
     }
     return p;
+}
+
+// derived fields of a UAV record from its velocity (obstacles of env b must be visible for p_pen)
+__device__ __forceinline__ void finish_uav(const Params &P, int b, UavRec &u, double vx, double vy) {
+    const double speed = sqrt(vx * vx + vy * vy);
+    if (speed < 1e-6) { u.wx = 1.0; u.wy = 0.0; u.inv_speed = -1.0; }
+    else { u.wx = vx / speed; u.wy = vy / speed; u.inv_speed = 1.0 / speed; }
+    u.p_pen = penetration_prob(P, b, u);
 }
 
 // envs/mechanics.py:185-241 get_state_vector (Eq.15): fp64 features, cast to f32, then the power-of-two

@@ -33,17 +33,14 @@ struct StepIO {
 };
 
 // ------------------------------------------------------------------------------------------------
-// block-cooperative helpers (all threads of the CTA must call)
+// warp-cooperative helpers (all 32 lanes of the warp must call).  A finished env is restarted by the
+// warp that owns it, so the step kernel needs no CTA-wide barrier on its hot path.
 
-__device__ __forceinline__ double block_sum(double v, double *s_red) {
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) s_red[w] = v;
-    __syncthreads();
-    double t = 0.0;
-    for (int i = 0; i < nw; ++i) t += s_red[i];
-    return t;
+constexpr unsigned kFullMask = 0xffffffffu;
+
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+    return v;
 }
 
 // position of element i in a sort of keys[0..n) by (key, index): a uniformly random permutation
@@ -58,31 +55,25 @@ __device__ __forceinline__ int rank_of(const uint32_t *keys, int n, int i) {
 }
 
 // _reset_state_only (envs/uav_env.py:175-182) for env b: every UAV available again, every lock list empty
-__device__ __forceinline__ void block_clear_allocation(const Params &P, int b) {
+__device__ __forceinline__ void warp_clear_allocation(const Params &P, int b, int lane) {
     int32_t *asg = P.assigned + (size_t)b * P.N;
-    for (int i = threadIdx.x; i < P.N; i += blockDim.x) asg[i] = -1;
+    for (int i = lane; i < P.N; i += 32) asg[i] = -1;
     TgtRec *T = P.tgt + (size_t)b * P.M;
-    for (int j = threadIdx.x; j < P.M; j += blockDim.x) {
+    for (int j = lane; j < P.M; j += 32) {
         T[j].nh = 1.0; T[j].nh_pure = 1.0; T[j].lock_cost = 0.0; T[j].lock_cnt = 0;
     }
 }
 
-// per-scene derived values of one UAV: speed and p_pen (obstacles of env b must be visible)
-__device__ __forceinline__ void finish_uav(const Params &P, int b, UavRec &u) {
-    u.speed = sqrt(u.vx * u.vx + u.vy * u.vy);
-    u.p_pen = penetration_prob(P, b, u.x, u.y, u.vx, u.vy, u.speed);
-}
-
 // _generate_scene (envs/uav_env.py:65-173) for env b with the counter RNG; also clears the allocation.
-// s_keys: >= max(N,M) uint32, s_vals: >= M doubles, s_red: >= 32 doubles.
-__device__ void block_generate_scene(const Params &P, int b, uint32_t scene, uint32_t *s_keys, double *s_vals,
-                                     double *s_red) {
-    const int tid = threadIdx.x, nt = blockDim.x;
+// s_keys: >= max(N,M) uint32, s_vals: >= M doubles (per-warp scratch).
+__device__ __noinline__ void warp_generate_scene(const Params &P, int b, uint32_t scene, uint32_t *s_keys,
+                                                 double *s_vals) {
+    const int lane = threadIdx.x & 31;
     const uint32_t k0 = P.seed_lo, k1 = P.seed_hi, env = P.env_id_base + (uint32_t)b;
     const int N = P.N, M = P.M;
     // obstacles first: the per-UAV penetration probability needs them   (uav_env.py:146-170)
     NfzRec *Z = P.nfz + (size_t)b * P.K1;
-    for (int i = tid; i < P.K1; i += nt) {
+    for (int i = lane; i < P.K1; i += 32) {
         const uint4 a = philox4x32(k0, k1, i, S_NFZ_A, scene, env);
         const uint4 c = philox4x32(k0, k1, i, S_NFZ_B, scene, env);
         Z[i].radius = 5.0 + (10.0 - 5.0) * u53(a.x, a.y);
@@ -90,7 +81,7 @@ __device__ void block_generate_scene(const Params &P, int b, uint32_t scene, uin
         Z[i].y = 0.0 + (P.map_h - 0.0) * u53(c.x, c.y);
     }
     IntRec *I = P.intc + (size_t)b * P.K2;
-    for (int i = tid; i < P.K2; i += nt) {
+    for (int i = lane; i < P.K2; i += 32) {
         const uint4 a = philox4x32(k0, k1, i, S_INT_A, scene, env);
         const uint4 c = philox4x32(k0, k1, i, S_INT_B, scene, env);
         I[i].x = 140.0 + (160.0 - 140.0) * u53(a.x, a.y);
@@ -101,14 +92,15 @@ __device__ void block_generate_scene(const Params &P, int b, uint32_t scene, uin
         I[i].vy = sin(ang) * sp;
     }
     // 1. UAV types: N//4 of type 2, uniformly permuted   (uav_env.py:81-84)
-    for (int i = tid; i < N; i += nt) s_keys[i] = philox4x32(k0, k1, i, S_UAV_TYPE, scene, env).x;
-    __syncthreads();  // keys + obstacles visible
+    __syncwarp();
+    for (int i = lane; i < N; i += 32) s_keys[i] = philox4x32(k0, k1, i, S_UAV_TYPE, scene, env).x;
+    __syncwarp();  // keys + obstacles visible to the warp
     const int num_type1 = N - N / 4;
     UavRec *U = P.uav + (size_t)b * N;
     int32_t *asg = P.assigned + (size_t)b * N;
     int32_t *typ = P.uav_type + (size_t)b * N;
     double cost_part = 0.0;
-    for (int i = tid; i < N; i += nt) {
+    for (int i = lane; i < N; i += 32) {
         const int type = rank_of(s_keys, N, i) >= num_type1 ? 2 : 1;
         const uint4 a = philox4x32(k0, k1, i, S_UAV_POS, scene, env);
         const uint4 d = philox4x32(k0, k1, i, S_UAV_DYN, scene, env);
@@ -121,35 +113,37 @@ __device__ void block_generate_scene(const Params &P, int b, uint32_t scene, uin
         const double real_speed = base_speed * P.weather_speed;                   // :106
         u.load = base_load * P.weather_load;                                      // :107
         const double ang = (-15.0 + (15.0 - (-15.0)) * u53(d.z, d.w)) * (3.141592653589793 / 180.0);  // :110
-        u.vx = cos(ang) * real_speed;
-        u.vy = sin(ang) * real_speed;                                             // :111
-        finish_uav(P, b, u);
+        const double vx = cos(ang) * real_speed, vy = sin(ang) * real_speed;      // :111
+        finish_uav(P, b, u, vx, vy);
         U[i] = u;
+        P.uav_vel[(size_t)b * N + i] = make_double2(vx, vy);
         asg[i] = -1;
         typ[i] = type;
         cost_part += u.cost;
     }
-    const double total_cost = block_sum(cost_part, s_red);  // (contains __syncthreads: s_keys reusable)
+    const double total_cost = warp_sum(cost_part);
     // 2. target values   (uav_env.py:121-129)
     const int n1 = M / 2, n_remain = M - n1 - 1;
     int n2 = 0;
     if (n_remain >= 1) n2 = 1 + (int)(((uint64_t)philox4x32(k0, k1, 0u, S_N2, scene, env).x * (uint64_t)n_remain) >> 32);
-    for (int i = tid; i < M; i += nt) s_keys[i] = philox4x32(k0, k1, i, S_TGT_VAL, scene, env).x;
-    __syncthreads();
+    __syncwarp();
+    for (int i = lane; i < M; i += 32) s_keys[i] = philox4x32(k0, k1, i, S_TGT_VAL, scene, env).x;
+    __syncwarp();
     double val_part = 0.0;
-    for (int i = tid; i < M; i += nt) {
+    for (int i = lane; i < M; i += 32) {
         const int q = rank_of(s_keys, M, i);
         const double v = q < n1 ? 4.0 : (q < n1 + n2 ? 6.0 : (q < n1 + n_remain ? 8.0 : 16.0));
         s_vals[i] = v;
         val_part += v;
     }
-    const double total_val = block_sum(val_part, s_red);
+    const double total_val = warp_sum(val_part);
     // 3. list permutation (uav_env.py:173) + kinematics: target id i lands at list position rank_i
-    for (int i = tid; i < M; i += nt) s_keys[i] = philox4x32(k0, k1, i, S_TGT_LIST, scene, env).x;
-    __syncthreads();
+    __syncwarp();
+    for (int i = lane; i < M; i += 32) s_keys[i] = philox4x32(k0, k1, i, S_TGT_LIST, scene, env).x;
+    __syncwarp();
     TgtRec *T = P.tgt + (size_t)b * M;
     double2 *TV = P.tgt_vel + (size_t)b * M;
-    for (int i = tid; i < M; i += nt) {
+    for (int i = lane; i < M; i += 32) {
         const int pos = rank_of(s_keys, M, i);
         const uint4 a = philox4x32(k0, k1, i, S_TGT_POS, scene, env);
         const uint4 v = philox4x32(k0, k1, i, S_TGT_VEL, scene, env);
@@ -163,87 +157,153 @@ __device__ void block_generate_scene(const Params &P, int b, uint32_t scene, uin
         T[pos] = t;
         TV[pos] = make_double2(vx, vy);
     }
-    if (tid == 0) { P.hd.total_cost[b] = total_cost; P.hd.total_val[b] = total_val; }
-    __syncthreads();
+    if (lane == 0) { P.header(b).f(F_TOTAL_COST) = total_cost; P.header(b).f(F_TOTAL_VAL) = total_val; }
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------
 // thread-level pieces
 
-// calc_advantage of pointer pair (k,m) + its observation row (uav_env.py:184-242 -> mechanics.py:185-241)
-__device__ __forceinline__ void eval_pointer_pair(const Params &P, int b, int k, int m, double cost_sum,
+// calc_advantage of the pointer pair + its observation row (uav_env.py:184-242 -> mechanics.py:185-241)
+// from the two gathered records and the running aggregates.
+__device__ __forceinline__ void eval_pointer_pair(const Params &P, const UavRec &u, const TgtRec &t, double cost_sum,
                                                   double covered_val, double total_cost, double total_val,
                                                   double &pf, double &pd, float *row) {
-    const UavRec u = P.uav[(size_t)b * P.N + k];
-    const TgtRec t = P.tgt[(size_t)b * P.M + m];
-    pd = damage_prob(P, u.x, u.y, u.vx, u.vy, u.speed, u.load, t.x, t.y, t.speed);
+    pd = damage_prob(P, u, t.x, t.y, t.speed);
     pf = pd * u.p_pen;                                                  // mechanics.py:179
-    const double chi_c = cost_sum / (total_cost + 1e-6);                // uav_env.py:195-196
+    const double inv_tc = 1.0 / (total_cost + 1e-6);
+    const double chi_c = cost_sum * inv_tc;                             // uav_env.py:195-196
     const double chi_v = covered_val / (total_val + 1e-6);              // :198-200
-    const double chi_mc = t.lock_cost / (total_cost + 1e-6);            // :202-206
+    const double chi_mc = t.lock_cost * inv_tc;                         // :202-206
     const double P_prev = 1.0 - t.nh, P_pure = 1.0 - t.nh_pure;         // :226-227
     state_vector(u.cost, t.value, chi_c, chi_v, chi_mc, pf, pd, P_prev, P_prev * t.value, P_pure, row);
 }
 
-// ------------------------------------------------------------------------------------------------
-// The fused step.  Thread t of a CTA owns env b = blockIdx.x*128 + t for the O(1) state machine;
-// finished envs are restarted by the whole CTA; the [5,14] windows leave through per-warp shared
-// memory tiles so the 280 B/env rows are written with coalesced 16 B stores.
+// capture the new current pair in the header (the next step's accept rule reads only these)
+__device__ __forceinline__ void store_current_pair(const Hdr &h, const UavRec &u, const TgtRec &t, double pf, double pd) {
+    h.f(F_CUR_PF) = pf; h.f(F_CUR_PD) = pd; h.f(F_CUR_VALUE) = t.value; h.f(F_CUR_NH) = t.nh; h.f(F_CUR_NHP) = t.nh_pure;
+    h.f(F_CUR_LOCK_COST) = t.lock_cost; h.f(F_CUR_UCOST) = u.cost; h.n(I_CUR_LOCK_CNT) = t.lock_cnt; h.n(I_CUR_TID) = t.id;
+}
 
-__global__ void __launch_bounds__(kStepThreads) step_kernel(const __grid_constant__ Params P, const StepIO io) {
+// ---- async copy / TMA helpers (sm_100a) --------------------------------------------------------------
+__device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gmem_src) {   // LDGSTS, 8 bytes
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+// TMA bulk store shared::cta -> global (UBLKCP): bytes % 16 == 0, both addresses 16 B aligned
+__device__ __forceinline__ void bulk_store(void *gmem_dst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gmem_dst),
+                 "r"((uint32_t)__cvta_generic_to_shared(smem_src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+// wait until the bulk stores of this thread have READ their shared-memory source (the CTA may then exit)
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// The fused step.  Thread t of a CTA owns env b = blockIdx.x*128 + t for the O(1) state machine.
+// Memory-level parallelism is what bounds this kernel (every env touches ~1 KB scattered over a few
+// hundred MB), so the dependent chain is kept to TWO round trips and there is no CTA-wide barrier:
+//   trip 1  scalar state (SoA, coalesced) + action + ring head; the four older window rows start
+//           streaming into the warp's shared-memory tile with cp.async (LDGSTS) as soon as the head is known
+//   trip 2  the two 64 B records of the NEW pointer pair - the accept rule itself needs no gather because the
+//           current pair's values were captured in the header when its observation row was computed
+// The [5,14] windows of a warp (32 x 280 B, contiguous in obs) leave through one TMA bulk store.
+// A finished env is restarted by its own warp, out of line (warp_restart), in a second pass of the
+// evaluation loop so that nothing but a few scalars is live across that call.
+
+__device__ __noinline__ void warp_restart(const Params &P, unsigned done_mask, int b0, uint32_t *s_keys, double *s_vals) {
+    const int lane = threadIdx.x & 31;
+    while (done_mask) {                     // main_train.py:79 schedule, one finished env at a time
+        const int src = __ffs(done_mask) - 1;
+        done_mask &= done_mask - 1;
+        const int eb = b0 + src;
+        const int episode = P.header(eb).n(I_EPISODE) + 1;
+        const bool full = P.reset_episodes > 0 && (episode % P.reset_episodes) == 0;
+        __syncwarp();
+        if (full) {
+            const int scene = P.header(eb).n(I_SCENE);
+            warp_generate_scene(P, eb, (uint32_t)scene, s_keys, s_vals);
+            if (lane == 0) P.header(eb).n(I_SCENE) = scene + 1;
+        } else {
+            warp_clear_allocation(P, eb, lane);
+        }
+        if (lane == 0) P.header(eb).n(I_EPISODE) = episode;
+        __syncwarp();
+    }
+    __threadfence_block();
+}
+
+__global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_constant__ Params P, const StepIO io) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
-    __shared__ __align__(16) float s_tile[kWarpsPerCta][32 * kObsFloats];
-    __shared__ int32_t s_done_env[kStepThreads];
-    __shared__ int32_t s_done_cnt;
-    double *s_red = reinterpret_cast<double *>(s_dyn);                 // 32 doubles
-    double *s_vals = s_red + 32;                                       // M doubles
-    uint32_t *s_keys = reinterpret_cast<uint32_t *>(s_vals + P.M);     // max(N,M) uint32
+    __shared__ __align__(128) float s_tile[kWarpsPerCta][32 * kObsFloats];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.x * kStepThreads + tid;
+    const int b0 = blockIdx.x * kStepThreads + warp * 32;   // first env of this warp
+    const int b = b0 + lane;
     const bool live = b < P.B;
+    const int bc = live ? b : P.B - 1;  // clamped index: idle tail lanes issue harmless loads
     const int N = P.N, M = P.M;
-    const uint32_t head_new = (P.step_ctr[0] + 1u) % (uint32_t)kSeqLen;  // ring slot of this step's row
-    if (tid == 0) s_done_cnt = 0;
-    __syncthreads();
+    const Hdr H = P.header(bc);
+    float *tile = s_tile[warp] + lane * kObsFloats;
 
-    // ---- phase A: action -> accept rule -> state update -> reward / done / info --------------------
-    int k = 0, m = 0, nA = 0, n0 = 0, age = 0;
-    double rev = 0, cost_sum = 0, covered_val = 0, sum_pd = 0, sum_pf = 0, total_val = 0, total_cost = 0;
-    bool was_finished = false, done = false, restarted = false;
+    // ---- trip 1: everything that depends on b only -------------------------------------------------
+    const uint32_t head_old = P.step_ctr[0];
+    const uint32_t head_new = (head_old + 1u) % (uint32_t)kSeqLen;       // ring slot of this step's row
+    if (tid == 0) {
+        // arrive; the last CTA to have READ the head publishes the new one (kept on the device so that
+        // CUDA-graph replays stay correct).  The increment depends on head_old, so the read is ordered first.
+        if (atomicAdd(&P.step_ctr[1], 1u + (head_old >> 31)) == gridDim.x - 1) {
+            P.step_ctr[1] = 0u;
+            P.step_ctr[0] = head_new;
+        }
+    }
+    int k = H.n(I_K), m = H.n(I_M), nA = H.n(I_NASSIGNED), n0 = H.n(I_NCOVERED), age = H.n(I_AGE);
+    double rev = H.f(F_REV), cost_sum = H.f(F_COST_SUM), covered_val = H.f(F_COVERED_VAL);
+    double sum_pd = H.f(F_SUM_PD), sum_pf = H.f(F_SUM_PF);
+    double total_val = H.f(F_TOTAL_VAL), total_cost = H.f(F_TOTAL_COST);
+    const double c_pf = H.f(F_CUR_PF), c_pd = H.f(F_CUR_PD), c_value = H.f(F_CUR_VALUE), c_nh = H.f(F_CUR_NH);
+    const double c_nhp = H.f(F_CUR_NHP), c_lock_cost = H.f(F_CUR_LOCK_COST), c_ucost = H.f(F_CUR_UCOST);
+    const int c_lock_cnt = H.n(I_CUR_LOCK_CNT), c_tid = H.n(I_CUR_TID);
+    const bool was_finished = !P.auto_reset && H.n(I_FINISHED);
+    const int64_t action = io.actions[bc];
+    // older rows of the window: ring tile [slot][feature pair][32 lanes] -> tile rows 0..3 (time order)
+    float2 *const ring = P.ring(bc);
+#pragma unroll
+    for (int a = kSeqLen - 1; a >= 1; --a) {
+        const uint32_t slot = (head_new + (uint32_t)(kSeqLen - a)) % (uint32_t)kSeqLen;
+        const float2 *src = ring + slot * (kStateDim / 2) * 32;
+        float *dst = tile + (kSeqLen - 1 - a) * kStateDim;
+#pragma unroll
+        for (int f = 0; f < kStateDim / 2; ++f) cp_async_8(dst + 2 * f, src + f * 32);
+    }
+
+    // ---- accept rule -> state update -> reward / done / info (uav_env.py:295-363, :426-433) ----------
+    bool done = false, restarted = false;
     if (live) {
-        k = P.hd.k[b]; m = P.hd.m[b]; nA = P.hd.n_assigned[b]; n0 = P.hd.n_covered[b]; age = P.hd.age[b];
-        rev = P.hd.rev[b]; cost_sum = P.hd.cost_sum[b]; covered_val = P.hd.covered_val[b];
-        sum_pd = P.hd.sum_pd[b]; sum_pf = P.hd.sum_pf[b];
-        total_val = P.hd.total_val[b]; total_cost = P.hd.total_cost[b];
-        was_finished = !P.auto_reset && P.hd.finished[b];
-        const int64_t action = io.actions[b];
         double reward = 0.0;
         if (!was_finished) {
-            const double prev_r = paper_reward(rev - (P.omega * cost_sum), n0, M);      // uav_env.py:301
+            const double prev_r = paper_reward(rev - (P.omega * cost_sum), n0, M);      // :301
             double cur_r = prev_r;
             bool advance_uav = false;
             if (action == 1) {                                                           // :306
-                const double pf = P.hd.cur_pf[b], pd = P.hd.cur_pd[b];
-                TgtRec *tp = P.tgt + (size_t)b * M + m;
-                const double value = tp->value, nh = tp->nh, nh_pure = tp->nh_pure, lock_cost = tp->lock_cost;
-                const int lock_cnt = tp->lock_cnt;
-                const double ucost = P.uav[(size_t)b * N + k].cost;
                 // tentative X' (:308-310): only target m's product, the cost sum and N0 change
-                const double nh2 = nh * (1.0 - pf);
-                const double rev2 = rev + ((1.0 - nh2) - (1.0 - nh)) * value;
-                const double cost2 = cost_sum + ucost;
-                const int n02 = n0 + (lock_cnt == 0);
+                const double nh2 = c_nh * (1.0 - c_pf);
+                const double rev2 = rev + ((1.0 - nh2) - (1.0 - c_nh)) * c_value;
+                const double cost2 = cost_sum + c_ucost;
+                const int n02 = n0 + (c_lock_cnt == 0);
                 const double new_r = paper_reward(rev2 - (P.omega * cost2), n02, M);    // :313
                 if (new_r >= prev_r) {                                                   // :317 (Eq.21)
                     reward = new_r - prev_r;                                             // :321
                     cur_r = new_r;
-                    tp->nh = nh2; tp->nh_pure = nh_pure * (1.0 - pd);
-                    tp->lock_cost = lock_cost + ucost; tp->lock_cnt = lock_cnt + 1;
-                    P.assigned[(size_t)b * N + k] = tp->id;                              // :308
+                    TgtRec *tp = P.tgt + (size_t)b * M + m;
+                    tp->nh = nh2; tp->nh_pure = c_nhp * (1.0 - c_pd);
+                    tp->lock_cost = c_lock_cost + c_ucost; tp->lock_cnt = c_lock_cnt + 1;
+                    P.assigned[(size_t)b * N + k] = c_tid;                               // :308
                     rev = rev2; cost_sum = cost2;
-                    if (lock_cnt == 0) { covered_val += value; n0 = n02; }
-                    sum_pd += pd; sum_pf += pf; nA += 1;
+                    if (c_lock_cnt == 0) { covered_val += c_value; n0 = n02; }
+                    sum_pd += c_pd; sum_pf += c_pf; nA += 1;
                     advance_uav = true;                                                  // :324-325
                 }
             }
@@ -264,161 +324,135 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const __grid_constan
         if (io.avg_p_dmg) io.avg_p_dmg[b] = nA > 0 ? (float)(sum_pd / nA) : 0.0f;        // :409
         if (io.avg_p_final) io.avg_p_final[b] = nA > 0 ? (float)(sum_pf / nA) : 0.0f;    // :416
         if (done && !was_finished) {
-            if (P.auto_reset) {
-                restarted = true;
-                s_done_env[atomicAdd(&s_done_cnt, 1)] = tid;
-            } else {
-                P.hd.finished[b] = 1;
+            if (P.auto_reset) restarted = true;
+            else H.n(I_FINISHED) = 1;
+        }
+    }
+    const bool inert = live && done && !restarted;  // finished, no auto-reset: zero window, frozen state
+
+    // ---- trip 2 + evaluation.  pass 0: envs that go on; pass 1 (rare): envs restarted by this warp ----
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1) {
+            const unsigned done_mask = __ballot_sync(kFullMask, restarted);
+            if (done_mask == 0u) break;
+            double *s_vals = reinterpret_cast<double *>(s_dyn) + (size_t)warp * M;
+            uint32_t *s_keys = reinterpret_cast<uint32_t *>(reinterpret_cast<double *>(s_dyn) + (size_t)kWarpsPerCta * M) +
+                               (size_t)warp * max(N, M);
+            warp_restart(P, done_mask, b0, s_keys, s_vals);
+            if (restarted) {
+                k = 0; m = 0; nA = 0; n0 = 0; age = 0;
+                rev = 0.0; cost_sum = 0.0; covered_val = 0.0; sum_pd = 0.0; sum_pf = 0.0;
+                total_val = H.f(F_TOTAL_VAL); total_cost = H.f(F_TOTAL_COST);
             }
         }
-    }
-    __syncthreads();
-
-    // ---- phase B: the CTA restarts its finished envs (main_train.py:79 schedule) -------------------
-    const int ndone = s_done_cnt;
-    for (int q = 0; q < ndone; ++q) {
-        const int eb = blockIdx.x * kStepThreads + s_done_env[q];
-        const int episode = P.hd.episode[eb] + 1;
-        const bool full = P.reset_episodes > 0 && (episode % P.reset_episodes) == 0;
-        if (full) {
-            const int scene = P.hd.scene_idx[eb];
-            block_generate_scene(P, eb, (uint32_t)scene, s_keys, s_vals, s_red);
-            if (tid == 0) P.hd.scene_idx[eb] = scene + 1;
-        } else {
-            block_clear_allocation(P, eb);
-        }
-        __syncthreads();
-        if (tid == 0) P.hd.episode[eb] = episode;
-    }
-    if (ndone > 0) __syncthreads();
-
-    // ---- phase C: pair score + observation row of the new pointer pair, window out -----------------
-    float *tile = s_tile[warp] + lane * kObsFloats;
-    if (live) {
-        const bool inert = done && !restarted;  // finished, no auto-reset: zero window
-        if (restarted) {
-            k = 0; m = 0; nA = 0; n0 = 0; age = 0;
-            rev = 0.0; cost_sum = 0.0; covered_val = 0.0; sum_pd = 0.0; sum_pf = 0.0;
-            total_val = P.hd.total_val[b]; total_cost = P.hd.total_cost[b];
-        }
-        const int nprev = inert ? 0 : (age < kSeqLen - 1 ? age : kSeqLen - 1);
-        // rows of the previous steps from the ring ([slot][feature pair][B], coalesced)
+        if (live && (pass == 0 ? !done : restarted)) {
+            const UavRec u = P.uav[(size_t)b * N + k];
+            const TgtRec t = P.tgt[(size_t)b * M + m];  // sees this thread's own accept store when it hits target m
+            cp_async_wait_all();                        // ring rows have landed in the tile (gathers still in flight)
+            const int nprev = age < kSeqLen - 1 ? age : kSeqLen - 1;
 #pragma unroll
-        for (int a = kSeqLen - 1; a >= 1; --a) {
-            float *dst = tile + (kSeqLen - 1 - a) * kStateDim;
-            if (a <= nprev) {
-                const uint32_t slot = (head_new + (uint32_t)(kSeqLen - a)) % (uint32_t)kSeqLen;
-                const float2 *src = P.hist + (size_t)slot * (kStateDim / 2) * P.B + b;
+            for (int a = kSeqLen - 1; a >= 1; --a) {     // rows older than the episode are zero (uav_env.py:58-61)
+                if (a > nprev) {
+                    float *dst = tile + (kSeqLen - 1 - a) * kStateDim;
 #pragma unroll
-                for (int f = 0; f < kStateDim / 2; ++f) {
-                    const float2 v = __ldg(src + (size_t)f * P.B);
-                    dst[2 * f] = v.x; dst[2 * f + 1] = v.y;
+                    for (int f = 0; f < kStateDim; f += 2) *reinterpret_cast<float2 *>(dst + f) = make_float2(0.f, 0.f);
                 }
-            } else {
-#pragma unroll
-                for (int f = 0; f < kStateDim; ++f) dst[f] = 0.0f;
             }
-        }
-        float row[kStateDim];
-        if (!inert) {
             double pf, pd;
-            eval_pointer_pair(P, b, k, m, cost_sum, covered_val, total_cost, total_val, pf, pd, row);
-            P.hd.cur_pf[b] = pf; P.hd.cur_pd[b] = pd;
-            float2 *dsth = P.hist + (size_t)head_new * (kStateDim / 2) * P.B + b;
+            float row[kStateDim];
+            eval_pointer_pair(P, u, t, cost_sum, covered_val, total_cost, total_val, pf, pd, row);
+            store_current_pair(H, u, t, pf, pd);
+            float2 *dsth = ring + head_new * (kStateDim / 2) * 32;
 #pragma unroll
-            for (int f = 0; f < kStateDim / 2; ++f) dsth[(size_t)f * P.B] = make_float2(row[2 * f], row[2 * f + 1]);
-            age = nprev + 1;
-        } else {
-#pragma unroll
-            for (int f = 0; f < kStateDim; ++f) row[f] = 0.0f;
-            age = 0;
-        }
-#pragma unroll
-        for (int f = 0; f < kStateDim; ++f) tile[(kSeqLen - 1) * kStateDim + f] = row[f];
-        if (!was_finished) {
-            P.hd.k[b] = k; P.hd.m[b] = m; P.hd.n_assigned[b] = nA; P.hd.n_covered[b] = n0; P.hd.age[b] = age;
-            P.hd.rev[b] = rev; P.hd.cost_sum[b] = cost_sum; P.hd.covered_val[b] = covered_val;
-            P.hd.sum_pd[b] = sum_pd; P.hd.sum_pf[b] = sum_pf;
+            for (int f = 0; f < kStateDim / 2; ++f) {
+                const float2 v = make_float2(row[2 * f], row[2 * f + 1]);
+                dsth[f * 32] = v;
+                *reinterpret_cast<float2 *>(tile + (kSeqLen - 1) * kStateDim + 2 * f) = v;
+            }
+            H.n(I_K) = k; H.n(I_M) = m; H.n(I_NASSIGNED) = nA; H.n(I_NCOVERED) = n0; H.n(I_AGE) = nprev + 1;
+            H.f(F_REV) = rev; H.f(F_COST_SUM) = cost_sum; H.f(F_COVERED_VAL) = covered_val;
+            H.f(F_SUM_PD) = sum_pd; H.f(F_SUM_PF) = sum_pf;
         }
     }
+    cp_async_wait_all();
+    if (inert) {
+#pragma unroll
+        for (int f = 0; f < kObsFloats; f += 2) *reinterpret_cast<float2 *>(tile + f) = make_float2(0.f, 0.f);
+        if (!was_finished) {  // the step that finished the episode: freeze the final pointers
+            H.n(I_K) = k; H.n(I_M) = m; H.n(I_NASSIGNED) = nA; H.n(I_NCOVERED) = n0; H.n(I_AGE) = 0;
+            H.f(F_REV) = rev; H.f(F_COST_SUM) = cost_sum; H.f(F_COVERED_VAL) = covered_val;
+            H.f(F_SUM_PD) = sum_pd; H.f(F_SUM_PF) = sum_pf;
+        }
+    }
+    // ---- window out: one TMA bulk store per warp (32 x 280 B contiguous in obs) ------------------------
+    fence_proxy_async_smem();
     __syncwarp();
-    // coalesced write-out of the warp's 32 windows (contiguous 32*280 B in obs)
     {
-        const int b0 = blockIdx.x * kStepThreads + warp * 32;
         const int nenv = min(32, P.B - b0);
         if (nenv > 0) {
             float *dst = io.obs + (size_t)b0 * kObsFloats;
             const float *src = s_tile[warp];
-            const int nfl = nenv * kObsFloats;
-            if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
-                const int nv = nfl >> 2;  // kObsFloats*4 = 280 B is a multiple of 8, 32 envs of 16
-                for (int i = lane; i < nv; i += 32)
-                    reinterpret_cast<float4 *>(dst)[i] = reinterpret_cast<const float4 *>(src)[i];
-                for (int i = (nv << 2) + lane; i < nfl; i += 32) dst[i] = src[i];
-            } else {
-                for (int i = lane; i < nfl; i += 32) dst[i] = src[i];
+            const uint32_t bytes = (uint32_t)nenv * kObsFloats * sizeof(float);
+            if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0 && (bytes & 15u) == 0) {
+                if (lane == 0) { bulk_store(dst, src, bytes); bulk_store_wait_read(); }
+            } else {  // ragged tail / unaligned caller buffer
+                for (int i = lane; i < nenv * kObsFloats; i += 32) dst[i] = src[i];
             }
-        }
-    }
-    // the last CTA to finish advances the ring head (kept on the device so graph replays stay correct)
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        if (atomicAdd(&P.step_ctr[1], 1u) == gridDim.x - 1) {
-            P.step_ctr[1] = 0u;
-            P.step_ctr[0] = head_new;  // stored modulo kSeqLen
-            __threadfence();
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// UAVEnv.reset (envs/uav_env.py:42-63) for the masked envs: one CTA per env.
+// UAVEnv.reset (envs/uav_env.py:42-63) for the masked envs: one warp per env.
 // mode: 0 = state only, 1 = generate a new scene, 2 = scene already packed (load_scene)
 
 __global__ void __launch_bounds__(kResetThreads) reset_kernel(const __grid_constant__ Params P, int mode,
                                                                const uint8_t *mask, int first_env, int count,
                                                                float *obs) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
-    double *s_red = reinterpret_cast<double *>(s_dyn);
-    double *s_vals = s_red + 32;
-    uint32_t *s_keys = reinterpret_cast<uint32_t *>(s_vals + P.M);
-    __shared__ float s_row[kStateDim];
-    const int tid = threadIdx.x;
-    for (int e = blockIdx.x; e < count; e += gridDim.x) {
+    __shared__ float s_row[kResetThreads / 32][kStateDim];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    double *s_vals = reinterpret_cast<double *>(s_dyn) + (size_t)warp * P.M;
+    uint32_t *s_keys = reinterpret_cast<uint32_t *>(reinterpret_cast<double *>(s_dyn) + (size_t)wpb * P.M) +
+                       (size_t)warp * max(P.N, P.M);
+    for (int e = blockIdx.x * wpb + warp; e < count; e += gridDim.x * wpb) {
         const int b = first_env + e;
-        if (mask && !mask[b]) continue;  // uniform across the CTA
+        if (mask && !mask[b]) continue;  // uniform across the warp
         if (mode == 1) {
-            const int scene = P.hd.scene_idx[b];
-            __syncthreads();
-            block_generate_scene(P, b, (uint32_t)scene, s_keys, s_vals, s_red);
-            if (tid == 0) P.hd.scene_idx[b] = scene + 1;
+            const int scene = P.header(b).n(I_SCENE);
+            __syncwarp();
+            warp_generate_scene(P, b, (uint32_t)scene, s_keys, s_vals);
+            if (lane == 0) P.header(b).n(I_SCENE) = scene + 1;
         } else {
-            block_clear_allocation(P, b);
+            warp_clear_allocation(P, b, lane);
         }
-        __syncthreads();
-        if (tid == 0) {
-            const double total_cost = P.hd.total_cost[b], total_val = P.hd.total_val[b];
+        __syncwarp();
+        if (lane == 0) {
+            const double total_cost = P.header(b).f(F_TOTAL_COST), total_val = P.header(b).f(F_TOTAL_VAL);
             double pf, pd;
             float row[kStateDim];
-            eval_pointer_pair(P, b, 0, 0, 0.0, 0.0, total_cost, total_val, pf, pd, row);
-            P.hd.k[b] = 0; P.hd.m[b] = 0; P.hd.n_assigned[b] = 0; P.hd.n_covered[b] = 0; P.hd.age[b] = 1;
-            P.hd.rev[b] = 0.0; P.hd.cost_sum[b] = 0.0; P.hd.covered_val[b] = 0.0;
-            P.hd.sum_pd[b] = 0.0; P.hd.sum_pf[b] = 0.0; P.hd.cur_pf[b] = pf; P.hd.cur_pd[b] = pd;
-            P.hd.finished[b] = 0;
-            P.hd.episode[b] = (mode == 0) ? P.hd.episode[b] + 1 : 1;
+            const UavRec u = P.uav[(size_t)b * P.N];
+            const TgtRec t = P.tgt[(size_t)b * P.M];
+            eval_pointer_pair(P, u, t, 0.0, 0.0, total_cost, total_val, pf, pd, row);
+            store_current_pair(P.header(b), u, t, pf, pd);
+            P.header(b).n(I_K) = 0; P.header(b).n(I_M) = 0; P.header(b).n(I_NASSIGNED) = 0; P.header(b).n(I_NCOVERED) = 0; P.header(b).n(I_AGE) = 1;
+            P.header(b).f(F_REV) = 0.0; P.header(b).f(F_COST_SUM) = 0.0; P.header(b).f(F_COVERED_VAL) = 0.0;
+            P.header(b).f(F_SUM_PD) = 0.0; P.header(b).f(F_SUM_PF) = 0.0;
+            P.header(b).n(I_FINISHED) = 0;
+            P.header(b).n(I_EPISODE) = (mode == 0) ? P.header(b).n(I_EPISODE) + 1 : 1;
             const uint32_t head = P.step_ctr[0] % (uint32_t)kSeqLen;
-            float2 *dsth = P.hist + (size_t)head * (kStateDim / 2) * P.B + b;
-            for (int f = 0; f < kStateDim / 2; ++f) dsth[(size_t)f * P.B] = make_float2(row[2 * f], row[2 * f + 1]);
-            for (int f = 0; f < kStateDim; ++f) s_row[f] = row[f];
+            float2 *dsth = P.ring(b) + head * (kStateDim / 2) * 32;
+            for (int f = 0; f < kStateDim / 2; ++f) dsth[f * 32] = make_float2(row[2 * f], row[2 * f + 1]);
+            for (int f = 0; f < kStateDim; ++f) s_row[warp][f] = row[f];
         }
-        __syncthreads();
+        __syncwarp();
         if (obs) {
             float *o = obs + (size_t)b * kObsFloats;
-            for (int i = tid; i < kObsFloats; i += blockDim.x)
-                o[i] = i < (kSeqLen - 1) * kStateDim ? 0.0f : s_row[i - (kSeqLen - 1) * kStateDim];
+            for (int i = lane; i < kObsFloats; i += 32)
+                o[i] = i < (kSeqLen - 1) * kStateDim ? 0.0f : s_row[warp][i - (kSeqLen - 1) * kStateDim];
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 
@@ -435,33 +469,33 @@ struct SceneSoA {
 
 __global__ void __launch_bounds__(kResetThreads) pack_scene_kernel(const __grid_constant__ Params P,
                                                                     const SceneSoA s, int first_env, int count) {
-    __shared__ double s_red[32];
-    const int tid = threadIdx.x, nt = blockDim.x;
-    for (int e = blockIdx.x; e < count; e += gridDim.x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    for (int e = blockIdx.x * wpb + warp; e < count; e += gridDim.x * wpb) {
         const int b = first_env + e;
-        for (int i = tid; i < P.K1; i += nt) {
+        for (int i = lane; i < P.K1; i += 32) {
             NfzRec z; z.x = s.nfz_x[(size_t)e * P.K1 + i]; z.y = s.nfz_y[(size_t)e * P.K1 + i];
             z.radius = s.nfz_radius ? s.nfz_radius[(size_t)e * P.K1 + i] : 0.0;
             P.nfz[(size_t)b * P.K1 + i] = z;
         }
-        for (int i = tid; i < P.K2; i += nt) {
+        for (int i = lane; i < P.K2; i += 32) {
             IntRec r; r.x = s.int_x[(size_t)e * P.K2 + i]; r.y = s.int_y[(size_t)e * P.K2 + i];
             r.vx = s.int_vx[(size_t)e * P.K2 + i]; r.vy = s.int_vy[(size_t)e * P.K2 + i];
             P.intc[(size_t)b * P.K2 + i] = r;
         }
-        __syncthreads();
+        __syncwarp();
         double cost_part = 0.0, val_part = 0.0;
-        for (int i = tid; i < P.N; i += nt) {
+        for (int i = lane; i < P.N; i += 32) {
             const size_t g = (size_t)e * P.N + i;
             UavRec u;
-            u.x = s.uav_x[g]; u.y = s.uav_y[g]; u.vx = s.uav_vx[g]; u.vy = s.uav_vy[g];
+            u.x = s.uav_x[g]; u.y = s.uav_y[g];
             u.load = s.uav_load[g]; u.cost = s.uav_cost[g];
-            finish_uav(P, b, u);
+            finish_uav(P, b, u, s.uav_vx[g], s.uav_vy[g]);
             P.uav[(size_t)b * P.N + i] = u;
+            P.uav_vel[(size_t)b * P.N + i] = make_double2(s.uav_vx[g], s.uav_vy[g]);
             P.uav_type[(size_t)b * P.N + i] = s.uav_type ? s.uav_type[g] : 1;
             cost_part += u.cost;
         }
-        for (int j = tid; j < P.M; j += nt) {
+        for (int j = lane; j < P.M; j += 32) {
             const size_t g = (size_t)e * P.M + j;
             TgtRec t;
             t.x = s.tgt_x[g]; t.y = s.tgt_y[g];
@@ -473,10 +507,10 @@ __global__ void __launch_bounds__(kResetThreads) pack_scene_kernel(const __grid_
             P.tgt_vel[(size_t)b * P.M + j] = make_double2(vx, vy);
             val_part += t.value;
         }
-        const double total_cost = block_sum(cost_part, s_red);
-        const double total_val = block_sum(val_part, s_red);
-        if (tid == 0) { P.hd.total_cost[b] = total_cost; P.hd.total_val[b] = total_val; }
-        __syncthreads();
+        const double total_cost = warp_sum(cost_part);
+        const double total_val = warp_sum(val_part);
+        if (lane == 0) { P.header(b).f(F_TOTAL_COST) = total_cost; P.header(b).f(F_TOTAL_VAL) = total_val; }
+        __syncwarp();
     }
 }
 
@@ -493,7 +527,7 @@ __global__ void __launch_bounds__(256) score_matrix_kernel(const __grid_constant
         const size_t b = bk / P.N;
         const UavRec u = P.uav[bk];
         const TgtRec *t = P.tgt + b * P.M + m;
-        const double pd = damage_prob(P, u.x, u.y, u.vx, u.vy, u.speed, u.load, t->x, t->y, t->speed);
+        const double pd = damage_prob(P, u, t->x, t->y, t->speed);
         if (p_damage) p_damage[idx] = (OutT)pd;
         if (p_final) p_final[idx] = (OutT)(pd * u.p_pen);
     }
@@ -529,10 +563,10 @@ __global__ void __launch_bounds__(256) recompute_kernel(const __grid_constant__ 
         }
         if (lane == 0) {
             const double J_fresh = rev - (P.omega * cost);
-            const double J_run = P.hd.rev[b] - (P.omega * P.hd.cost_sum[b]);
+            const double J_run = P.header(b).f(F_REV) - (P.omega * P.header(b).f(F_COST_SUM));
             worst = fmax(worst, fabs(J_fresh - J_run));
-            if (n0 != P.hd.n_covered[b]) worst = fmax(worst, 1e30);  // integer state must agree exactly
-            if (fix) { P.hd.rev[b] = rev; P.hd.cost_sum[b] = cost; P.hd.covered_val[b] = cval; }
+            if (n0 != P.header(b).n(I_NCOVERED)) worst = fmax(worst, 1e30);  // integer state must agree exactly
+            if (fix) { P.header(b).f(F_REV) = rev; P.header(b).f(F_COST_SUM) = cost; P.header(b).f(F_COVERED_VAL) = cval; }
         }
     }
     if (lane == 0 && max_abs_diff && worst > 0.0) {

@@ -229,6 +229,11 @@ class UAVEnvBatched:
         self._chk(self._lib.uavenv_get_state(self._h, C.byref(st), int(first_env), int(count)))
         return out
 
+    def set_episode_counters(self, episode, first_env=0):
+        """Restore the 1-based per-env episode counters behind the main_train.py:79 schedule."""
+        ep = np.ascontiguousarray(np.asarray(episode, dtype=np.int32).reshape(-1))
+        self._chk(self._lib.uavenv_set_episode_counters(self._h, C.c_void_p(ep.ctypes.data), int(first_env), ep.size))
+
     def scene(self, b):
         """(uavs, targets, nfz_list, interceptors) of env b as reference-style entity objects."""
         sc = {k: v[0] for k, v in self.get_scene(b, 1).items()}
