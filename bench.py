@@ -193,6 +193,8 @@ def main():
         env.random_actions(BURN_IN_STEPS + i, ACTION_SEED, out=pool[i])
     pool_host = pool.cpu().pin_memory()
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    sweep = torch.zeros(L2_FLUSH_BYTES // 4, dtype=torch.int32, device=dev)
+    sink = torch.zeros(1, dtype=torch.int64, device=dev)
     stream = torch.cuda.current_stream(dev)
 
     def timed(step_fn, n_warm, n_timed):
@@ -203,7 +205,9 @@ def main():
         torch.cuda.synchronize(dev)
         for i in range(n_timed):
             if not args.no_flush:
-                flush.fill_(i & 0xff)          # L2 flush, outside the bracket
+                flush.fill_(i & 0xff)          # L2 flush (256 MiB write), outside the bracket ...
+                sink.add_(sweep.sum())         # ... then a 256 MiB read sweep, so the timed kernel starts on a
+                                               # cold but CLEAN L2 and does not pay write-backs of the flush data
             ev[i][0].record(stream)
             step_fn(n_warm + i)
             ev[i][1].record(stream)
@@ -248,7 +252,7 @@ def main():
             "config": {"workload": w["name"], "envs_per_gpu": B, "num_uavs": w["N"], "num_targets": w["M"],
                        "actions": "Bernoulli(0.5), counter RNG keyed (seed=1, step, global env id), resident in HBM",
                        "auto_reset": True, "reset_schedule": "full reset every %d episodes, staggered steady state" % args.reset_episodes,
-                       "burn_in_steps": BURN_IN_STEPS, "l2": "flushed between timed steps (256 MiB write)"
+                       "burn_in_steps": BURN_IN_STEPS, "l2": "flushed between timed steps (256 MiB write, then a 256 MiB read sweep leaving clean lines)"
                        if not args.no_flush else "NOT flushed (diagnostic)",
                        "timing": "CUDA events per step on the launching stream, summed; max over ranks",
                        "pair_evals_per_sec": value, "objective_drift_max_abs": drift,

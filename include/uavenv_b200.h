@@ -127,7 +127,9 @@ int uavenv_step(uavenv_t *h, const int64_t *d_actions, float *d_obs, float *d_re
                 const uavenv_info_t *info, void *stream);
 
 /* same step through HOST buffers (the reference's caller lives on the host: main_train.py:111-113):
- * copies h_actions host->device, steps, copies reward/done back and synchronises the stream.
+ * moves h_actions host->device, steps, moves reward/done back and synchronises the stream.  Pinned,
+ * device-mapped host buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are read and written
+ * in place by the fused kernel over PCIe; pageable buffers go through staging copies.
  * The observation window stays on the device (d_obs, or the handle's own buffer when NULL -
  * see uavenv_obs_buffer) where the policy consumes it. */
 int uavenv_step_host(uavenv_t *h, const int64_t *h_actions, float *h_reward, uint8_t *h_done, float *d_obs,

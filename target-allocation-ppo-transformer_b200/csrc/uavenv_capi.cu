@@ -28,6 +28,8 @@ struct uavenv {
     double *d_scratch = nullptr;     // one double (recompute max diff)
     size_t reset_smem = 0;
     bool ready = false;              // reset() or load_scene() happened
+    const void *zc_key[3] = {nullptr, nullptr, nullptr};  // last host buffers seen by step_host ...
+    void *zc_dev[3] = {nullptr, nullptr, nullptr};        // ... and their device aliases when pinned + mapped
     std::string err;
 };
 
@@ -212,12 +214,32 @@ extern "C" int uavenv_step(uavenv_t *h, const int64_t *d_actions, float *d_obs, 
     return launch_check(h, "step_kernel");
 }
 
+// device alias of a pinned + mapped host allocation (cudaHostAlloc / cudaHostRegister; torch pin_memory), or NULL
+static void *mapped_alias(const void *host_ptr) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, host_ptr) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return attr.type == cudaMemoryTypeHost ? attr.devicePointer : nullptr;
+}
+
 extern "C" int uavenv_step_host(uavenv_t *h, const int64_t *h_actions, float *h_reward, uint8_t *h_done, float *d_obs,
                                 void *stream) {
     if (!h) return UAVENV_EINVAL;
     if (!h_actions || !h_reward || !h_done) return fail(h, UAVENV_EINVAL, "uavenv_step_host: NULL host buffer");
     cudaStream_t s = (cudaStream_t)stream;
     CU_TRY(h, cudaSetDevice(h->device));
+    // Pinned, device-mapped host buffers are used in place: the fused kernel reads the actions and writes
+    // reward / done straight over PCIe (no separate copy launches).  Pageable buffers go through staging copies.
+    if (h_actions != h->zc_key[0] || h_reward != h->zc_key[1] || h_done != h->zc_key[2]) {
+        h->zc_key[0] = h_actions; h->zc_key[1] = h_reward; h->zc_key[2] = h_done;
+        h->zc_dev[0] = mapped_alias(h_actions); h->zc_dev[1] = mapped_alias(h_reward); h->zc_dev[2] = mapped_alias(h_done);
+    }
+    if (h->zc_dev[0] && h->zc_dev[1] && h->zc_dev[2]) {
+        int rc = uavenv_step(h, (const int64_t *)h->zc_dev[0], d_obs ? d_obs : h->obs_buf, (float *)h->zc_dev[1],
+                             (uint8_t *)h->zc_dev[2], nullptr, stream);
+        if (rc != UAVENV_OK) return rc;
+        CU_TRY(h, cudaStreamSynchronize(s));
+        return UAVENV_OK;
+    }
     CU_TRY(h, cudaMemcpyAsync(h->d_actions, h_actions, (size_t)h->B * sizeof(int64_t), cudaMemcpyHostToDevice, s));
     int rc = uavenv_step(h, h->d_actions, d_obs ? d_obs : h->obs_buf, h->d_reward, h->d_done, nullptr, stream);
     if (rc != UAVENV_OK) return rc;

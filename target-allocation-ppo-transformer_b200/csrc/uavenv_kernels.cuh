@@ -248,17 +248,8 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
     const Hdr H = P.header(bc);
     float *tile = s_tile[warp] + lane * kObsFloats;
 
-    // ---- trip 1: everything that depends on b only -------------------------------------------------
+    // ---- trip 1: everything that depends on b only (all loads issued before anything is consumed) ----
     const uint32_t head_old = P.step_ctr[0];
-    const uint32_t head_new = (head_old + 1u) % (uint32_t)kSeqLen;       // ring slot of this step's row
-    if (tid == 0) {
-        // arrive; the last CTA to have READ the head publishes the new one (kept on the device so that
-        // CUDA-graph replays stay correct).  The increment depends on head_old, so the read is ordered first.
-        if (atomicAdd(&P.step_ctr[1], 1u + (head_old >> 31)) == gridDim.x - 1) {
-            P.step_ctr[1] = 0u;
-            P.step_ctr[0] = head_new;
-        }
-    }
     int k = H.n(I_K), m = H.n(I_M), nA = H.n(I_NASSIGNED), n0 = H.n(I_NCOVERED), age = H.n(I_AGE);
     double rev = H.f(F_REV), cost_sum = H.f(F_COST_SUM), covered_val = H.f(F_COVERED_VAL);
     double sum_pd = H.f(F_SUM_PD), sum_pf = H.f(F_SUM_PF);
@@ -268,6 +259,7 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
     const int c_lock_cnt = H.n(I_CUR_LOCK_CNT), c_tid = H.n(I_CUR_TID);
     const bool was_finished = !P.auto_reset && H.n(I_FINISHED);
     const int64_t action = io.actions[bc];
+    const uint32_t head_new = (head_old + 1u) % (uint32_t)kSeqLen;       // ring slot of this step's row
     // older rows of the window: ring tile [slot][feature pair][32 lanes] -> tile rows 0..3 (time order)
     float2 *const ring = P.ring(bc);
 #pragma unroll
@@ -277,6 +269,14 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
         float *dst = tile + (kSeqLen - 1 - a) * kStateDim;
 #pragma unroll
         for (int f = 0; f < kStateDim / 2; ++f) cp_async_8(dst + 2 * f, src + f * 32);
+    }
+    if (tid == 0) {
+        // arrive; the last CTA to have READ the head publishes the new one (kept on the device so that
+        // CUDA-graph replays stay correct).  The increment depends on head_old, so the read is ordered first.
+        if (atomicAdd(&P.step_ctr[1], 1u + (head_old >> 31)) == gridDim.x - 1) {
+            P.step_ctr[1] = 0u;
+            P.step_ctr[0] = head_new;
+        }
     }
 
     // ---- accept rule -> state update -> reward / done / info (uav_env.py:295-363, :426-433) ----------
