@@ -39,10 +39,10 @@ BURN_IN_STEPS = 300      # untimed: de-synchronises the envs' decision pointers 
 POOL = 64                # pre-generated action vectors cycled through the timed steps
 L2_FLUSH_BYTES = 256 << 20
 
-# Algorithmic bytes per env-step of THIS design (DESIGN.md §4 derives each term): actions 8, reward 4, done 1,
-# info 21, scalar state read 92 / write 76, window ring read 224 / write 56, window out 280, records of the new
-# pointer pair 128, accept path (p=1/2) 0.5*(64+32+32+4).
-ALGO_BYTES_PER_ENV_STEP = 8 + 4 + 1 + 21 + 92 + 76 + 224 + 56 + 280 + 128 + 0.5 * (64 + 32 + 32 + 4)
+# Algorithmic bytes per env-step of THIS design (DESIGN.md section 4.1 derives each term): io 38 (int64 action 8,
+# reward 4, done 1, info 25), header read 140 / write 124, window ring read 224 / write 56, window out 280,
+# records of the new pointer pair 128, accept path (p = 1/2 under Bernoulli actions) 0.5 * (32 + 4).
+ALGO_BYTES_PER_ENV_STEP = 38 + 140 + 124 + 224 + 56 + 280 + 128 + 0.5 * (32 + 4)
 
 
 def survey_bytes(M):     # SURVEY.md §8d traffic model (re-sums J over all M targets every step)
@@ -191,7 +191,8 @@ def main():
     pool = torch.empty(POOL, B, dtype=torch.int64, device=dev)
     for i in range(POOL):
         env.random_actions(BURN_IN_STEPS + i, ACTION_SEED, out=pool[i])
-    pool_host = pool.cpu().pin_memory()
+    pool_host = pool.cpu().pin_memory()                        # int64, the dtype Categorical.sample() yields
+    pool_host_i8 = pool.cpu().to(torch.int8).pin_memory()      # one byte per binary action
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     sweep = torch.zeros(L2_FLUSH_BYTES // 4, dtype=torch.int32, device=dev)
     sink = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -222,7 +223,8 @@ def main():
     # --- device-resident inputs: the fused kernel alone --------------------------------------------------
     ms_dev = timed(lambda i: env.step(pool[i % POOL]), W, K)
     # --- end to end through the host-buffer entry point ----------------------------------------------------
-    ms_e2e = timed(lambda i: env.step_host(pool_host[i % POOL]), W, K)
+    ms_e2e = timed(lambda i: env.step_host(pool_host_i8[i % POOL]), W, K)
+    ms_e2e_i64 = timed(lambda i: env.step_host(pool_host[i % POOL]), W, K)
     clocks = sampler.stop() if rank == 0 else None
     drift = env.recompute_objective()
     drift = parallel.reduce_scalar(drift, "max", dev)
@@ -267,9 +269,11 @@ def main():
                                                   "step; this kernel carries the objective incrementally and does "
                                                   "not move those bytes"}},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "ms_per_step": ms_e2e / K,
-                    "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": B * 5,
-                    "api": "UAVEnvBatched.step_host -> uavenv_step_host (pinned host actions in; reward, done out; "
-                           "observation window stays in HBM for the policy)"},
+                    "h2d_bytes_per_step": B * 1, "d2h_bytes_per_step": B * 5,
+                    "api": "UAVEnvBatched.step_host -> uavenv_step_host_i8 (pinned host int8 actions in; f32 reward + u8 "
+                           "done out, in place over PCIe; observation window stays in HBM for the policy)",
+                    "int64_actions": {"value": total_envs * K / (ms_e2e_i64 * 1e-3), "ms_per_step": ms_e2e_i64 / K,
+                                      "h2d_bytes_per_step": B * 8}},
             "gpu_launches": K, "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -134,6 +134,9 @@ int uavenv_step(uavenv_t *h, const int64_t *d_actions, float *d_obs, float *d_re
  * see uavenv_obs_buffer) where the policy consumes it. */
 int uavenv_step_host(uavenv_t *h, const int64_t *h_actions, float *h_reward, uint8_t *h_done, float *d_obs,
                      void *stream);
+/* the same with one byte per action (the action space is {0,1}, envs/uav_env.py:18): 8x less PCIe traffic */
+int uavenv_step_host_i8(uavenv_t *h, const int8_t *h_actions, float *h_reward, uint8_t *h_done, float *d_obs,
+                        void *stream);
 float *uavenv_obs_buffer(uavenv_t *h); /* device [B,5,14] owned by the handle */
 
 /* replaces assigning env.uavs / env.targets / env.nfz_list / env.interceptors by hand: injects

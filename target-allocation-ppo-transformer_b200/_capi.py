@@ -96,6 +96,8 @@ def load():
     L.uavenv_reset.argtypes = [vp, i32, vp, vp, vp]
     L.uavenv_step.argtypes = [vp, vp, vp, vp, vp, C.POINTER(UavenvInfo), vp]
     L.uavenv_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.uavenv_step_host_i8.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.uavenv_step_host_i8.restype = C.c_int
     L.uavenv_obs_buffer.argtypes = [vp]
     L.uavenv_obs_buffer.restype = vp
     L.uavenv_load_scene.argtypes = [vp, C.POINTER(UavenvScene), i32, i32, vp]

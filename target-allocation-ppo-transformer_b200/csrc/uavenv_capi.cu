@@ -195,14 +195,14 @@ extern "C" int uavenv_reset(uavenv_t *h, int32_t full_reset, const uint8_t *d_en
     return rc;
 }
 
-extern "C" int uavenv_step(uavenv_t *h, const int64_t *d_actions, float *d_obs, float *d_reward, uint8_t *d_done,
-                           const uavenv_info_t *info, void *stream) {
+static int launch_step(uavenv_t *h, const void *d_actions, int action_bytes, float *d_obs, float *d_reward,
+                       uint8_t *d_done, const uavenv_info_t *info, void *stream) {
     if (!h) return UAVENV_EINVAL;
     if (!d_actions || !d_obs || !d_reward || !d_done)
         return fail(h, UAVENV_EINVAL, "uavenv_step: actions/obs/reward/done must be non-NULL device pointers");
     if (!h->ready) return fail(h, UAVENV_ESTATE, "uavenv_step before reset()/load_scene()");
     StepIO io;
-    io.actions = d_actions; io.obs = d_obs; io.reward = d_reward; io.done = d_done;
+    io.actions = d_actions; io.action_bytes = action_bytes; io.obs = d_obs; io.reward = d_reward; io.done = d_done;
     io.J_val = info ? info->d_J_val : nullptr;
     io.num_assigned = info ? info->d_num_assigned : nullptr;
     io.is_valid = info ? info->d_is_valid_action : nullptr;
@@ -214,6 +214,11 @@ extern "C" int uavenv_step(uavenv_t *h, const int64_t *d_actions, float *d_obs, 
     return launch_check(h, "step_kernel");
 }
 
+extern "C" int uavenv_step(uavenv_t *h, const int64_t *d_actions, float *d_obs, float *d_reward, uint8_t *d_done,
+                           const uavenv_info_t *info, void *stream) {
+    return launch_step(h, d_actions, 8, d_obs, d_reward, d_done, info, stream);
+}
+
 // device alias of a pinned + mapped host allocation (cudaHostAlloc / cudaHostRegister; torch pin_memory), or NULL
 static void *mapped_alias(const void *host_ptr) {
     cudaPointerAttributes attr;
@@ -221,8 +226,8 @@ static void *mapped_alias(const void *host_ptr) {
     return attr.type == cudaMemoryTypeHost ? attr.devicePointer : nullptr;
 }
 
-extern "C" int uavenv_step_host(uavenv_t *h, const int64_t *h_actions, float *h_reward, uint8_t *h_done, float *d_obs,
-                                void *stream) {
+static int step_host_impl(uavenv_t *h, const void *h_actions, int action_bytes, float *h_reward, uint8_t *h_done,
+                          float *d_obs, void *stream) {
     if (!h) return UAVENV_EINVAL;
     if (!h_actions || !h_reward || !h_done) return fail(h, UAVENV_EINVAL, "uavenv_step_host: NULL host buffer");
     cudaStream_t s = (cudaStream_t)stream;
@@ -234,19 +239,29 @@ extern "C" int uavenv_step_host(uavenv_t *h, const int64_t *h_actions, float *h_
         h->zc_dev[0] = mapped_alias(h_actions); h->zc_dev[1] = mapped_alias(h_reward); h->zc_dev[2] = mapped_alias(h_done);
     }
     if (h->zc_dev[0] && h->zc_dev[1] && h->zc_dev[2]) {
-        int rc = uavenv_step(h, (const int64_t *)h->zc_dev[0], d_obs ? d_obs : h->obs_buf, (float *)h->zc_dev[1],
+        int rc = launch_step(h, h->zc_dev[0], action_bytes, d_obs ? d_obs : h->obs_buf, (float *)h->zc_dev[1],
                              (uint8_t *)h->zc_dev[2], nullptr, stream);
         if (rc != UAVENV_OK) return rc;
         CU_TRY(h, cudaStreamSynchronize(s));
         return UAVENV_OK;
     }
-    CU_TRY(h, cudaMemcpyAsync(h->d_actions, h_actions, (size_t)h->B * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-    int rc = uavenv_step(h, h->d_actions, d_obs ? d_obs : h->obs_buf, h->d_reward, h->d_done, nullptr, stream);
+    CU_TRY(h, cudaMemcpyAsync(h->d_actions, h_actions, (size_t)h->B * action_bytes, cudaMemcpyHostToDevice, s));
+    int rc = launch_step(h, h->d_actions, action_bytes, d_obs ? d_obs : h->obs_buf, h->d_reward, h->d_done, nullptr, stream);
     if (rc != UAVENV_OK) return rc;
     CU_TRY(h, cudaMemcpyAsync(h_reward, h->d_reward, (size_t)h->B * sizeof(float), cudaMemcpyDeviceToHost, s));
     CU_TRY(h, cudaMemcpyAsync(h_done, h->d_done, (size_t)h->B, cudaMemcpyDeviceToHost, s));
     CU_TRY(h, cudaStreamSynchronize(s));
     return UAVENV_OK;
+}
+
+extern "C" int uavenv_step_host(uavenv_t *h, const int64_t *h_actions, float *h_reward, uint8_t *h_done, float *d_obs,
+                                void *stream) {
+    return step_host_impl(h, h_actions, 8, h_reward, h_done, d_obs, stream);
+}
+
+extern "C" int uavenv_step_host_i8(uavenv_t *h, const int8_t *h_actions, float *h_reward, uint8_t *h_done, float *d_obs,
+                                   void *stream) {
+    return step_host_impl(h, h_actions, 1, h_reward, h_done, d_obs, stream);
 }
 
 // ---- scene injection / readback ----------------------------------------------------------------

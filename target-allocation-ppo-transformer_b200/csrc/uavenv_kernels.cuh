@@ -21,7 +21,8 @@ constexpr int kWarpsPerCta = kStepThreads / 32;
 constexpr int kResetThreads = 128;
 
 struct StepIO {
-    const int64_t *actions;  // [B]
+    const void *actions;     // [B] int64 (action_bytes = 8) or int8 (action_bytes = 1)
+    int32_t action_bytes;
     float *obs;              // [B,5,14]
     float *reward;           // [B]
     uint8_t *done;           // [B]
@@ -258,7 +259,8 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
     const double c_nhp = H.f(F_CUR_NHP), c_lock_cost = H.f(F_CUR_LOCK_COST), c_ucost = H.f(F_CUR_UCOST);
     const int c_lock_cnt = H.n(I_CUR_LOCK_CNT), c_tid = H.n(I_CUR_TID);
     const bool was_finished = !P.auto_reset && H.n(I_FINISHED);
-    const int64_t action = io.actions[bc];
+    const int64_t action = io.action_bytes == 8 ? static_cast<const int64_t *>(io.actions)[bc]
+                                                : (int64_t) static_cast<const int8_t *>(io.actions)[bc];
     const uint32_t head_new = (head_old + 1u) % (uint32_t)kSeqLen;       // ring slot of this step's row
     // older rows of the window: ring tile [slot][feature pair][32 lanes] -> tile rows 0..3 (time order)
     float2 *const ring = P.ring(bc);

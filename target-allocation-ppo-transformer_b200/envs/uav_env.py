@@ -155,17 +155,20 @@ class UAVEnvBatched:
 
     def step_host(self, actions_cpu, reward_out=None, done_out=None):
         """The same step driven from HOST buffers (the reference's caller lives on the host):
-        actions are copied host->device, reward/done device->host, inside the call.  The observation
+        actions (int64, or one byte each as int8/uint8) travel host->device, reward/done device->host, inside the
+        call - in place over PCIe when the tensors are pinned, through staging copies otherwise.  The observation
         window stays in self.obs on the device for the policy.  Returns (reward_cpu, done_cpu)."""
         if self._h_reward is None:
             self._h_reward = torch.zeros(self.num_envs, dtype=torch.float32).pin_memory()
             self._h_done = torch.zeros(self.num_envs, dtype=torch.uint8).pin_memory()
         r = self._h_reward if reward_out is None else reward_out
         d = self._h_done if done_out is None else done_out
-        if actions_cpu.dtype != torch.int64 or actions_cpu.numel() != self.num_envs or actions_cpu.is_cuda:
-            raise ValueError("actions_cpu must be a host int64 tensor with num_envs elements")
-        self._chk(self._lib.uavenv_step_host(self._h, C.c_void_p(actions_cpu.data_ptr()), C.c_void_p(r.data_ptr()),
-                                             C.c_void_p(d.data_ptr()), C.c_void_p(self.obs.data_ptr()), self._stream()))
+        if actions_cpu.is_cuda or actions_cpu.numel() != self.num_envs or not actions_cpu.is_contiguous() \
+                or actions_cpu.dtype not in (torch.int64, torch.int8, torch.uint8):
+            raise ValueError("actions_cpu must be a contiguous host int64 / int8 / uint8 tensor with num_envs elements")
+        fn = self._lib.uavenv_step_host if actions_cpu.dtype == torch.int64 else self._lib.uavenv_step_host_i8
+        self._chk(fn(self._h, C.c_void_p(actions_cpu.data_ptr()), C.c_void_p(r.data_ptr()), C.c_void_p(d.data_ptr()),
+                     C.c_void_p(self.obs.data_ptr()), self._stream()))
         return r, d
 
     def random_actions(self, step, action_seed=1, out=None):
