@@ -157,6 +157,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="diagnostic only: keep L2 warm between steps")
     ap.add_argument("--reset-episodes", type=int, default=200, help="diagnostic only: cfg.RESET_EPISODES (200)")
+    ap.add_argument("--flush-mode", default="write+read", choices=["write+read", "write", "read", "sleep"],
+                    help="diagnostic only: what runs between timed steps (default: the documented L2 flush)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     w = dict(WORKLOADS[args.workload])
@@ -206,9 +208,13 @@ def main():
         torch.cuda.synchronize(dev)
         for i in range(n_timed):
             if not args.no_flush:
-                flush.fill_(i & 0xff)          # L2 flush (256 MiB write), outside the bracket ...
-                sink.add_(sweep.sum())         # ... then a 256 MiB read sweep, so the timed kernel starts on a
+                if args.flush_mode in ("write+read", "write"):
+                    flush.fill_(i & 0xff)      # L2 flush (256 MiB write), outside the bracket ...
+                if args.flush_mode in ("write+read", "read"):
+                    sink.add_(sweep.sum())     # ... then a 256 MiB read sweep, so the timed kernel starts on a
                                                # cold but CLEAN L2 and does not pay write-backs of the flush data
+                if args.flush_mode == "sleep":
+                    torch.cuda._sleep(60000)   # diagnostic: GPU-side delay only (L2 stays warm, host runs ahead)
             ev[i][0].record(stream)
             step_fn(n_warm + i)
             ev[i][1].record(stream)
@@ -216,6 +222,29 @@ def main():
         parallel.barrier()
         ms = sum(a.elapsed_time(b) for a, b in ev)
         return parallel.reduce_scalar(ms, "max", dev)
+
+    graph_us = None
+    if os.environ.get("UAVENV_BENCH_GRAPH"):
+        # diagnostic: POOL steps captured in one CUDA graph and replayed back to back (no host gaps, warm L2)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for i in range(3):
+                env.step(pool[i])
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                for i in range(POOL):
+                    env.step(pool[i])
+            for _ in range(3):
+                g.replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(side)
+            for _ in range(5):
+                g.replay()
+            e1.record(side)
+        torch.cuda.synchronize(dev)
+        graph_us = 1e3 * e0.elapsed_time(e1) / (5 * POOL)
+        print("graph replay: %.2f us/step" % graph_us, file=sys.stderr)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:

@@ -55,6 +55,7 @@ def build(force=False, verbose=False):
     objs = []
     for src, extra in UNITS:
         obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        extra = extra + os.environ.get("UAVENV_EXTRA_NVCC_FLAGS", "").split()
         cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + [
             "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -98,6 +98,7 @@ struct Params {
     double map_w, map_h, uav_x_lo, uav_x_hi, tgt_x_lo, tgt_x_hi, intercept_rad;
     uint32_t seed_lo, seed_hi;
     uint32_t env_id_base;
+    int32_t debug;      // only read when built with -DUAVENV_DEBUG_FLAGS (bandwidth attribution experiments)
     // device arrays
     UavRec *uav;        // [B][N]
     TgtRec *tgt;        // [B][M]

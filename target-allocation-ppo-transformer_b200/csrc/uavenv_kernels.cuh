@@ -211,26 +211,35 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 //   trip 2  the two 64 B records of the NEW pointer pair - the accept rule itself needs no gather because the
 //           current pair's values were captured in the header when its observation row was computed
 // The [5,14] windows of a warp (32 x 280 B, contiguous in obs) leave through one TMA bulk store.
-// A finished env is restarted by its own warp, out of line (warp_restart), in a second pass of the
-// evaluation loop so that nothing but a few scalars is live across that call.
+// A finished env restarts inside the launch.  The common case (same scene, uav_env.py:175-182) stays on the
+// two-trip chain: its owner simply evaluates pointer pair (0,0) with the target's products taken as cleared,
+// and the warp clears the allocation arrays afterwards with fire-and-forget stores (warp_soft_reset).
+// Only the scheduled regeneration (every RESET_EPISODES-th episode) takes a second pass of the evaluation
+// loop after warp_regen (out of line, so that nothing but a few scalars is live across the call).
 
-__device__ __noinline__ void warp_restart(const Params &P, unsigned done_mask, int b0, uint32_t *s_keys, double *s_vals) {
+// state-only restart (uav_env.py:175-182) of the finished envs in soft_mask: stores only, nothing waits on it
+__device__ __noinline__ void warp_soft_reset(const Params &P, unsigned soft_mask, int b0) {
     const int lane = threadIdx.x & 31;
-    while (done_mask) {                     // main_train.py:79 schedule, one finished env at a time
-        const int src = __ffs(done_mask) - 1;
-        done_mask &= done_mask - 1;
+    __syncwarp();  // orders the owners' accept stores before the clears
+    while (soft_mask) {
+        const int src = __ffs(soft_mask) - 1;
+        soft_mask &= soft_mask - 1;
+        warp_clear_allocation(P, b0 + src, lane);
+    }
+    __syncwarp();
+}
+
+// scheduled regeneration (main_train.py:79: every RESET_EPISODES-th episode) of the envs in regen_mask
+__device__ __noinline__ void warp_regen(const Params &P, unsigned regen_mask, int b0, uint32_t *s_keys, double *s_vals) {
+    const int lane = threadIdx.x & 31;
+    while (regen_mask) {
+        const int src = __ffs(regen_mask) - 1;
+        regen_mask &= regen_mask - 1;
         const int eb = b0 + src;
-        const int episode = P.header(eb).n(I_EPISODE) + 1;
-        const bool full = P.reset_episodes > 0 && (episode % P.reset_episodes) == 0;
+        const int scene = P.header(eb).n(I_SCENE);
         __syncwarp();
-        if (full) {
-            const int scene = P.header(eb).n(I_SCENE);
-            warp_generate_scene(P, eb, (uint32_t)scene, s_keys, s_vals);
-            if (lane == 0) P.header(eb).n(I_SCENE) = scene + 1;
-        } else {
-            warp_clear_allocation(P, eb, lane);
-        }
-        if (lane == 0) P.header(eb).n(I_EPISODE) = episode;
+        warp_generate_scene(P, eb, (uint32_t)scene, s_keys, s_vals);
+        if (lane == 0) P.header(eb).n(I_SCENE) = scene + 1;
         __syncwarp();
     }
     __threadfence_block();
@@ -248,6 +257,11 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
     const int N = P.N, M = P.M;
     const Hdr H = P.header(bc);
     float *tile = s_tile[warp] + lane * kObsFloats;
+#ifdef UAVENV_DEBUG_FLAGS
+    const int dbg = P.debug;  // 1: no window store, 2: no ring loads, 4: no ring store, 8: records of env-local pair 0
+#else
+    constexpr int dbg = 0;
+#endif
 
     // ---- trip 1: everything that depends on b only (all loads issued before anything is consumed) ----
     const uint32_t head_old = P.step_ctr[0];
@@ -258,6 +272,7 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
     const double c_pf = H.f(F_CUR_PF), c_pd = H.f(F_CUR_PD), c_value = H.f(F_CUR_VALUE), c_nh = H.f(F_CUR_NH);
     const double c_nhp = H.f(F_CUR_NHP), c_lock_cost = H.f(F_CUR_LOCK_COST), c_ucost = H.f(F_CUR_UCOST);
     const int c_lock_cnt = H.n(I_CUR_LOCK_CNT), c_tid = H.n(I_CUR_TID);
+    const int episode_new = H.n(I_EPISODE) + 1;
     const bool was_finished = !P.auto_reset && H.n(I_FINISHED);
     const int64_t action = io.action_bytes == 8 ? static_cast<const int64_t *>(io.actions)[bc]
                                                 : (int64_t) static_cast<const int8_t *>(io.actions)[bc];
@@ -270,7 +285,7 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
         const float2 *src = ring + slot * (kStateDim / 2) * 32;
         float *dst = tile + (kSeqLen - 1 - a) * kStateDim;
 #pragma unroll
-        for (int f = 0; f < kStateDim / 2; ++f) cp_async_8(dst + 2 * f, src + f * 32);
+        for (int f = 0; f < kStateDim / 2; ++f) if (!(dbg & 2)) cp_async_8(dst + 2 * f, src + f * 32);
     }
     if (tid == 0) {
         // arrive; the last CTA to have READ the head publishes the new one (kept on the device so that
@@ -331,26 +346,32 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
         }
     }
     const bool inert = live && done && !restarted;  // finished, no auto-reset: zero window, frozen state
+    const bool regen = restarted && P.reset_episodes > 0 && (episode_new % P.reset_episodes) == 0;  // main_train.py:79
+    const bool soft = restarted && !regen;
+    if (restarted) {  // pointers and running sums of the next episode (uav_env.py:54-55, :175-182)
+        k = 0; m = 0; nA = 0; n0 = 0; age = 0;
+        rev = 0.0; cost_sum = 0.0; covered_val = 0.0; sum_pd = 0.0; sum_pf = 0.0;
+        H.n(I_EPISODE) = episode_new;
+    }
 
-    // ---- trip 2 + evaluation.  pass 0: envs that go on; pass 1 (rare): envs restarted by this warp ----
+    // ---- trip 2 + evaluation.  pass 0: every env but the (rare) regenerated ones; pass 1: those ----------
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
         if (pass == 1) {
-            const unsigned done_mask = __ballot_sync(kFullMask, restarted);
-            if (done_mask == 0u) break;
+            const unsigned soft_mask = __ballot_sync(kFullMask, soft);
+            if (soft_mask) warp_soft_reset(P, soft_mask, b0);
+            const unsigned regen_mask = __ballot_sync(kFullMask, regen);
+            if (regen_mask == 0u) break;
             double *s_vals = reinterpret_cast<double *>(s_dyn) + (size_t)warp * M;
             uint32_t *s_keys = reinterpret_cast<uint32_t *>(reinterpret_cast<double *>(s_dyn) + (size_t)kWarpsPerCta * M) +
                                (size_t)warp * max(N, M);
-            warp_restart(P, done_mask, b0, s_keys, s_vals);
-            if (restarted) {
-                k = 0; m = 0; nA = 0; n0 = 0; age = 0;
-                rev = 0.0; cost_sum = 0.0; covered_val = 0.0; sum_pd = 0.0; sum_pf = 0.0;
-                total_val = H.f(F_TOTAL_VAL); total_cost = H.f(F_TOTAL_COST);
-            }
+            warp_regen(P, regen_mask, b0, s_keys, s_vals);
+            if (regen) { total_val = H.f(F_TOTAL_VAL); total_cost = H.f(F_TOTAL_COST); }
         }
-        if (live && (pass == 0 ? !done : restarted)) {
-            const UavRec u = P.uav[(size_t)b * N + k];
-            const TgtRec t = P.tgt[(size_t)b * M + m];  // sees this thread's own accept store when it hits target m
+        if (live && (pass == 0 ? (!done || soft) : regen)) {
+            const UavRec u = P.uav[(size_t)b * N + ((dbg & 8) ? 0 : k)];
+            TgtRec t = P.tgt[(size_t)b * M + ((dbg & 8) ? 0 : m)];  // sees this thread's own accept store on target m
+            if (soft) { t.nh = 1.0; t.nh_pure = 1.0; t.lock_cost = 0.0; t.lock_cnt = 0; }  // cleared below by the warp
             cp_async_wait_all();                        // ring rows have landed in the tile (gathers still in flight)
             const int nprev = age < kSeqLen - 1 ? age : kSeqLen - 1;
 #pragma unroll
@@ -369,7 +390,7 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
 #pragma unroll
             for (int f = 0; f < kStateDim / 2; ++f) {
                 const float2 v = make_float2(row[2 * f], row[2 * f + 1]);
-                dsth[f * 32] = v;
+                if (!(dbg & 4)) dsth[f * 32] = v;
                 *reinterpret_cast<float2 *>(tile + (kSeqLen - 1) * kStateDim + 2 * f) = v;
             }
             H.n(I_K) = k; H.n(I_M) = m; H.n(I_NASSIGNED) = nA; H.n(I_NCOVERED) = n0; H.n(I_AGE) = nprev + 1;
@@ -392,7 +413,7 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
     __syncwarp();
     {
         const int nenv = min(32, P.B - b0);
-        if (nenv > 0) {
+        if (nenv > 0 && !(dbg & 1)) {
             float *dst = io.obs + (size_t)b0 * kObsFloats;
             const float *src = s_tile[warp];
             const uint32_t bytes = (uint32_t)nenv * kObsFloats * sizeof(float);
