@@ -28,6 +28,7 @@ struct uavenv {
     uint8_t *d_done = nullptr;
     double *d_scratch = nullptr;     // one double (recompute max diff)
     size_t reset_smem = 0;
+    int n_service = 0;
     bool ready = false;              // reset() or load_scene() happened
     const void *zc_key[3] = {nullptr, nullptr, nullptr};  // last host buffers seen by step_host ...
     void *zc_dev[3] = {nullptr, nullptr, nullptr};        // ... and their device aliases when pinned + mapped
@@ -105,19 +106,33 @@ static int create_impl(uavenv *h) {
     P.seed_lo = (uint32_t)h->seed; P.seed_hi = (uint32_t)(h->seed >> 32);
     P.env_id_base = (uint32_t)h->env_id_base;
     if (const char *dbg = getenv("UAVENV_DEBUG")) P.debug = atoi(dbg);
-    CU_TRY(h, dev_alloc(h, &P.uav, B * N));
-    CU_TRY(h, dev_alloc(h, &P.tgt, B * M));
+    // scene storage is double-buffered (current scene + the pre-generated next one)
+    CU_TRY(h, dev_alloc(h, &P.uav, 2 * B * N));
+    CU_TRY(h, dev_alloc(h, &P.tgt, 2 * B * M));
     CU_TRY(h, dev_alloc(h, &P.assigned, B * N));
-    CU_TRY(h, dev_alloc(h, &P.uav_type, B * N));
-    CU_TRY(h, dev_alloc(h, &P.uav_vel, B * N));
-    CU_TRY(h, dev_alloc(h, &P.tgt_vel, B * M));
-    CU_TRY(h, dev_alloc(h, &P.nfz, B * K1));
-    CU_TRY(h, dev_alloc(h, &P.intc, B * K2));
+    CU_TRY(h, dev_alloc(h, &P.uav_type, 2 * B * N));
+    CU_TRY(h, dev_alloc(h, &P.uav_vel, 2 * B * N));
+    CU_TRY(h, dev_alloc(h, &P.tgt_vel, 2 * B * M));
+    CU_TRY(h, dev_alloc(h, &P.nfz, 2 * B * K1));
+    CU_TRY(h, dev_alloc(h, &P.intc, 2 * B * K2));
+    const size_t req_bytes = (B + kServiceEnvsPerWarp - 1) / kServiceEnvsPerWarp * kServiceEnvsPerWarp;
+    CU_TRY(h, dev_alloc(h, &P.pregen_req, req_bytes));
+    CU_TRY(h, dev_alloc(h, &P.pregen_ack, req_bytes));
+    CU_TRY(h, cudaMemset(P.pregen_req, 0, req_bytes));
+    CU_TRY(h, cudaMemset(P.pregen_ack, 0, req_bytes));
     const size_t tiles = (B + 31) / 32;
     CU_TRY(h, dev_alloc(h, &P.hist, tiles * kRingTileElems));
     CU_TRY(h, dev_alloc(h, &P.step_ctr, 2));
     CU_TRY(h, dev_alloc(h, &P.hdr, tiles * kHdrTileBytes));
-    CU_TRY(h, cudaMemset(P.hdr, 0, tiles * kHdrTileBytes));
+    {   // headers start zeroed, with "no scene prepared" in the service-owned words
+        std::vector<unsigned char> init(tiles * kHdrTileBytes, 0);
+        for (size_t b = 0; b < tiles * 32; ++b) {
+            const Hdr hv = header_at(init.data(), (int)b);
+            hv.n(I_NEXT_TAG) = -1;
+            hv.n(I_JOB) = -256;
+        }
+        CU_TRY(h, cudaMemcpy(P.hdr, init.data(), init.size(), cudaMemcpyHostToDevice));
+    }
     CU_TRY(h, cudaMemset(P.step_ctr, 0, 2 * sizeof(uint32_t)));
     CU_TRY(h, cudaMemset(P.hist, 0, tiles * kRingTileElems * sizeof(float2)));
     CU_TRY(h, cudaMemset(P.assigned, 0xff, B * N * sizeof(int32_t)));
@@ -126,8 +141,12 @@ static int create_impl(uavenv *h) {
     CU_TRY(h, dev_alloc(h, &h->d_reward, B));
     CU_TRY(h, dev_alloc(h, &h->d_done, B));
     CU_TRY(h, dev_alloc(h, &h->d_scratch, 1));
-    // per-warp scratch of the scene generator: M doubles + max(N,M) keys, for the 4 warps of a CTA
-    h->reset_smem = (size_t)kWarpsPerCta * (M * sizeof(double) + std::max(N, M) * sizeof(uint32_t));
+    // per-warp scratch of the scene generator: max(N,M) sort keys, for the 4 warps of a CTA
+    h->reset_smem = (size_t)kWarpsPerCta * std::max(N, M) * sizeof(uint32_t);
+    // CTAs appended to every step launch that prepare next scenes (only when scenes are ever regenerated)
+    h->n_service = (c.auto_reset && c.reset_episodes > 0)
+                       ? (int)((B + (size_t)kServiceEnvsPerWarp * kWarpsPerCta - 1) / ((size_t)kServiceEnvsPerWarp * kWarpsPerCta))
+                       : 0;
     if (h->reset_smem > 8 * 1024) {
         CU_TRY(h, cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->reset_smem));
         CU_TRY(h, cudaFuncSetAttribute(reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->reset_smem));
@@ -211,8 +230,8 @@ static int launch_step(uavenv_t *h, const void *d_actions, int action_bytes, flo
     io.avg_p_dmg = info ? info->d_avg_p_dmg : nullptr;
     io.avg_p_final = info ? info->d_avg_p_final : nullptr;
     io.reward_f64 = info ? info->d_reward_f64 : nullptr;
-    const int grid = (h->B + kStepThreads - 1) / kStepThreads;
-    step_kernel<<<grid, kStepThreads, h->reset_smem, (cudaStream_t)stream>>>(h->P, io);
+    const int n_main = (h->B + kStepThreads - 1) / kStepThreads;
+    step_kernel<<<n_main + h->n_service, kStepThreads, h->reset_smem, (cudaStream_t)stream>>>(h->P, io, n_main);
     return launch_check(h, "step_kernel");
 }
 
@@ -330,15 +349,36 @@ extern "C" int uavenv_get_scene(uavenv_t *h, uavenv_scene_t *sc, int32_t first_e
     CU_TRY(h, cudaSetDevice(h->device));
     CU_TRY(h, cudaDeviceSynchronize());
     const size_t n = (size_t)count * P.N, m = (size_t)count * P.M, k1 = (size_t)count * P.K1, k2 = (size_t)count * P.K2;
-    std::vector<UavRec> U; std::vector<TgtRec> T; std::vector<int32_t> ty; std::vector<double2> tv, uv;
-    std::vector<NfzRec> Z; std::vector<IntRec> I;
-    CU_TRY(h, fetch(U, P.uav + (size_t)first_env * P.N, n));
-    CU_TRY(h, fetch(T, P.tgt + (size_t)first_env * P.M, m));
-    CU_TRY(h, fetch(ty, P.uav_type + (size_t)first_env * P.N, n));
-    CU_TRY(h, fetch(tv, P.tgt_vel + (size_t)first_env * P.M, m));
-    CU_TRY(h, fetch(uv, P.uav_vel + (size_t)first_env * P.N, n));
-    CU_TRY(h, fetch(Z, P.nfz + (size_t)first_env * P.K1, k1));
-    CU_TRY(h, fetch(I, P.intc + (size_t)first_env * P.K2, k2));
+    // both storage slots are fetched; each env's current slot (I_GEN & 1) selects
+    const size_t B = (size_t)h->B, fe = (size_t)first_env, ce = (size_t)count;
+    std::vector<UavRec> U(n); std::vector<TgtRec> T(m); std::vector<int32_t> ty(n); std::vector<double2> tv(m), uv(n);
+    std::vector<NfzRec> Z(k1); std::vector<IntRec> I(k2);
+    {
+        const size_t t0 = fe / 32, t1 = (fe + ce + 31) / 32;
+        std::vector<unsigned char> tiles;
+        CU_TRY(h, fetch(tiles, P.hdr + t0 * kHdrTileBytes, (t1 - t0) * kHdrTileBytes));
+        std::vector<UavRec> U2; std::vector<TgtRec> T2; std::vector<int32_t> ty2; std::vector<double2> tv2, uv2;
+        std::vector<NfzRec> Z2; std::vector<IntRec> I2;
+        for (int slot = 0; slot < 2; ++slot) {
+            CU_TRY(h, fetch(U2, P.uav + (slot * B + fe) * P.N, n));
+            CU_TRY(h, fetch(T2, P.tgt + (slot * B + fe) * P.M, m));
+            CU_TRY(h, fetch(ty2, P.uav_type + (slot * B + fe) * P.N, n));
+            CU_TRY(h, fetch(tv2, P.tgt_vel + (slot * B + fe) * P.M, m));
+            CU_TRY(h, fetch(uv2, P.uav_vel + (slot * B + fe) * P.N, n));
+            CU_TRY(h, fetch(Z2, P.nfz + (slot * B + fe) * P.K1, k1));
+            CU_TRY(h, fetch(I2, P.intc + (slot * B + fe) * P.K2, k2));
+            for (size_t e = 0; e < ce; ++e) {
+                if ((header_at(tiles.data(), (int)(fe + e - t0 * 32)).n(I_GEN) & 1) != slot) continue;
+                std::copy(U2.begin() + e * P.N, U2.begin() + (e + 1) * P.N, U.begin() + e * P.N);
+                std::copy(ty2.begin() + e * P.N, ty2.begin() + (e + 1) * P.N, ty.begin() + e * P.N);
+                std::copy(uv2.begin() + e * P.N, uv2.begin() + (e + 1) * P.N, uv.begin() + e * P.N);
+                std::copy(T2.begin() + e * P.M, T2.begin() + (e + 1) * P.M, T.begin() + e * P.M);
+                std::copy(tv2.begin() + e * P.M, tv2.begin() + (e + 1) * P.M, tv.begin() + e * P.M);
+                std::copy(Z2.begin() + e * P.K1, Z2.begin() + (e + 1) * P.K1, Z.begin() + e * P.K1);
+                std::copy(I2.begin() + e * P.K2, I2.begin() + (e + 1) * P.K2, I.begin() + e * P.K2);
+            }
+        }
+    }
     for (size_t i = 0; i < n; ++i) {
         if (sc->uav_x) sc->uav_x[i] = U[i].x;
         if (sc->uav_y) sc->uav_y[i] = U[i].y;
@@ -391,17 +431,22 @@ extern "C" int uavenv_get_state(uavenv_t *h, uavenv_state_t *st, int32_t first_e
         if (st->uav_idx) st->uav_idx[i] = hv.n(I_K);
         if (st->target_idx) st->target_idx[i] = hv.n(I_M);
         if (st->episode) st->episode[i] = hv.n(I_EPISODE);
-        if (st->scene_index) st->scene_index[i] = hv.n(I_SCENE);
+        if (st->scene_index) st->scene_index[i] = hv.n(I_GEN) >> 1;
         if (st->finished) st->finished[i] = (uint8_t)(hv.n(I_FINISHED) != 0);
         if (st->J_val) st->J_val[i] = hv.f(F_REV) - (P.omega * hv.f(F_COST_SUM));
     }
     if (st->lock_count || st->not_hit || st->not_hit_pure) {
         std::vector<TgtRec> T;
-        CU_TRY(h, fetch(T, P.tgt + f * P.M, c * P.M));
-        for (size_t j = 0; j < T.size(); ++j) {
-            if (st->lock_count) st->lock_count[j] = T[j].lock_cnt;
-            if (st->not_hit) st->not_hit[j] = T[j].nh;
-            if (st->not_hit_pure) st->not_hit_pure[j] = T[j].nh_pure;
+        for (int slot = 0; slot < 2; ++slot) {
+            CU_TRY(h, fetch(T, P.tgt + ((size_t)slot * h->B + f) * P.M, c * P.M));
+            for (size_t e = 0; e < c; ++e) {
+                if ((header_at(tiles.data(), (int)(f + e - t0 * 32)).n(I_GEN) & 1) != slot) continue;
+                for (size_t j = e * P.M; j < (e + 1) * P.M; ++j) {
+                    if (st->lock_count) st->lock_count[j] = T[j].lock_cnt;
+                    if (st->not_hit) st->not_hit[j] = T[j].nh;
+                    if (st->not_hit_pure) st->not_hit_pure[j] = T[j].nh_pure;
+                }
+            }
         }
     }
     return UAVENV_OK;

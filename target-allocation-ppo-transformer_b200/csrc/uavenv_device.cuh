@@ -67,10 +67,13 @@ enum I32Field {
     I_NCOVERED,       // N0                                      envs/uav_env.py:278-282
     I_AGE,            // valid rows of the observation window (0..5)
     I_EPISODE,        // 1-based episode counter                 main_train.py:77
-    I_SCENE,          // scenes generated so far
+    I_GEN,            // (index of the NEXT scene to generate << 1) | storage slot of the current scene.
+                      // One word so the pre-generation service reads a consistent pair.  Written by the env's owner.
     I_CUR_LOCK_CNT,   // target_m lock count
     I_CUR_TID,        // target_m.id
     I_FINISHED,       // auto_reset = 0 only
+    I_NEXT_TAG,       // scene index held complete in the OTHER slot (-1: none).   Written by the service only.
+    I_JOB,            // (scene index << 8) | chunks done, of the service's job.   Written by the service only.
     NI32
 };
 constexpr size_t kHdrTileBytes = (size_t)NF64 * 32 * sizeof(double) + (size_t)NI32 * 32 * sizeof(int32_t);
@@ -99,19 +102,25 @@ struct Params {
     uint32_t seed_lo, seed_hi;
     uint32_t env_id_base;
     int32_t debug;      // only read when built with -DUAVENV_DEBUG_FLAGS (bandwidth attribution experiments)
-    // device arrays
-    UavRec *uav;        // [B][N]
-    TgtRec *tgt;        // [B][M]
+    // device arrays.  Scene storage is double-buffered ([2 slots]...): the current scene of an env lives in
+    // slot (I_GEN & 1); the other slot receives the env's NEXT scene ahead of time (pre-generation service),
+    // so the scheduled regeneration of main_train.py:79 is a slot flip on the step's critical path.
+    UavRec *uav;        // [2][B][N]
+    TgtRec *tgt;        // [2][B][M]
     int32_t *assigned;  // [B][N]  target id or -1     envs/entities.py:30
-    int32_t *uav_type;  // [B][N]  cold
-    double2 *uav_vel;   // [B][N]  cold (the records keep heading + speed)
-    double2 *tgt_vel;   // [B][M]  cold
-    NfzRec *nfz;        // [B][K1]
-    IntRec *intc;       // [B][K2]
+    int32_t *uav_type;  // [2][B][N]  cold
+    double2 *uav_vel;   // [2][B][N]  cold (the records keep heading + speed)
+    double2 *tgt_vel;   // [2][B][M]  cold
+    NfzRec *nfz;        // [2][B][K1]
+    IntRec *intc;       // [2][B][K2]
+    uint8_t *pregen_req;  // [B] request counter, written by the env's owner when it consumes / invalidates the next scene
+    uint8_t *pregen_ack;  // [B] value of pregen_req the service has satisfied
     float2 *hist;       // [B/32][5 slots][7 feature pairs][32 lanes] observation ring, warp-tile major
     uint32_t *step_ctr; // [0] = ring head (mod 5), [1] = CTA arrival counter of the running step
     unsigned char *hdr; // [B/32] header tiles (kHdrTileBytes each)
     __host__ __device__ __forceinline__ Hdr header(int b) const { return header_at(hdr, b); }
+    __host__ __device__ __forceinline__ size_t uoff(int slot, int b) const { return ((size_t)slot * B + b) * N; }
+    __host__ __device__ __forceinline__ size_t toff(int slot, int b) const { return ((size_t)slot * B + b) * M; }
     // ring element (slot, feature pair f) of env b: ring(b)[slot * 224 + f * 32]
     __host__ __device__ __forceinline__ float2 *ring(int b) const { return hist + (size_t)(b >> 5) * kRingTileElems + (b & 31); }
 };
@@ -186,16 +195,16 @@ __device__ __forceinline__ double damage_prob(const Params &P, const UavRec &u, 
 }
 
 // envs/mechanics.py:118-163 calc_penetration_prob (Eq.5-6): depends on the UAV only
-__device__ __forceinline__ double penetration_prob(const Params &P, int b, const UavRec &u) {
+__device__ __forceinline__ double penetration_prob(const Params &P, int slot, int b, const UavRec &u) {
     double p = 1.0;
-    const NfzRec *Z = P.nfz + (size_t)b * P.K1;
+    const NfzRec *Z = P.nfz + ((size_t)slot * P.B + b) * P.K1;
     for (int i = 0; i < P.K1; ++i) {                               // :130-141
         double dist;
         const double ea = angle_score(u.x, u.y, u.wx, u.wy, Z[i].x, Z[i].y, dist);
         const double qd = dist / 10.0, ed = exp(-(qd * qd));       // zeta = 10 for obstacles (:78)
         p *= clip01((1.0 - ea) * (1.0 - ed));
     }
-    const IntRec *I = P.intc + (size_t)b * P.K2;
+    const IntRec *I = P.intc + ((size_t)slot * P.B + b) * P.K2;
     for (int i = 0; i < P.K2; ++i) {                               // :144-161
         double dist;
         const double ea = angle_score(u.x, u.y, u.wx, u.wy, I[i].x, I[i].y, dist);
@@ -209,11 +218,11 @@ __device__ __forceinline__ double penetration_prob(const Params &P, int b, const
 }
 
 // derived fields of a UAV record from its velocity (obstacles of env b must be visible for p_pen)
-__device__ __forceinline__ void finish_uav(const Params &P, int b, UavRec &u, double vx, double vy) {
+__device__ __forceinline__ void finish_uav(const Params &P, int slot, int b, UavRec &u, double vx, double vy) {
     const double speed = sqrt(vx * vx + vy * vy);
     if (speed < 1e-6) { u.wx = 1.0; u.wy = 0.0; u.inv_speed = -1.0; }
     else { u.wx = vx / speed; u.wy = vy / speed; u.inv_speed = 1.0 / speed; }
-    u.p_pen = penetration_prob(P, b, u);
+    u.p_pen = penetration_prob(P, slot, b, u);
 }
 
 // envs/mechanics.py:185-241 get_state_vector (Eq.15): fp64 features, cast to f32, then the power-of-two

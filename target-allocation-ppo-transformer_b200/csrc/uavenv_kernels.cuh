@@ -5,7 +5,7 @@
 //                        reward / done / info -> auto-reset of finished envs (counter RNG scene
 //                        generation, uav_env.py:65-182) -> pair score + observation row of the new
 //                        pointer pair (mechanics.py:167-241) -> [B,5,14] window.
-//   reset_kernel         UAVEnv.reset for a masked subset (uav_env.py:42-63), one CTA per env.
+//   reset_kernel         UAVEnv.reset for a masked subset (uav_env.py:42-63), one warp per env.
 //   pack_scene_kernel    scene injection (host SoA -> device records) + per-scene derived values.
 //   score_matrix_kernel  p_final / p_damage [B,N,M] (main.py:38-45 over mechanics.py:167-181).
 //   recompute_kernel     fresh J / N0 / sums from the per-target products, a warp per env with
@@ -55,111 +55,183 @@ __device__ __forceinline__ int rank_of(const uint32_t *keys, int n, int i) {
     return r;
 }
 
-// _reset_state_only (envs/uav_env.py:175-182) for env b: every UAV available again, every lock list empty
-__device__ __forceinline__ void warp_clear_allocation(const Params &P, int b, int lane) {
+// _reset_state_only (envs/uav_env.py:175-182) for env b (scene in `slot`): every UAV available again, every
+// lock list empty
+__device__ __forceinline__ void warp_clear_allocation(const Params &P, int slot, int b, int lane) {
     int32_t *asg = P.assigned + (size_t)b * P.N;
     for (int i = lane; i < P.N; i += 32) asg[i] = -1;
-    TgtRec *T = P.tgt + (size_t)b * P.M;
+    TgtRec *T = P.tgt + P.toff(slot, b);
     for (int j = lane; j < P.M; j += 32) {
         T[j].nh = 1.0; T[j].nh_pure = 1.0; T[j].lock_cost = 0.0; T[j].lock_cnt = 0;
     }
 }
 
-// _generate_scene (envs/uav_env.py:65-173) for env b with the counter RNG; also clears the allocation.
-// s_keys: >= max(N,M) uint32, s_vals: >= M doubles (per-warp scratch).
-__device__ __noinline__ void warp_generate_scene(const Params &P, int b, uint32_t scene, uint32_t *s_keys,
-                                                 double *s_vals) {
+// ---- _generate_scene (envs/uav_env.py:65-173) with the counter RNG, in independent chunks of 32 entities ----
+// A scene is a pure function of (seed, global env id, scene index); it is produced chunk by chunk so that the
+// pre-generation service can spread one scene over several launches.  Chunk order: target chunks first
+// (chunk 0 also draws the obstacles), then UAV chunks (their p_pen needs the obstacles, already visible).
+
+__device__ __forceinline__ int scene_chunks(const Params &P) { return (P.M + 31) / 32 + (P.N + 31) / 32; }
+
+// number of value-6 targets, n2 = randint(1, n_remain+1)   (uav_env.py:121-126)
+__device__ __forceinline__ int scene_n2(const Params &P, uint32_t env, uint32_t scene) {
+    const int n_remain = P.M - P.M / 2 - 1;
+    if (n_remain < 1) return 0;
+    return 1 + (int)(((uint64_t)philox4x32(P.seed_lo, P.seed_hi, 0u, S_N2, scene, env).x * (uint64_t)n_remain) >> 32);
+}
+
+// total_swarm_cost (uav_env.py:118) and sum of target values (:198) of a generated scene, in closed form
+// (type / value class counts are fixed by construction; all terms are exact in fp64)
+__device__ __forceinline__ void scene_totals(const Params &P, int b, uint32_t scene, double &total_val, double &total_cost) {
+    const int n1 = P.M / 2, n_remain = P.M - n1 - 1, n2 = scene_n2(P, P.env_id_base + (uint32_t)b, scene);
+    total_val = 4.0 * n1 + 6.0 * n2 + 8.0 * (n_remain > 0 ? n_remain - n2 : 0) + 16.0;
+    total_cost = 1.0 * (P.N - P.N / 4) + 1.25 * (P.N / 4);
+}
+
+__device__ void warp_generate_chunk(const Params &P, int slot, int b, uint32_t scene, int chunk, uint32_t *s_keys) {
     const int lane = threadIdx.x & 31;
     const uint32_t k0 = P.seed_lo, k1 = P.seed_hi, env = P.env_id_base + (uint32_t)b;
-    const int N = P.N, M = P.M;
-    // obstacles first: the per-UAV penetration probability needs them   (uav_env.py:146-170)
-    NfzRec *Z = P.nfz + (size_t)b * P.K1;
-    for (int i = lane; i < P.K1; i += 32) {
-        const uint4 a = philox4x32(k0, k1, i, S_NFZ_A, scene, env);
-        const uint4 c = philox4x32(k0, k1, i, S_NFZ_B, scene, env);
-        Z[i].radius = 5.0 + (10.0 - 5.0) * u53(a.x, a.y);
-        Z[i].x = 120.0 + (140.0 - 120.0) * u53(a.z, a.w);
-        Z[i].y = 0.0 + (P.map_h - 0.0) * u53(c.x, c.y);
+    const int N = P.N, M = P.M, tchunks = (M + 31) / 32;
+    if (chunk == 0) {  // obstacles   (uav_env.py:146-170)
+        NfzRec *Z = P.nfz + ((size_t)slot * P.B + b) * P.K1;
+        for (int i = lane; i < P.K1; i += 32) {
+            const uint4 a = philox4x32(k0, k1, i, S_NFZ_A, scene, env);
+            const uint4 c = philox4x32(k0, k1, i, S_NFZ_B, scene, env);
+            Z[i].radius = 5.0 + (10.0 - 5.0) * u53(a.x, a.y);
+            Z[i].x = 120.0 + (140.0 - 120.0) * u53(a.z, a.w);
+            Z[i].y = 0.0 + (P.map_h - 0.0) * u53(c.x, c.y);
+        }
+        IntRec *I = P.intc + ((size_t)slot * P.B + b) * P.K2;
+        for (int i = lane; i < P.K2; i += 32) {
+            const uint4 a = philox4x32(k0, k1, i, S_INT_A, scene, env);
+            const uint4 c = philox4x32(k0, k1, i, S_INT_B, scene, env);
+            I[i].x = 140.0 + (160.0 - 140.0) * u53(a.x, a.y);
+            I[i].y = 0.0 + (P.map_h - 0.0) * u53(a.z, a.w);
+            const double sp = 0.30 + (0.32 - 0.30) * u53(c.x, c.y);
+            const double ang = 0.0 + (2.0 * 3.141592653589793 - 0.0) * u53(c.z, c.w);
+            I[i].vx = cos(ang) * sp;
+            I[i].vy = sin(ang) * sp;
+        }
     }
-    IntRec *I = P.intc + (size_t)b * P.K2;
-    for (int i = lane; i < P.K2; i += 32) {
-        const uint4 a = philox4x32(k0, k1, i, S_INT_A, scene, env);
-        const uint4 c = philox4x32(k0, k1, i, S_INT_B, scene, env);
-        I[i].x = 140.0 + (160.0 - 140.0) * u53(a.x, a.y);
-        I[i].y = 0.0 + (P.map_h - 0.0) * u53(a.z, a.w);
-        const double sp = 0.30 + (0.32 - 0.30) * u53(c.x, c.y);
-        const double ang = 0.0 + (2.0 * 3.141592653589793 - 0.0) * u53(c.z, c.w);
-        I[i].vx = cos(ang) * sp;
-        I[i].vy = sin(ang) * sp;
+    __syncwarp();
+    if (chunk < tchunks) {
+        // targets [32*chunk, 32*chunk+32): value by rank among the value keys (uav_env.py:121-129), list position
+        // by rank among the list keys (the shuffle of :173: target id i lands at list position rank_i)
+        const int i = chunk * 32 + lane;
+        const int n1 = M / 2, n_remain = M - n1 - 1, n2 = scene_n2(P, env, scene);
+        for (int j = lane; j < M; j += 32) s_keys[j] = philox4x32(k0, k1, j, S_TGT_VAL, scene, env).x;
+        __syncwarp();
+        double value = 0.0;
+        if (i < M) {
+            const int q = rank_of(s_keys, M, i);
+            value = q < n1 ? 4.0 : (q < n1 + n2 ? 6.0 : (q < n1 + n_remain ? 8.0 : 16.0));
+        }
+        __syncwarp();
+        for (int j = lane; j < M; j += 32) s_keys[j] = philox4x32(k0, k1, j, S_TGT_LIST, scene, env).x;
+        __syncwarp();
+        if (i < M) {
+            const int pos = rank_of(s_keys, M, i);
+            const uint4 a = philox4x32(k0, k1, i, S_TGT_POS, scene, env);
+            const uint4 v = philox4x32(k0, k1, i, S_TGT_VEL, scene, env);
+            TgtRec t;
+            t.x = P.tgt_x_lo + (P.tgt_x_hi - P.tgt_x_lo) * u53(a.x, a.y);            // :134
+            t.y = 0.0 + (P.map_h - 0.0) * u53(a.z, a.w);                              // :135
+            const double vx = (u53(v.x, v.y) - 0.5) * 0.03, vy = (u53(v.z, v.w) - 0.5) * 0.03;  // :139
+            t.speed = sqrt(vx * vx + vy * vy);
+            t.value = value;
+            t.nh = 1.0; t.nh_pure = 1.0; t.lock_cost = 0.0; t.lock_cnt = 0; t.id = i;
+            P.tgt[P.toff(slot, b) + pos] = t;
+            P.tgt_vel[P.toff(slot, b) + pos] = make_double2(vx, vy);
+        }
+    } else {
+        // UAVs [32*c, 32*c+32): N//4 of type 2, uniformly permuted (uav_env.py:81-84); kinematics (:88-111)
+        const int i = (chunk - tchunks) * 32 + lane;
+        for (int j = lane; j < N; j += 32) s_keys[j] = philox4x32(k0, k1, j, S_UAV_TYPE, scene, env).x;
+        __syncwarp();
+        if (i < N) {
+            const int type = rank_of(s_keys, N, i) >= N - N / 4 ? 2 : 1;
+            const uint4 a = philox4x32(k0, k1, i, S_UAV_POS, scene, env);
+            const uint4 d = philox4x32(k0, k1, i, S_UAV_DYN, scene, env);
+            UavRec u;
+            u.x = P.uav_x_lo + (P.uav_x_hi - P.uav_x_lo) * u53(a.x, a.y);            // :88
+            u.y = 0.0 + (P.map_h - 0.0) * u53(a.z, a.w);                              // :89
+            double base_speed, base_load;
+            if (type == 1) { base_speed = 0.35 + (0.50 - 0.35) * u53(d.x, d.y); u.cost = 1.0; base_load = 0.95; }
+            else { base_speed = 0.75 + (0.90 - 0.75) * u53(d.x, d.y); u.cost = 1.25; base_load = 1.0; }  // :93-102
+            const double real_speed = base_speed * P.weather_speed;                   // :106
+            u.load = base_load * P.weather_load;                                      // :107
+            const double ang = (-15.0 + (15.0 - (-15.0)) * u53(d.z, d.w)) * (3.141592653589793 / 180.0);  // :110
+            const double vx = cos(ang) * real_speed, vy = sin(ang) * real_speed;      // :111
+            finish_uav(P, slot, b, u, vx, vy);
+            P.uav[P.uoff(slot, b) + i] = u;
+            P.uav_vel[P.uoff(slot, b) + i] = make_double2(vx, vy);
+            P.uav_type[P.uoff(slot, b) + i] = type;
+        }
     }
-    // 1. UAV types: N//4 of type 2, uniformly permuted   (uav_env.py:81-84)
     __syncwarp();
-    for (int i = lane; i < N; i += 32) s_keys[i] = philox4x32(k0, k1, i, S_UAV_TYPE, scene, env).x;
-    __syncwarp();  // keys + obstacles visible to the warp
-    const int num_type1 = N - N / 4;
-    UavRec *U = P.uav + (size_t)b * N;
-    int32_t *asg = P.assigned + (size_t)b * N;
-    int32_t *typ = P.uav_type + (size_t)b * N;
-    double cost_part = 0.0;
-    for (int i = lane; i < N; i += 32) {
-        const int type = rank_of(s_keys, N, i) >= num_type1 ? 2 : 1;
-        const uint4 a = philox4x32(k0, k1, i, S_UAV_POS, scene, env);
-        const uint4 d = philox4x32(k0, k1, i, S_UAV_DYN, scene, env);
-        UavRec u;
-        u.x = P.uav_x_lo + (P.uav_x_hi - P.uav_x_lo) * u53(a.x, a.y);            // :88
-        u.y = 0.0 + (P.map_h - 0.0) * u53(a.z, a.w);                              // :89
-        double base_speed, base_load;
-        if (type == 1) { base_speed = 0.35 + (0.50 - 0.35) * u53(d.x, d.y); u.cost = 1.0; base_load = 0.95; }
-        else { base_speed = 0.75 + (0.90 - 0.75) * u53(d.x, d.y); u.cost = 1.25; base_load = 1.0; }  // :93-102
-        const double real_speed = base_speed * P.weather_speed;                   // :106
-        u.load = base_load * P.weather_load;                                      // :107
-        const double ang = (-15.0 + (15.0 - (-15.0)) * u53(d.z, d.w)) * (3.141592653589793 / 180.0);  // :110
-        const double vx = cos(ang) * real_speed, vy = sin(ang) * real_speed;      // :111
-        finish_uav(P, b, u, vx, vy);
-        U[i] = u;
-        P.uav_vel[(size_t)b * N + i] = make_double2(vx, vy);
-        asg[i] = -1;
-        typ[i] = type;
-        cost_part += u.cost;
+}
+
+// whole scene in one go (reset(), and the fallback when the next scene was not pre-generated in time)
+__device__ __noinline__ void warp_generate_scene(const Params &P, int slot, int b, uint32_t scene, uint32_t *s_keys) {
+    const int nchunks = scene_chunks(P);
+    for (int c = 0; c < nchunks; ++c) {
+        warp_generate_chunk(P, slot, b, scene, c, s_keys);
+        if (c == 0) __threadfence_block();  // obstacles visible to the UAV chunks of this warp
     }
-    const double total_cost = warp_sum(cost_part);
-    // 2. target values   (uav_env.py:121-129)
-    const int n1 = M / 2, n_remain = M - n1 - 1;
-    int n2 = 0;
-    if (n_remain >= 1) n2 = 1 + (int)(((uint64_t)philox4x32(k0, k1, 0u, S_N2, scene, env).x * (uint64_t)n_remain) >> 32);
+    warp_clear_allocation(P, slot, b, threadIdx.x & 31);
     __syncwarp();
-    for (int i = lane; i < M; i += 32) s_keys[i] = philox4x32(k0, k1, i, S_TGT_VAL, scene, env).x;
+}
+
+// ---- pre-generation service: CTAs appended to the step grid (blockIdx >= main CTAs) ------------------
+// Every env always has its NEXT scene (index I_GEN >> 1) prepared in the slot it is not playing on.  The owner
+// bumps pregen_req[b] whenever that scene was consumed or invalidated; a service warp that finds
+// req != ack advances the env's job by ONE chunk per launch (a few microseconds, hidden behind the step),
+// and publishes I_NEXT_TAG = scene index + ack when the last chunk is in.  Single writer per word:
+// owner -> I_GEN, pregen_req; service -> I_JOB, I_NEXT_TAG, pregen_ack and the other slot's records.
+constexpr int kServiceEnvsPerWarp = 256;  // 32 lanes x 8 request bytes, scanned with one 8 B load per lane
+
+__device__ __noinline__ void pregen_service(const Params &P, int service_cta, uint32_t *s_keys) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int base = (service_cta * kWarpsPerCta + warp) * kServiceEnvsPerWarp;
+    if (base >= P.B) return;
+    const int nchunks = scene_chunks(P);
+    // req/ack are padded to a multiple of kServiceEnvsPerWarp bytes, so the vector loads stay in bounds
+    const uint2 rq = *reinterpret_cast<const uint2 *>(P.pregen_req + base + lane * 8);
+    const uint2 ak = *reinterpret_cast<const uint2 *>(P.pregen_ack + base + lane * 8);
+    const uint64_t diff = ((uint64_t)(rq.y ^ ak.y) << 32) | (uint64_t)(rq.x ^ ak.x);
+    // ONE chunk of ONE env per warp and launch: bounded work, so the service never outlasts the step itself;
+    // whatever else is pending waits for the next launch (the scene is not needed for ~200 episodes)
+    int my_first = -1;
+#pragma unroll
+    for (int byte = 7; byte >= 0; --byte)
+        if (((diff >> (8 * byte)) & 0xffu) != 0u && base + lane * 8 + byte < P.B) my_first = byte;
+    const unsigned mask = __ballot_sync(kFullMask, my_first >= 0);
+    if (mask == 0u) return;
+    const int src = __ffs(mask) - 1;
+    const int byte = __shfl_sync(kFullMask, my_first, src);
+    const int eb = base + src * 8 + byte;
+    // the request value seen BEFORE I_GEN is read is the one acknowledged (a later bump stays pending)
+    const uint64_t rq64 = ((uint64_t)rq.y << 32) | (uint64_t)rq.x;
+    const uint8_t req = (uint8_t)__shfl_sync(kFullMask, (unsigned)((rq64 >> (8 * (byte & 7))) & 0xffu), src);
+    const Hdr h = P.header(eb);
+    __threadfence();                                        // acquire: I_GEN was written before the request became visible
+    const int gen = *(volatile int32_t *)&h.n(I_GEN);
+    const int job = *(volatile int32_t *)&h.n(I_JOB);
+    const int scene = gen >> 1, slot = (gen & 1) ^ 1;
+    const int done_chunks = (job >> 8) == scene ? (job & 0xff) : 0;       // a job for another scene is stale
     __syncwarp();
-    double val_part = 0.0;
-    for (int i = lane; i < M; i += 32) {
-        const int q = rank_of(s_keys, M, i);
-        const double v = q < n1 ? 4.0 : (q < n1 + n2 ? 6.0 : (q < n1 + n_remain ? 8.0 : 16.0));
-        s_vals[i] = v;
-        val_part += v;
+    if (done_chunks < nchunks) warp_generate_chunk(P, slot, eb, (uint32_t)scene, done_chunks, s_keys);
+    if (lane == 0) {
+        __threadfence();                                    // records before the job word / tag
+        if (done_chunks + 1 >= nchunks) {
+            h.n(I_JOB) = (scene << 8) | nchunks;
+            h.n(I_NEXT_TAG) = scene;
+            __threadfence();
+            P.pregen_ack[eb] = req;
+        } else {
+            h.n(I_JOB) = (scene << 8) | (done_chunks + 1);
+        }
     }
-    const double total_val = warp_sum(val_part);
-    // 3. list permutation (uav_env.py:173) + kinematics: target id i lands at list position rank_i
-    __syncwarp();
-    for (int i = lane; i < M; i += 32) s_keys[i] = philox4x32(k0, k1, i, S_TGT_LIST, scene, env).x;
-    __syncwarp();
-    TgtRec *T = P.tgt + (size_t)b * M;
-    double2 *TV = P.tgt_vel + (size_t)b * M;
-    for (int i = lane; i < M; i += 32) {
-        const int pos = rank_of(s_keys, M, i);
-        const uint4 a = philox4x32(k0, k1, i, S_TGT_POS, scene, env);
-        const uint4 v = philox4x32(k0, k1, i, S_TGT_VEL, scene, env);
-        TgtRec t;
-        t.x = P.tgt_x_lo + (P.tgt_x_hi - P.tgt_x_lo) * u53(a.x, a.y);            // :134
-        t.y = 0.0 + (P.map_h - 0.0) * u53(a.z, a.w);                              // :135
-        const double vx = (u53(v.x, v.y) - 0.5) * 0.03, vy = (u53(v.z, v.w) - 0.5) * 0.03;  // :139
-        t.speed = sqrt(vx * vx + vy * vy);
-        t.value = s_vals[i];
-        t.nh = 1.0; t.nh_pure = 1.0; t.lock_cost = 0.0; t.lock_cnt = 0; t.id = i;
-        T[pos] = t;
-        TV[pos] = make_double2(vx, vy);
-    }
-    if (lane == 0) { P.header(b).f(F_TOTAL_COST) = total_cost; P.header(b).f(F_TOTAL_VAL) = total_val; }
-    __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -214,42 +286,49 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 // A finished env restarts inside the launch.  The common case (same scene, uav_env.py:175-182) stays on the
 // two-trip chain: its owner simply evaluates pointer pair (0,0) with the target's products taken as cleared,
 // and the warp clears the allocation arrays afterwards with fire-and-forget stores (warp_soft_reset).
-// Only the scheduled regeneration (every RESET_EPISODES-th episode) takes a second pass of the evaluation
-// loop after warp_regen (out of line, so that nothing but a few scalars is live across the call).
+// The scheduled regeneration (every RESET_EPISODES-th episode, main_train.py:79) is a slot flip: the env's
+// next scene was prepared in the other storage slot by the pre-generation service (the CTAs past the main
+// grid, pregen_service above) - so it, too, stays on the two-trip chain.  Only when that scene is not ready
+// (first episodes after a reset with a very short schedule) does the owner's warp generate it in place, in a
+// second pass of the evaluation loop (out of line, so nothing but a few scalars is live across the call).
 
-// state-only restart (uav_env.py:175-182) of the finished envs in soft_mask: stores only, nothing waits on it
-__device__ __noinline__ void warp_soft_reset(const Params &P, unsigned soft_mask, int b0) {
+// restart bookkeeping of the finished envs in mask (their scene is in slot_of[lane]): stores only
+__device__ __noinline__ void warp_soft_reset(const Params &P, unsigned soft_mask, int b0, int my_slot) {
     const int lane = threadIdx.x & 31;
     __syncwarp();  // orders the owners' accept stores before the clears
     while (soft_mask) {
         const int src = __ffs(soft_mask) - 1;
         soft_mask &= soft_mask - 1;
-        warp_clear_allocation(P, b0 + src, lane);
+        const int slot = __shfl_sync(kFullMask, my_slot, src);
+        warp_clear_allocation(P, slot, b0 + src, lane);
     }
     __syncwarp();
 }
 
-// scheduled regeneration (main_train.py:79: every RESET_EPISODES-th episode) of the envs in regen_mask
-__device__ __noinline__ void warp_regen(const Params &P, unsigned regen_mask, int b0, uint32_t *s_keys, double *s_vals) {
-    const int lane = threadIdx.x & 31;
-    while (regen_mask) {
-        const int src = __ffs(regen_mask) - 1;
-        regen_mask &= regen_mask - 1;
-        const int eb = b0 + src;
-        const int scene = P.header(eb).n(I_SCENE);
+// fallback regeneration in place (the next scene was not pre-generated in time) of the envs in mask
+__device__ __noinline__ void warp_regen_inline(const Params &P, unsigned mask, int b0, int my_slot, int my_scene,
+                                               uint32_t *s_keys) {
+    while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int slot = __shfl_sync(kFullMask, my_slot, src), scene = __shfl_sync(kFullMask, my_scene, src);
         __syncwarp();
-        warp_generate_scene(P, eb, (uint32_t)scene, s_keys, s_vals);
-        if (lane == 0) P.header(eb).n(I_SCENE) = scene + 1;
-        __syncwarp();
+        warp_generate_scene(P, slot, b0 + src, (uint32_t)scene, s_keys);
     }
     __threadfence_block();
 }
 
-__global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_constant__ Params P, const StepIO io) {
+__global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_constant__ Params P, const StepIO io,
+                                                               const int n_main) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ __align__(128) float s_tile[kWarpsPerCta][32 * kObsFloats];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t *const s_keys = reinterpret_cast<uint32_t *>(s_dyn) + (size_t)warp * max(P.N, P.M);  // per-warp scratch
+    if ((int)blockIdx.x >= n_main) {  // service CTAs: prepare next scenes, off the step's critical path
+        pregen_service(P, (int)blockIdx.x - n_main, s_keys);
+        return;
+    }
     const int b0 = blockIdx.x * kStepThreads + warp * 32;   // first env of this warp
     const int b = b0 + lane;
     const bool live = b < P.B;
@@ -273,6 +352,8 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
     const double c_nhp = H.f(F_CUR_NHP), c_lock_cost = H.f(F_CUR_LOCK_COST), c_ucost = H.f(F_CUR_UCOST);
     const int c_lock_cnt = H.n(I_CUR_LOCK_CNT), c_tid = H.n(I_CUR_TID);
     const int episode_new = H.n(I_EPISODE) + 1;
+    const int gen = H.n(I_GEN);
+    int slot = gen & 1;                                                  // storage slot of the current scene
     const bool was_finished = !P.auto_reset && H.n(I_FINISHED);
     const int64_t action = io.action_bytes == 8 ? static_cast<const int64_t *>(io.actions)[bc]
                                                 : (int64_t) static_cast<const int8_t *>(io.actions)[bc];
@@ -290,7 +371,7 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
     if (tid == 0) {
         // arrive; the last CTA to have READ the head publishes the new one (kept on the device so that
         // CUDA-graph replays stay correct).  The increment depends on head_old, so the read is ordered first.
-        if (atomicAdd(&P.step_ctr[1], 1u + (head_old >> 31)) == gridDim.x - 1) {
+        if (atomicAdd(&P.step_ctr[1], 1u + (head_old >> 31)) == (unsigned)n_main - 1u) {
             P.step_ctr[1] = 0u;
             P.step_ctr[0] = head_new;
         }
@@ -314,7 +395,7 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
                 if (new_r >= prev_r) {                                                   // :317 (Eq.21)
                     reward = new_r - prev_r;                                             // :321
                     cur_r = new_r;
-                    TgtRec *tp = P.tgt + (size_t)b * M + m;
+                    TgtRec *tp = P.tgt + P.toff(slot, b) + m;
                     tp->nh = nh2; tp->nh_pure = c_nhp * (1.0 - c_pd);
                     tp->lock_cost = c_lock_cost + c_ucost; tp->lock_cnt = c_lock_cnt + 1;
                     P.assigned[(size_t)b * N + k] = c_tid;                               // :308
@@ -347,30 +428,38 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
     }
     const bool inert = live && done && !restarted;  // finished, no auto-reset: zero window, frozen state
     const bool regen = restarted && P.reset_episodes > 0 && (episode_new % P.reset_episodes) == 0;  // main_train.py:79
-    const bool soft = restarted && !regen;
+    bool inline_regen = false;
     if (restarted) {  // pointers and running sums of the next episode (uav_env.py:54-55, :175-182)
         k = 0; m = 0; nA = 0; n0 = 0; age = 0;
         rev = 0.0; cost_sum = 0.0; covered_val = 0.0; sum_pd = 0.0; sum_pf = 0.0;
         H.n(I_EPISODE) = episode_new;
+        if (regen) {
+            const int scene = gen >> 1;
+            scene_totals(P, b, (uint32_t)scene, total_val, total_cost);
+            H.f(F_TOTAL_VAL) = total_val; H.f(F_TOTAL_COST) = total_cost;
+            if (H.n(I_NEXT_TAG) == scene) slot ^= 1;        // the pre-generated scene: flip the storage slot
+            else inline_regen = true;                       // not there yet: generate in place (second pass)
+            __threadfence();                                // this step's accept store lands before the old slot is recycled
+            H.n(I_GEN) = ((scene + 1) << 1) | slot;
+            __threadfence();
+            P.pregen_req[b] = (uint8_t)(P.pregen_req[b] + 1);  // ask the service for scene+1 in the other slot
+        }
     }
+    const bool soft = restarted && !inline_regen;
 
-    // ---- trip 2 + evaluation.  pass 0: every env but the (rare) regenerated ones; pass 1: those ----------
+    // ---- trip 2 + evaluation.  pass 0: every env but the (rare) inline-regenerated ones; pass 1: those ----
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
         if (pass == 1) {
             const unsigned soft_mask = __ballot_sync(kFullMask, soft);
-            if (soft_mask) warp_soft_reset(P, soft_mask, b0);
-            const unsigned regen_mask = __ballot_sync(kFullMask, regen);
+            if (soft_mask) warp_soft_reset(P, soft_mask, b0, slot);
+            const unsigned regen_mask = __ballot_sync(kFullMask, inline_regen);
             if (regen_mask == 0u) break;
-            double *s_vals = reinterpret_cast<double *>(s_dyn) + (size_t)warp * M;
-            uint32_t *s_keys = reinterpret_cast<uint32_t *>(reinterpret_cast<double *>(s_dyn) + (size_t)kWarpsPerCta * M) +
-                               (size_t)warp * max(N, M);
-            warp_regen(P, regen_mask, b0, s_keys, s_vals);
-            if (regen) { total_val = H.f(F_TOTAL_VAL); total_cost = H.f(F_TOTAL_COST); }
+            warp_regen_inline(P, regen_mask, b0, slot, gen >> 1, s_keys);
         }
-        if (live && (pass == 0 ? (!done || soft) : regen)) {
-            const UavRec u = P.uav[(size_t)b * N + ((dbg & 8) ? 0 : k)];
-            TgtRec t = P.tgt[(size_t)b * M + ((dbg & 8) ? 0 : m)];  // sees this thread's own accept store on target m
+        if (live && (pass == 0 ? (!done || soft) : inline_regen)) {
+            const UavRec u = P.uav[P.uoff(slot, b) + ((dbg & 8) ? 0 : k)];
+            TgtRec t = P.tgt[P.toff(slot, b) + ((dbg & 8) ? 0 : m)];  // sees this thread's own accept store on target m
             if (soft) { t.nh = 1.0; t.nh_pure = 1.0; t.lock_cost = 0.0; t.lock_cnt = 0; }  // cleared below by the warp
             cp_async_wait_all();                        // ring rows have landed in the tile (gathers still in flight)
             const int nprev = age < kSeqLen - 1 ? age : kSeqLen - 1;
@@ -436,34 +525,52 @@ __global__ void __launch_bounds__(kResetThreads) reset_kernel(const __grid_const
     extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ float s_row[kResetThreads / 32][kStateDim];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    double *s_vals = reinterpret_cast<double *>(s_dyn) + (size_t)warp * P.M;
-    uint32_t *s_keys = reinterpret_cast<uint32_t *>(reinterpret_cast<double *>(s_dyn) + (size_t)wpb * P.M) +
-                       (size_t)warp * max(P.N, P.M);
+    uint32_t *s_keys = reinterpret_cast<uint32_t *>(s_dyn) + (size_t)warp * max(P.N, P.M);
     for (int e = blockIdx.x * wpb + warp; e < count; e += gridDim.x * wpb) {
         const int b = first_env + e;
         if (mask && !mask[b]) continue;  // uniform across the warp
+        const Hdr H = P.header(b);
+        const int gen = H.n(I_GEN), slot = gen & 1;
+        __syncwarp();
+        const bool ahead = P.auto_reset && P.reset_episodes > 0;  // keep the NEXT scene prepared in the other slot
         if (mode == 1) {
-            const int scene = P.header(b).n(I_SCENE);
-            __syncwarp();
-            warp_generate_scene(P, b, (uint32_t)scene, s_keys, s_vals);
-            if (lane == 0) P.header(b).n(I_SCENE) = scene + 1;
+            // a new scene now, in place (index gen >> 1) ...
+            const int scene = gen >> 1;
+            warp_generate_scene(P, slot, b, (uint32_t)scene, s_keys);
+            // ... and the one after it into the other slot, so that the first scheduled regeneration is a flip
+            // (a reset is off the hot path; the step-time service only has to keep up with later flips)
+            if (ahead) warp_generate_scene(P, slot ^ 1, b, (uint32_t)(scene + 1), s_keys);
+            if (lane == 0) {
+                double tv, tc;
+                scene_totals(P, b, (uint32_t)scene, tv, tc);
+                H.f(F_TOTAL_VAL) = tv; H.f(F_TOTAL_COST) = tc;
+                H.n(I_GEN) = ((scene + 1) << 1) | slot;
+                if (ahead) { H.n(I_NEXT_TAG) = scene + 1; H.n(I_JOB) = ((scene + 1) << 8) | scene_chunks(P); }
+            }
+        } else if (mode == 2) {
+            // injected scene (already packed into the current slot); prepare the generated scene that follows it
+            if (ahead) {
+                warp_generate_scene(P, slot ^ 1, b, (uint32_t)(gen >> 1), s_keys);
+                if (lane == 0) { H.n(I_NEXT_TAG) = gen >> 1; H.n(I_JOB) = ((gen >> 1) << 8) | scene_chunks(P); }
+            }
+            warp_clear_allocation(P, slot, b, lane);
         } else {
-            warp_clear_allocation(P, b, lane);
+            warp_clear_allocation(P, slot, b, lane);
         }
         __syncwarp();
         if (lane == 0) {
-            const double total_cost = P.header(b).f(F_TOTAL_COST), total_val = P.header(b).f(F_TOTAL_VAL);
+            const double total_cost = H.f(F_TOTAL_COST), total_val = H.f(F_TOTAL_VAL);
             double pf, pd;
             float row[kStateDim];
-            const UavRec u = P.uav[(size_t)b * P.N];
-            const TgtRec t = P.tgt[(size_t)b * P.M];
+            const UavRec u = P.uav[P.uoff(slot, b)];
+            const TgtRec t = P.tgt[P.toff(slot, b)];
             eval_pointer_pair(P, u, t, 0.0, 0.0, total_cost, total_val, pf, pd, row);
-            store_current_pair(P.header(b), u, t, pf, pd);
-            P.header(b).n(I_K) = 0; P.header(b).n(I_M) = 0; P.header(b).n(I_NASSIGNED) = 0; P.header(b).n(I_NCOVERED) = 0; P.header(b).n(I_AGE) = 1;
-            P.header(b).f(F_REV) = 0.0; P.header(b).f(F_COST_SUM) = 0.0; P.header(b).f(F_COVERED_VAL) = 0.0;
-            P.header(b).f(F_SUM_PD) = 0.0; P.header(b).f(F_SUM_PF) = 0.0;
-            P.header(b).n(I_FINISHED) = 0;
-            P.header(b).n(I_EPISODE) = (mode == 0) ? P.header(b).n(I_EPISODE) + 1 : 1;
+            store_current_pair(H, u, t, pf, pd);
+            H.n(I_K) = 0; H.n(I_M) = 0; H.n(I_NASSIGNED) = 0; H.n(I_NCOVERED) = 0; H.n(I_AGE) = 1;
+            H.f(F_REV) = 0.0; H.f(F_COST_SUM) = 0.0; H.f(F_COVERED_VAL) = 0.0;
+            H.f(F_SUM_PD) = 0.0; H.f(F_SUM_PF) = 0.0;
+            H.n(I_FINISHED) = 0;
+            H.n(I_EPISODE) = (mode == 0) ? H.n(I_EPISODE) + 1 : 1;
             const uint32_t head = P.step_ctr[0] % (uint32_t)kSeqLen;
             float2 *dsth = P.ring(b) + head * (kStateDim / 2) * 32;
             for (int f = 0; f < kStateDim / 2; ++f) dsth[f * 32] = make_float2(row[2 * f], row[2 * f + 1]);
@@ -495,15 +602,16 @@ __global__ void __launch_bounds__(kResetThreads) pack_scene_kernel(const __grid_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     for (int e = blockIdx.x * wpb + warp; e < count; e += gridDim.x * wpb) {
         const int b = first_env + e;
+        const int slot = P.header(b).n(I_GEN) & 1;
         for (int i = lane; i < P.K1; i += 32) {
             NfzRec z; z.x = s.nfz_x[(size_t)e * P.K1 + i]; z.y = s.nfz_y[(size_t)e * P.K1 + i];
             z.radius = s.nfz_radius ? s.nfz_radius[(size_t)e * P.K1 + i] : 0.0;
-            P.nfz[(size_t)b * P.K1 + i] = z;
+            P.nfz[((size_t)slot * P.B + b) * P.K1 + i] = z;
         }
         for (int i = lane; i < P.K2; i += 32) {
             IntRec r; r.x = s.int_x[(size_t)e * P.K2 + i]; r.y = s.int_y[(size_t)e * P.K2 + i];
             r.vx = s.int_vx[(size_t)e * P.K2 + i]; r.vy = s.int_vy[(size_t)e * P.K2 + i];
-            P.intc[(size_t)b * P.K2 + i] = r;
+            P.intc[((size_t)slot * P.B + b) * P.K2 + i] = r;
         }
         __syncwarp();
         double cost_part = 0.0, val_part = 0.0;
@@ -512,10 +620,10 @@ __global__ void __launch_bounds__(kResetThreads) pack_scene_kernel(const __grid_
             UavRec u;
             u.x = s.uav_x[g]; u.y = s.uav_y[g];
             u.load = s.uav_load[g]; u.cost = s.uav_cost[g];
-            finish_uav(P, b, u, s.uav_vx[g], s.uav_vy[g]);
-            P.uav[(size_t)b * P.N + i] = u;
-            P.uav_vel[(size_t)b * P.N + i] = make_double2(s.uav_vx[g], s.uav_vy[g]);
-            P.uav_type[(size_t)b * P.N + i] = s.uav_type ? s.uav_type[g] : 1;
+            finish_uav(P, slot, b, u, s.uav_vx[g], s.uav_vy[g]);
+            P.uav[P.uoff(slot, b) + i] = u;
+            P.uav_vel[P.uoff(slot, b) + i] = make_double2(s.uav_vx[g], s.uav_vy[g]);
+            P.uav_type[P.uoff(slot, b) + i] = s.uav_type ? s.uav_type[g] : 1;
             cost_part += u.cost;
         }
         for (int j = lane; j < P.M; j += 32) {
@@ -526,8 +634,8 @@ __global__ void __launch_bounds__(kResetThreads) pack_scene_kernel(const __grid_
             t.speed = sqrt(vx * vx + vy * vy);
             t.value = s.tgt_value[g];
             t.nh = 1.0; t.nh_pure = 1.0; t.lock_cost = 0.0; t.lock_cnt = 0; t.id = s.tgt_id[g];
-            P.tgt[(size_t)b * P.M + j] = t;
-            P.tgt_vel[(size_t)b * P.M + j] = make_double2(vx, vy);
+            P.tgt[P.toff(slot, b) + j] = t;
+            P.tgt_vel[P.toff(slot, b) + j] = make_double2(vx, vy);
             val_part += t.value;
         }
         const double total_cost = warp_sum(cost_part);
@@ -547,9 +655,10 @@ __global__ void __launch_bounds__(256) score_matrix_kernel(const __grid_constant
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int m = (int)(idx % P.M);
         const size_t bk = idx / P.M;  // b*N + k
-        const size_t b = bk / P.N;
-        const UavRec u = P.uav[bk];
-        const TgtRec *t = P.tgt + b * P.M + m;
+        const int b = (int)(bk / P.N), kk = (int)(bk % P.N);
+        const int slot = P.header(b).n(I_GEN) & 1;
+        const UavRec u = P.uav[P.uoff(slot, b) + kk];
+        const TgtRec *t = P.tgt + P.toff(slot, b) + m;
         const double pd = damage_prob(P, u, t->x, t->y, t->speed);
         if (p_damage) p_damage[idx] = (OutT)pd;
         if (p_final) p_final[idx] = (OutT)(pd * u.p_pen);
@@ -570,12 +679,13 @@ __global__ void __launch_bounds__(256) recompute_kernel(const __grid_constant__ 
     for (int b = wglobal; b < P.B; b += nwarps) {
         double rev = 0.0, cval = 0.0, cost = 0.0;
         int n0 = 0;
-        const TgtRec *T = P.tgt + (size_t)b * P.M;
+        const int slot = P.header(b).n(I_GEN) & 1;
+        const TgtRec *T = P.tgt + P.toff(slot, b);
         for (int j = lane; j < P.M; j += 32) {
             rev += (1.0 - T[j].nh) * T[j].value;
             if (T[j].lock_cnt > 0) { cval += T[j].value; n0 += 1; }
         }
-        const UavRec *U = P.uav + (size_t)b * P.N;
+        const UavRec *U = P.uav + P.uoff(slot, b);
         const int32_t *asg = P.assigned + (size_t)b * P.N;
         for (int i = lane; i < P.N; i += 32) if (asg[i] >= 0) cost += U[i].cost;
         for (int o = 16; o > 0; o >>= 1) {
