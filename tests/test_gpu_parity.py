@@ -317,3 +317,71 @@ def test_error_paths():
     with pytest.raises(KeyError):
         env.load_scene({"uav_x": np.zeros(30)})
     env.close()
+
+
+def test_scene_generator_matches_reference_distributions():
+    """Counter-RNG scene generator vs the reference's _generate_scene (uav_env.py:65-173): moments recorded from
+    400 reference scenes (tests/golden/scene_stats.npz, oracle/gen_golden.py) against 4096 generated scenes,
+    plus the exact structural constraints (type counts, value multiset, permutations)."""
+    ub = _ub()
+    import os
+    from conftest import GOLDEN
+    ref = np.load(os.path.join(GOLDEN, "scene_stats.npz"))
+    B = 4096
+    env = ub.UAVEnvBatched(B, seed=7)
+    env.reset()
+    sc = env.get_scene()
+    speed = np.hypot(sc["uav_vx"], sc["uav_vy"])
+    heading = np.arctan2(sc["uav_vy"], sc["uav_vx"])
+    t2 = sc["uav_type"] == 2
+    got = {"uav_x": sc["uav_x"], "uav_y": sc["uav_y"], "speed1": speed[~t2], "speed2": speed[t2], "heading": heading,
+           "tgt_x": sc["tgt_x"], "tgt_y": sc["tgt_y"], "tgt_vx": sc["tgt_vx"], "nfz_x": sc["nfz_x"], "int_x": sc["int_x"],
+           "int_speed": np.hypot(sc["int_vx"], sc["int_vy"]), "n2": (sc["tgt_value"] == 6.0).sum(1),
+           "value_sum": sc["tgt_value"].sum(1), "id_at_0": sc["tgt_id"][:, 0], "type_at_0": sc["uav_type"][:, 0]}
+    for k, v in got.items():
+        mean, std, lo, hi, n = ref[k]
+        v = np.asarray(v, np.float64).reshape(-1)
+        # means agree within 5 standard errors of the smaller (reference) sample; spreads within 10 %
+        se = std / np.sqrt(n) + std / np.sqrt(v.size) + 1e-12
+        assert abs(v.mean() - mean) <= 5 * se + 1e-9, (k, v.mean(), mean)
+        if std > 0:
+            assert abs(v.std() - std) <= 0.1 * std, (k, v.std(), std)
+        span = hi - lo
+        assert v.min() >= lo - 0.05 * span - 1e-9 and v.max() <= hi + 0.05 * span + 1e-9, k
+    # structure: exactly N//4 type-2 UAVs with cost 1.25 / load 1.0 (uav_env.py:81-102)
+    assert (t2.sum(1) == 30 // 4).all()
+    assert np.array_equal(sc["uav_cost"][t2], np.full(t2.sum(), 1.25)) and (sc["uav_cost"][~t2] == 1.0).all()
+    assert (sc["uav_load"][t2] == 1.0).all() and (sc["uav_load"][~t2] == 0.95).all()
+    # values: M//2 fours, one sixteen, n2 in [1, M - M//2 - 1] sixes, the rest eights (uav_env.py:121-129)
+    vals = sc["tgt_value"]
+    assert ((vals == 4.0).sum(1) == 5).all() and ((vals == 16.0).sum(1) == 1).all()
+    n2 = (vals == 6.0).sum(1)
+    assert n2.min() >= 1 and n2.max() <= 4 and ((vals == 8.0).sum(1) == 4 - n2).all()
+    assert set(np.unique(n2)) == {1, 2, 3, 4}
+    # target list is a permutation of the ids (uav_env.py:173), uniformly: every id shows up at position 0
+    assert (np.sort(sc["tgt_id"], 1) == np.arange(10)).all()
+    assert set(np.unique(sc["tgt_id"][:, 0])) == set(range(10))
+    counts = np.bincount(sc["tgt_id"][:, 0], minlength=10)
+    assert counts.min() > 0.7 * B / 10 and counts.max() < 1.3 * B / 10
+    env.close()
+
+
+def test_pregenerated_scene_flip_equals_inline_generation():
+    """The scheduled regeneration takes the scene from the pre-generation service (slot flip) when it is ready
+    and generates it in place otherwise; both must give the same scene, and the same one on any shard."""
+    ub = _ub()
+    cfg = ub.Config(RESET_EPISODES=1, NUM_UAVS=6, NUM_TARGETS=3)      # regenerate at EVERY episode end: the service
+    a = ub.UAVEnvBatched(96, config=cfg, seed=5)                       # is often late -> both paths are exercised
+    b = ub.UAVEnvBatched(32, config=cfg, seed=5, env_id_base=32)
+    a.reset(); b.reset()
+    for s in range(120):
+        act = a.random_actions(s, action_seed=3)
+        oa, ra, da, _ = a.step(act)
+        ob, rb, db, _ = b.step(act[32:64].clone())
+        assert torch.equal(oa[32:64], ob) and torch.equal(ra[32:64], rb) and torch.equal(da[32:64], db)
+    sa, sb = a.get_scene(32, 32), b.get_scene()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k
+    st = a.get_state()
+    assert (st["scene_index"] >= 5).all()
+    a.close(); b.close()
