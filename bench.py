@@ -196,7 +196,7 @@ def main():
     pool_host = pool.cpu().pin_memory()                        # int64, the dtype Categorical.sample() yields
     pool_host_i8 = pool.cpu().to(torch.int8).pin_memory()      # one byte per binary action
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
-    sweep = torch.zeros(L2_FLUSH_BYTES // 4, dtype=torch.int32, device=dev)
+    sweep = torch.zeros(L2_FLUSH_BYTES // 8, dtype=torch.int64, device=dev)
     sink = torch.zeros(1, dtype=torch.int64, device=dev)
     stream = torch.cuda.current_stream(dev)
 
@@ -251,6 +251,8 @@ def main():
         sampler.start()
     # --- device-resident inputs: the fused kernel alone --------------------------------------------------
     ms_dev = timed(lambda i: env.step(pool[i % POOL]), W, K)
+    # the same bracket around a ~2 us kernel (the action generator): what the protocol itself costs per step
+    ms_floor = timed(lambda i: env.random_actions(i, ACTION_SEED), 3, min(K, 50)) / min(K, 50)
     # --- end to end through the host-buffer entry point ----------------------------------------------------
     ms_e2e = timed(lambda i: env.step_host(pool_host_i8[i % POOL]), W, K)
     ms_e2e_i64 = timed(lambda i: env.step_host(pool_host[i % POOL]), W, K)
@@ -273,7 +275,8 @@ def main():
         surv = survey_bytes(w["M"]) * B / per_launch_s / 1e9
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json"))).get(args.workload)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")))[args.workload][
+                "per_launch_total"]
         except Exception:
             pass
         out = {
@@ -287,6 +290,7 @@ def main():
                        if not args.no_flush else "NOT flushed (diagnostic)",
                        "timing": "CUDA events per step on the launching stream, summed; max over ranks",
                        "pair_evals_per_sec": value, "objective_drift_max_abs": drift,
+                       "bracket_floor_us": 1e3 * ms_floor,
                        "parallelism": "env-sharded x%d, no rollout collective" % world},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "uavk::step_kernel",

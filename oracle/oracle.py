@@ -274,4 +274,8 @@ class OracleBatch:
 
 
 def max_threads():
-    return int(lib().orc_max_threads())
+    """Host threads available to this process (CPU affinity), regardless of OMP_NUM_THREADS (torchrun sets it to 1)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
