@@ -12,9 +12,12 @@ def __getattr__(name):  # torch / CUDA are only touched when the env classes are
     if name in ("UAVEnvBatched", "UAVEnv"):
         from .envs import uav_env
         return getattr(uav_env, name)
-    if name in ("compute_gae", "normalize_advantages"):
+    if name in ("compute_gae", "normalize_advantages", "PPOAgent"):
         from .agents import ppo
         return getattr(ppo, name)
+    if name in ("TransformerActorCritic", "TransformerBlock"):
+        from .networks import transformer_net
+        return getattr(transformer_net, name)
     if name == "load_library":
         from ._capi import load
         return load

@@ -62,3 +62,122 @@ def normalize_advantages(adv, stats):
     if rc != 0:
         raise _capi.UavenvError(rc, "ppo_normalize_advantages failed")
     return adv
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Batched PPO agent (agents/ppo.py:12-183 of the reference, for a [T,B] device-resident rollout)
+
+class PPOAgent:
+    """select_action / store_transition / update with the reference's losses and optimiser
+    (ppo.py:17-22 four Adam groups; :131-153 clipped surrogate, max-of-means clipped value loss, entropy bonus;
+    :160 global-norm clip), over a fixed-horizon rollout of B envs instead of a Python list of single steps.
+
+    Differences forced by batching: the rollout is cut at a fixed horizon T, so V(s_T)
+    bootstraps the last step (the reference only updates at episode ends, where it is 0, ppo.py:77); the
+    minibatch is `minibatch_size` transitions (default T*B/4; cfg.BATCH_SIZE = 64 suits the reference's
+    ~300-sample buffers).  With a process group, gradients are summed over ranks in ONE flat NCCL all-reduce
+    per minibatch (the parameters' .grad are views into one buffer), then averaged, clipped and applied.
+    """
+
+    def __init__(self, num_envs, horizon, device, cfg=None, group=None, minibatch_size=None, seed=0):
+        from ..configs.config import cfg as global_cfg
+        from ..networks.transformer_net import TransformerActorCritic
+        self.cfg = cfg or global_cfg
+        self.device = torch.device(device)
+        self.B, self.T = int(num_envs), int(horizon)
+        self.group = group
+        self.world = torch.distributed.get_world_size(group) if (
+            torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
+        torch.manual_seed(seed)                       # identical initial weights on every rank
+        self.policy = TransformerActorCritic(self.cfg).to(self.device)
+        self.policy_old = TransformerActorCritic(self.cfg).to(self.device)
+        self.policy_old.load_state_dict(self.policy.state_dict())
+        c = self.cfg
+        self.optimizer = torch.optim.Adam([                                       # ppo.py:17-22
+            {"params": self.policy.actor_head.parameters(), "lr": c.LR_ACTOR},
+            {"params": self.policy.actor_net.parameters(), "lr": c.LR_ACTOR},
+            {"params": self.policy.critic_head.parameters(), "lr": c.LR_CRITIC},
+            {"params": self.policy.critic_net.parameters(), "lr": c.LR_CRITIC},
+        ])
+        params = list(self.policy.parameters())
+        self._flat_grad = torch.zeros(sum(p.numel() for p in params), device=self.device)
+        off = 0
+        for p in params:                               # .grad of every parameter is a view of one flat buffer
+            p.grad = self._flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        T, B, dev = self.T, self.B, self.device
+        self.buf_obs = torch.zeros(T, B, c.SEQ_LEN, c.STATE_DIM, device=dev)
+        self.buf_action = torch.zeros(T, B, dtype=torch.int64, device=dev)
+        self.buf_logp = torch.zeros(T, B, device=dev)
+        self.buf_value = torch.zeros(T, B, device=dev)
+        self.buf_reward = torch.zeros(T, B, device=dev)
+        self.buf_done = torch.zeros(T, B, dtype=torch.bool, device=dev)
+        self.t = 0
+        self.minibatch_size = int(minibatch_size) if minibatch_size else max(c.BATCH_SIZE, (T * B) // 4)
+        self._gen = torch.Generator(device=dev).manual_seed(seed + 1 + (
+            torch.distributed.get_rank(group) if self.world > 1 else 0))
+
+    # -- rollout ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def select_action(self, obs):
+        """ppo.py:52-62 for a batch: sample from policy_old, remember (state, action, log-prob, value)."""
+        action, logp, value, _ = self.policy_old.get_action(obs, generator=self._gen)
+        t = self.t
+        self.buf_obs[t].copy_(obs); self.buf_action[t].copy_(action)
+        self.buf_logp[t].copy_(logp); self.buf_value[t].copy_(value.squeeze(-1))
+        return action
+
+    def store_transition(self, reward, done):
+        """ppo.py:64-66"""
+        self.buf_reward[self.t].copy_(reward); self.buf_done[self.t].copy_(done)
+        self.t += 1
+
+    def full(self):
+        return self.t >= self.T
+
+    # -- update -------------------------------------------------------------------------------------------
+    def update(self, last_obs):
+        """ppo.py:68-181.  Returns the mean losses like the reference ({"loss_actor","loss_critic","entropy"})."""
+        c = self.cfg
+        assert self.t == self.T, "update() needs a full rollout"
+        with torch.no_grad():
+            _, last_value = self.policy_old.logits_and_value(last_obs)
+        returns, adv = compute_gae(self.buf_reward, self.buf_value, self.buf_done, last_value.squeeze(-1), c.GAMMA,
+                                   c.GAE_LAMBDA, normalize=True, group=self.group if self.world > 1 else None)
+        n = self.T * self.B
+        obs = self.buf_obs.view(n, c.SEQ_LEN, c.STATE_DIM)
+        act, old_logp, old_val = self.buf_action.view(n), self.buf_logp.view(n), self.buf_value.view(n)
+        returns, adv = returns.view(n), adv.view(n)
+        sums = torch.zeros(3, device=self.device)
+        count = 0
+        mb = min(self.minibatch_size, n)
+        for _ in range(c.K_EPOCHS):                                                # ppo.py:112
+            perm = torch.randperm(n, device=self.device, generator=self._gen)
+            for i in range(0, n - mb + 1, mb):                                     # drop_last=True (:115)
+                idx = perm[i:i + mb]
+                logp, value, entropy = self.policy.evaluate(obs[idx], act[idx])
+                value = value.squeeze(-1)
+                ratio = torch.exp(logp - old_logp[idx])                             # :131
+                a = adv[idx]
+                loss_actor = -torch.min(ratio * a, torch.clamp(ratio, 1 - c.EPS_CLIP, 1 + c.EPS_CLIP) * a).mean()
+                v_clip = old_val[idx] + torch.clamp(value - old_val[idx], -c.EPS_CLIP, c.EPS_CLIP)     # :141
+                r = returns[idx]
+                loss_critic = torch.max(((value - r) ** 2).mean(), ((v_clip - r) ** 2).mean())           # :143-147
+                ent = entropy.mean()
+                loss = loss_actor + 0.5 * loss_critic - 0.01 * ent                  # :153
+                self._flat_grad.zero_()
+                loss.backward()
+                if self.world > 1:                                                  # the only collective of training
+                    torch.distributed.all_reduce(self._flat_grad, group=self.group)
+                    self._flat_grad.div_(self.world)
+                norm = self._flat_grad.norm()                                       # clip_grad_norm_ (:160) on the flat view
+                self._flat_grad.mul_(torch.clamp(c.GRAD_NORM_CLIP / (norm + 1e-6), max=1.0))
+                self.optimizer.step()
+                sums += torch.stack([loss_actor.detach(), loss_critic.detach(), ent.detach()])
+                count += 1
+        self.policy_old.load_state_dict(self.policy.state_dict())                  # ppo.py:172
+        self.t = 0
+        if count == 0:
+            return None
+        m = (sums / count).tolist()
+        return {"loss_actor": m[0], "loss_critic": m[1], "entropy": m[2]}
