@@ -64,3 +64,19 @@ def test_rollout_and_update_run_end_to_end():
     sd_old, sd_new = agent.policy_old.state_dict(), agent.policy.state_dict()
     assert all(torch.equal(sd_old[k], sd_new[k]) for k in sd_new)          # ppo.py:172
     env.close()
+
+
+def test_train_loop_logs_reference_columns_and_saves_reference_loadable_checkpoint(tmp_path):
+    import csv
+    import uavenv_b200 as ub
+    from target_allocation_ppo_transformer_b200 import train as tr
+    hist = tr.train(num_envs=256, horizon=40, iterations=2, log_dir=str(tmp_path), minibatch_size=4096, verbose=False)
+    assert len(hist) == 2 and hist[-1]["samples_per_sec"] > 0 and hist[-1]["Episode"] > 0
+    rows = list(csv.reader(open(tmp_path / "training_stats.csv")))
+    assert rows[0] == ["Episode", "Avg_Reward", "Avg_J_Val", "Max_Coverage", "Q0_Value", "Action1_Ratio",
+                       "Valid_Assign_Rate", "Avg_P_Dmg", "Avg_P_Final", "Loss_Critic", "Loss_Actor", "Entropy"]
+    assert len(rows) == 3
+    sd = torch.load(tmp_path / "final_model.pth", map_location="cpu")
+    fx = np.load(os.path.join(GOLDEN, "policy_net.npz"))
+    assert list(sd.keys()) == [str(k) for k in fx["keys"]]              # the keys the reference network expects
+    assert all(tuple(sd[str(k)].shape) == fx["p::" + str(k)].shape for k in fx["keys"])
