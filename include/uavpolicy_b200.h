@@ -1,0 +1,55 @@
+/*
+ * uavpolicy_b200.h - C ABI of the sm_100a rollout forward of the policy / value network.
+ *
+ * Replaces TransformerActorCritic.get_action (networks/transformer_net.py:96-122) as called once per rollout
+ * step by PPOAgent.select_action (agents/ppo.py:52-62): for a batch of observation windows [B,5,14] it returns
+ * the sampled action, its log-probability, the state value and the policy entropy.  All dense contractions run
+ * on the 5th-generation tensor cores (tcgen05.mma, operands staged by TMA, fp32 accumulators in TMEM; bf16
+ * operands) through CUTLASS/CuTe sm100 collectives instantiated in csrc/policy_gemm.cu; embedding, attention
+ * over the 5-token window, residual + LayerNorm and the MLP heads + sampling are hand-written kernels
+ * (csrc/policy_forward.cu).  Training (backward) stays on the fp32 PyTorch mirror of the network.
+ *
+ * Conventions as in uavenv_b200.h: 0 on success, negative error code otherwise; d_ = device pointers; work is
+ * enqueued on the caller's stream; a handle is not thread-safe; no CPU fallback.
+ */
+#ifndef UAVPOLICY_B200_H
+#define UAVPOLICY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UAVPOLICY_NUM_PARAMS 419267 /* parameters of TransformerActorCritic */
+
+typedef struct uavpolicy uavpolicy_t;
+
+/* max_batch: largest B the handle will be called with (activation workspaces are allocated once). */
+int uavpolicy_create(int32_t device, int32_t max_batch, uavpolicy_t **out);
+int uavpolicy_destroy(uavpolicy_t *p);
+const char *uavpolicy_last_error(const uavpolicy_t *p);
+
+/* Load the network weights from ONE flat fp32 device buffer holding every parameter in
+ * `TransformerActorCritic.named_parameters()` order (== state_dict order of the reference network):
+ *   actor_net.{pos_embedding[5*128], embedding.0.{weight[128*14], bias[128]},
+ *              transformer.layers.0.{self_attn.in_proj_weight[384*128], in_proj_bias[384], out_proj.{weight[128*128],
+ *              bias[128]}, linear1.{weight[256*128], bias[256]}, linear2.{weight[128*256], bias[128]},
+ *              norm1.{weight,bias}[128], norm2.{weight,bias}[128]}},
+ *   actor_head.{0.{weight[64*128], bias[64]}, 2.{weight[2*64], bias[2]}},
+ *   critic_net.{... as actor_net with layers.0 and layers.1}, critic_head.{0.{...}, 2.{weight[64], bias[1]}}
+ * GEMM weights are converted to bf16, everything else stays fp32. */
+int uavpolicy_set_weights(uavpolicy_t *p, const float *d_flat_params, void *stream);
+
+/* get_action for B windows.  d_obs [B,5,14] f32 (rows that are entirely zero are padding, except the newest row:
+ * transformer_net.py:52-54).  The action of env b is drawn from Categorical(softmax(logits_b)) with a counter RNG
+ * keyed (seed, step, env_id_base + b).  Outputs (each may be NULL except d_action): d_action [B] int64,
+ * d_logp [B], d_value [B], d_entropy [B], d_logits [B,2]. */
+int uavpolicy_get_action(uavpolicy_t *p, const float *d_obs, int32_t B, uint64_t seed, uint64_t step,
+                         uint64_t env_id_base, int64_t *d_action, float *d_logp, float *d_value, float *d_entropy,
+                         float *d_logits, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

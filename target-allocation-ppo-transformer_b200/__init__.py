@@ -18,6 +18,9 @@ def __getattr__(name):  # torch / CUDA are only touched when the env classes are
     if name in ("TransformerActorCritic", "TransformerBlock"):
         from .networks import transformer_net
         return getattr(transformer_net, name)
+    if name == "FusedPolicyForward":
+        from .networks.fused_forward import FusedPolicyForward
+        return FusedPolicyForward
     if name == "load_library":
         from ._capi import load
         return load

@@ -13,16 +13,38 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libuavenv_b200.so")
+LIB_PATH = os.path.join(LIB_DIR, "libuavenv_b200.so")            # the env + GAE (include/uavenv_b200.h)
+POLICY_LIB_PATH = os.path.join(LIB_DIR, "libuavpolicy_b200.so")   # the policy rollout forward (include/uavpolicy_b200.h)
 OBJ_DIR = os.path.join(LIB_DIR, "obj")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
-# (source, extra flags).  The env kernels reproduce the reference's fp64 operation order: no FMA contraction.
-UNITS = [
-    ("uavenv_capi.cu", ["-fmad=false"]),
-    ("ppo_gae.cu", []),
-]
+
+
+def _cutlass_includes():
+    """CUTLASS / CuTe header trees vendored in site-packages (no /opt/cutlass in this image)."""
+    import site
+    for sp in site.getsitepackages():
+        for rel in ("flashinfer/data/cutlass", "tilelang/3rdparty/cutlass"):
+            base = os.path.join(sp, rel)
+            if os.path.isfile(os.path.join(base, "include", "cutlass", "gemm", "collective", "builders",
+                                           "sm100_umma_builder.inl")):
+                return ["-I", os.path.join(base, "include"), "-I", os.path.join(base, "tools", "util", "include")]
+    raise RuntimeError("no CUTLASS header tree with sm100 collectives found")
+
+
+# library -> [(source, extra flags, headers it depends on)].  The env kernels reproduce the reference's fp64
+# operation order: no FMA contraction there.
+LIBS = {
+    LIB_PATH: [
+        ("uavenv_capi.cu", ["-fmad=false"], ["uavenv_device.cuh", "uavenv_kernels.cuh", "../../include/uavenv_b200.h"]),
+        ("ppo_gae.cu", [], ["../../include/uavenv_b200.h"]),
+    ],
+    POLICY_LIB_PATH: [
+        ("policy_gemm.cu", "CUTLASS", ["policy_gemm.cuh"]),
+        ("policy_forward.cu", [], ["policy_gemm.cuh", "../../include/uavpolicy_b200.h"]),
+    ],
+}
 
 
 def _nvcc():
@@ -32,44 +54,53 @@ def _nvcc():
     raise RuntimeError("nvcc not found: the CUDA extension cannot be built (there is no CPU fallback)")
 
 
-def sources():
-    deps = [os.path.join(ROOT, "include", "uavenv_b200.h")]
-    for f in sorted(os.listdir(CSRC)):
-        if f.endswith((".cu", ".cuh", ".h")):
-            deps.append(os.path.join(CSRC, f))
-    return deps
+def _stale(target, deps):
+    if not os.path.isfile(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
 
 
-def up_to_date():
-    if not os.path.isfile(LIB_PATH):
-        return False
-    t = os.path.getmtime(LIB_PATH)
-    return all(os.path.getmtime(s) <= t for s in sources())
+def _unit_deps(src, headers):
+    return [os.path.join(CSRC, src)] + [os.path.normpath(os.path.join(CSRC, h)) for h in headers]
 
 
-def build(force=False, verbose=False):
-    if not force and up_to_date():
-        return LIB_PATH
-    nvcc = _nvcc()
-    os.makedirs(OBJ_DIR, exist_ok=True)
-    objs = []
-    for src, extra in UNITS:
-        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
-        extra = extra + os.environ.get("UAVENV_EXTRA_NVCC_FLAGS", "").split()
-        cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + [
-            "-c", os.path.join(CSRC, src), "-o", obj]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if verbose or r.returncode != 0:
-            sys.stderr.write(r.stdout + r.stderr)
+def up_to_date(lib=LIB_PATH):
+    """True when `lib` exists and is not older than any source it is built from."""
+    deps = []
+    for src, _, headers in LIBS[lib]:
+        deps += _unit_deps(src, headers)
+    return not _stale(lib, deps)
+
+
+def build(force=False, verbose=False, lib=None):
+    """Compile what is stale.  lib=None builds both libraries; returns the env library's path."""
+    for target in ([lib] if lib else list(LIBS)):
+        if not force and up_to_date(target):
+            continue
+        nvcc = _nvcc()
+        os.makedirs(OBJ_DIR, exist_ok=True)
+        objs = []
+        for src, extra, headers in LIBS[target]:
+            obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+            objs.append(obj)
+            if not force and not _stale(obj, _unit_deps(src, headers)):
+                continue
+            flags = (_cutlass_includes() + ["--expt-relaxed-constexpr"]) if extra == "CUTLASS" else list(extra)
+            flags += os.environ.get("UAVENV_EXTRA_NVCC_FLAGS", "").split()
+            cmd = [nvcc] + ARCH + COMMON + flags + (["-Xptxas", "-v"] if verbose else []) + [
+                "-c", os.path.join(CSRC, src), "-o", obj]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if verbose or r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+            if r.returncode != 0:
+                raise RuntimeError("nvcc failed on %s" % src)
+        tmp = target + ".tmp"
+        r = subprocess.run([nvcc] + ARCH + ["-shared", "-o", tmp] + objs, capture_output=True, text=True)
         if r.returncode != 0:
-            raise RuntimeError("nvcc failed on %s" % src)
-        objs.append(obj)
-    tmp = LIB_PATH + ".tmp"
-    r = subprocess.run([nvcc] + ARCH + ["-shared", "-o", tmp] + objs, capture_output=True, text=True)
-    if r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc link failed")
-    os.replace(tmp, LIB_PATH)
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("nvcc link failed")
+        os.replace(tmp, target)
     return LIB_PATH
 
 

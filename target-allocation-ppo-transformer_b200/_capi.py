@@ -126,3 +126,33 @@ def check(rc, handle=None):
     if rc != 0:
         msg = load().uavenv_last_error(handle)
         raise UavenvError(rc, msg.decode() if msg else "(no message)")
+
+
+# ---- policy rollout forward (include/uavpolicy_b200.h, lib/libuavpolicy_b200.so) ---------------------------------
+_policy_lib = None
+
+
+def load_policy():
+    """Load (building first if stale) the tcgen05 policy-forward library.  Raises on any failure."""
+    global _policy_lib
+    if _policy_lib is not None:
+        return _policy_lib
+    path = _build.POLICY_LIB_PATH
+    if not _build.up_to_date(path):
+        try:
+            _build.build(lib=path)
+        except Exception as exc:
+            if not os.path.isfile(path):
+                raise ImportError("libuavpolicy_b200.so is missing and could not be built (%s)" % exc) from exc
+    L = C.CDLL(path)
+    vp, i32, u64 = C.c_void_p, C.c_int32, C.c_uint64
+    L.uavpolicy_create.argtypes = [i32, i32, C.POINTER(vp)]
+    L.uavpolicy_destroy.argtypes = [vp]
+    L.uavpolicy_last_error.argtypes = [vp]
+    L.uavpolicy_last_error.restype = C.c_char_p
+    L.uavpolicy_set_weights.argtypes = [vp, vp, vp]
+    L.uavpolicy_get_action.argtypes = [vp, vp, i32, u64, u64, u64, vp, vp, vp, vp, vp, vp]
+    for name in ("uavpolicy_create", "uavpolicy_destroy", "uavpolicy_set_weights", "uavpolicy_get_action"):
+        getattr(L, name).restype = C.c_int
+    _policy_lib = L
+    return L

@@ -1,0 +1,14 @@
+// policy_gemm.cuh - the dense contraction of the policy forward: D[M,N] = act(A[M,K] W[N,K]^T + bias[N]) in bf16
+// with fp32 accumulation on tcgen05 (instantiated in policy_gemm.cu from CUTLASS/CuTe sm100 collectives).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace uavp {
+// A: bf16, row stride lda elements (lda % 8 == 0); W: bf16 [N,K] row-major; D: bf16 [M,N] row-major; bias fp32 [N].
+// relu != 0 applies max(0, .).  Returns 0 or a negative code.  workspace: device scratch of workspace_bytes.
+int gemm_bias_act(const void *A, int64_t lda, const void *W, const float *bias, void *D, int M, int N, int K, int relu,
+                  void *workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t gemm_workspace_bytes();
+}  // namespace uavp

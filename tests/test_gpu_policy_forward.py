@@ -1,0 +1,83 @@
+"""tcgen05 rollout forward (csrc/policy_forward.cu) against the fp32 PyTorch network with the reference's weights
+(tests/golden/policy_net.npz).  bf16 operands: logits / values within 3e-2 absolute, log-probs within 2e-2;
+sampling follows the returned probabilities; the library has no CPU fallback."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+import uavenv_b200  # noqa: F401  (registers the package under an importable name)
+
+pytestmark = pytest.mark.gpu
+
+
+def _net():
+    import uavenv_b200 as ub
+    fx = np.load(os.path.join(GOLDEN, "policy_net.npz"))
+    net = ub.TransformerActorCritic().cuda()
+    net.load_state_dict({str(k): torch.from_numpy(fx["p::" + str(k)]) for k in fx["keys"]})
+    return net.eval(), fx
+
+
+def test_forward_matches_fp32_network_and_reference_golden():
+    from target_allocation_ppo_transformer_b200.networks.fused_forward import FusedPolicyForward
+    net, fx = _net()
+    obs = torch.from_numpy(fx["obs"]).cuda()
+    fused = FusedPolicyForward(256, "cuda")
+    fused.sync(net)
+    a, lp, v, e = fused.get_action(obs, step=0)
+    logits = fused.logits[: obs.shape[0]]
+    with torch.no_grad():
+        ref_logits, ref_v = net.logits_and_value(obs)
+    assert float((logits - ref_logits).abs().max()) < 3e-2
+    assert float((v - ref_v).abs().max()) < 3e-2 * max(1.0, float(ref_v.abs().max()))
+    # against the values recorded from the UNMODIFIED reference network
+    assert float((logits.cpu() - torch.from_numpy(fx["logits"])).abs().max()) < 3e-2
+    assert float((v.cpu() - torch.from_numpy(fx["value"])).abs().max()) < 3e-2 * max(1.0, float(np.abs(fx["value"]).max()))
+    ref_lp = torch.log_softmax(ref_logits, -1).gather(-1, a[:, None]).squeeze(-1)
+    assert float((lp - ref_lp).abs().max()) < 2e-2
+    p = torch.softmax(logits, -1)
+    assert torch.allclose(e, -(p * p.log()).sum(-1), atol=1e-5)
+    assert set(a.tolist()) <= {0, 1}
+    fused.close()
+
+
+def test_padding_rows_and_batch_tails():
+    """Episode starts (leading zero rows are masked keys) and batch sizes that are not tile multiples."""
+    from target_allocation_ppo_transformer_b200.networks.fused_forward import FusedPolicyForward
+    net, _ = _net()
+    fused = FusedPolicyForward(1000, "cuda")
+    fused.sync(net)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for B in (1, 7, 129, 1000):
+        obs = torch.rand(B, 5, 14, device="cuda", generator=g)
+        obs[:, :, 13] = 1.0
+        for b in range(B):
+            obs[b, : b % 5] = 0.0
+        _, _, v, _ = fused.get_action(obs, step=3)
+        with torch.no_grad():
+            ref_logits, ref_v = net.logits_and_value(obs)
+        assert float((fused.logits[:B] - ref_logits).abs().max()) < 3e-2
+        assert float((v - ref_v).abs().max()) < 3e-2 * max(1.0, float(ref_v.abs().max()))
+    fused.close()
+
+
+def test_sampling_is_counter_based_and_follows_the_probabilities():
+    from target_allocation_ppo_transformer_b200.networks.fused_forward import FusedPolicyForward
+    net, _ = _net()
+    with torch.no_grad():                       # make the policy opinionated so p1 is far from 1/2
+        net.actor_head[2].bias.copy_(torch.tensor([0.0, 1.0]))
+    B = 8192
+    fused = FusedPolicyForward(B, "cuda", seed=11)
+    fused.sync(net)
+    obs = torch.rand(B, 5, 14, device="cuda")
+    a1 = fused.get_action(obs, step=5)[0].clone()
+    a2 = fused.get_action(obs, step=5)[0].clone()
+    a3 = fused.get_action(obs, step=6)[0].clone()
+    assert torch.equal(a1, a2) and not torch.equal(a1, a3)           # same (seed, step, env) -> same draw
+    p1 = torch.softmax(fused.logits[:B], -1)[:, 1]
+    assert abs(float(a3.float().mean()) - float(p1.mean())) < 4 * 0.5 / np.sqrt(B)
+    fused.close()
