@@ -79,7 +79,8 @@ class PPOAgent:
     per minibatch (the parameters' .grad are views into one buffer), then averaged, clipped and applied.
     """
 
-    def __init__(self, num_envs, horizon, device, cfg=None, group=None, minibatch_size=None, seed=0):
+    def __init__(self, num_envs, horizon, device, cfg=None, group=None, minibatch_size=None, seed=0,
+                 fused_rollout=False, env_id_base=0):
         from ..configs.config import cfg as global_cfg
         from ..networks.transformer_net import TransformerActorCritic
         self.cfg = cfg or global_cfg
@@ -116,12 +117,23 @@ class PPOAgent:
         self.minibatch_size = int(minibatch_size) if minibatch_size else max(c.BATCH_SIZE, (T * B) // 4)
         self._gen = torch.Generator(device=dev).manual_seed(seed + 1 + (
             torch.distributed.get_rank(group) if self.world > 1 else 0))
+        # rollout forward on the tensor cores (csrc/policy_forward.cu) instead of the fp32 PyTorch mirror
+        self.fused = None
+        self._rollout_step = 0
+        if fused_rollout:
+            from ..networks.fused_forward import FusedPolicyForward
+            self.fused = FusedPolicyForward(self.B, dev, seed=seed, env_id_base=env_id_base)
+            self.fused.sync(self.policy_old)
 
     # -- rollout ------------------------------------------------------------------------------------------
     @torch.no_grad()
     def select_action(self, obs):
         """ppo.py:52-62 for a batch: sample from policy_old, remember (state, action, log-prob, value)."""
-        action, logp, value, _ = self.policy_old.get_action(obs, generator=self._gen)
+        if self.fused is not None:
+            action, logp, value, _ = self.fused.get_action(obs, self._rollout_step)
+            self._rollout_step += 1
+        else:
+            action, logp, value, _ = self.policy_old.get_action(obs, generator=self._gen)
         t = self.t
         self.buf_obs[t].copy_(obs); self.buf_action[t].copy_(action)
         self.buf_logp[t].copy_(logp); self.buf_value[t].copy_(value.squeeze(-1))
@@ -176,6 +188,8 @@ class PPOAgent:
                 sums += torch.stack([loss_actor.detach(), loss_critic.detach(), ent.detach()])
                 count += 1
         self.policy_old.load_state_dict(self.policy.state_dict())                  # ppo.py:172
+        if self.fused is not None:
+            self.fused.sync(self.policy_old)
         self.t = 0
         if count == 0:
             return None

@@ -23,7 +23,7 @@ CSV_COLUMNS = ["Episode", "Avg_Reward", "Avg_J_Val", "Max_Coverage", "Q0_Value",
 
 
 def train(num_envs=16384, horizon=32, iterations=10, cfg=None, log_dir=None, seed=None, minibatch_size=None,
-          save_every=0, verbose=True):
+          save_every=0, verbose=True, fused_rollout=True):
     """Returns a list of per-iteration stat dicts (rank 0 also writes training_stats.csv / checkpoints)."""
     cfg = cfg or global_cfg
     rank, local_rank, world = parallel.init()
@@ -31,7 +31,8 @@ def train(num_envs=16384, horizon=32, iterations=10, cfg=None, log_dir=None, see
     torch.cuda.set_device(device)
     seed = cfg.SEED if seed is None else seed
     env = UAVEnvBatched(num_envs, device=device, seed=seed, env_id_base=rank * num_envs, config=cfg)
-    agent = PPOAgent(num_envs, horizon, device, cfg=cfg, minibatch_size=minibatch_size, seed=seed)
+    agent = PPOAgent(num_envs, horizon, device, cfg=cfg, minibatch_size=minibatch_size, seed=seed,
+                     fused_rollout=fused_rollout, env_id_base=rank * num_envs)
     writer = fh = None
     if rank == 0 and log_dir:
         os.makedirs(log_dir, exist_ok=True)

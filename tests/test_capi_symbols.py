@@ -12,19 +12,36 @@ from conftest import ROOT
 import uavenv_b200 as ub
 
 
-def _declared():
-    text = open(os.path.join(ROOT, "include", "uavenv_b200.h")).read()
+def _declared(header="uavenv_b200.h", prefix="uavenv|ppo"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    names = set(re.findall(r"\b((?:uavenv|ppo)_[a-z0-9_]+)\s*\(", text))
-    assert len(names) >= 18
-    return sorted(names)
+    return sorted(set(re.findall(r"\b((?:%s)_[a-z0-9_]+)\s*\(" % prefix, text)))
 
 
 def test_library_exports_every_declared_symbol():
     L = ub.load_library()
-    for name in _declared():
+    names = _declared()
+    assert len(names) >= 20
+    for name in names:
         assert hasattr(L, name), "libuavenv_b200.so does not export %s" % name
     assert L.uavenv_abi_version() == 1
+
+
+def test_policy_library_exports_every_declared_symbol_and_is_tcgen05():
+    import subprocess
+    from target_allocation_ppo_transformer_b200 import _build, _capi
+    L = _capi.load_policy()
+    names = _declared("uavpolicy_b200.h", "uavpolicy")
+    assert len(names) == 5
+    for name in names:
+        assert hasattr(L, name), "libuavpolicy_b200.so does not export %s" % name
+    sass = subprocess.run(["cuobjdump", "-sass", _build.POLICY_LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass and "UTMALDG" in sass          # tcgen05.mma and TMA loads (B200_PROFILING.md)
+    h = C.c_void_p()
+    assert L.uavpolicy_create(0, 0, C.byref(h)) == -1       # argument validation without a GPU
+    import torch
+    if not torch.cuda.is_available():
+        assert L.uavpolicy_create(0, 64, C.byref(h)) == -2 and b"no CPU fallback" in L.uavpolicy_last_error(None)
 
 
 def test_library_is_sm100a_only():

@@ -80,3 +80,27 @@ def test_train_loop_logs_reference_columns_and_saves_reference_loadable_checkpoi
     fx = np.load(os.path.join(GOLDEN, "policy_net.npz"))
     assert list(sd.keys()) == [str(k) for k in fx["keys"]]              # the keys the reference network expects
     assert all(tuple(sd[str(k)].shape) == fx["p::" + str(k)].shape for k in fx["keys"])
+
+
+def test_fused_rollout_forward_drives_training():
+    """The tcgen05 rollout forward inside the PPO loop: buffers hold its actions / log-probs / values, the update
+    runs on the fp32 mirror, the weights are re-synchronised afterwards."""
+    import uavenv_b200 as ub
+    B, T = 384, 12
+    env = ub.UAVEnvBatched(B, seed=2)
+    agent = ub.PPOAgent(B, T, "cuda", minibatch_size=1152, fused_rollout=True)
+    obs = env.reset()
+    while not agent.full():
+        a = agent.select_action(obs)
+        # log-prob / value stored by the fused forward agree with the fp32 network on the same states
+        with torch.no_grad():
+            lp, v, _ = agent.policy_old.evaluate(obs, a)
+        assert float((lp - agent.buf_logp[agent.t]).abs().max()) < 2e-2
+        assert float((v.squeeze(-1) - agent.buf_value[agent.t]).abs().max()) < 5e-2
+        obs, reward, done, _ = env.step(a)
+        agent.store_transition(reward, done)
+    stats = agent.update(obs)
+    assert stats is not None and np.isfinite(stats["loss_critic"])
+    a2 = agent.select_action(obs)                       # runs with the re-synchronised weights
+    assert set(a2.tolist()) <= {0, 1}
+    env.close()
