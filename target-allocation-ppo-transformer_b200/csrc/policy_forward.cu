@@ -39,7 +39,7 @@ struct BlockW {
     LayerW layer[2];
     int layers;
 };
-struct HeadW { const float *w1, *b1, *w2, *b2; };
+struct HeadW { const __nv_bfloat16 *w1; const float *b1, *w2, *b2; };  // w1 [64,128] bf16 (GEMM), the rest fp32
 
 // ------------------------------------------------------------------------------------------------ kernels
 
@@ -49,36 +49,46 @@ __global__ void f32_to_bf16_kernel(const float *__restrict__ src, __nv_bfloat16 
 }
 
 // embedding of both nets: E = relu(obs W^T + b) + pos (transformer_net.py:24-30,57-59) and the key-padding mask
-// (rows that are all zero, newest row never: :52-54).  One CTA = 16 tokens, thread = output feature.
-constexpr int kEmbTok = 16;
+// (rows that are all zero, newest row never: :52-54).  One CTA = 64 tokens; thread = (net, feature pair), so a warp
+// stores 128 contiguous bytes per token.
+constexpr int kEmbTok = 64;
 __global__ void __launch_bounds__(D) embed_kernel(const float *__restrict__ obs, int R, BlockW a, BlockW c,
                                                   __nv_bfloat16 *__restrict__ Ea, __nv_bfloat16 *__restrict__ Ec,
                                                   uint8_t *__restrict__ pad) {
     __shared__ float s_obs[kEmbTok][F];
-    const int t0 = blockIdx.x * kEmbTok, d = threadIdx.x;
+    const int t0 = blockIdx.x * kEmbTok;
     for (int i = threadIdx.x; i < kEmbTok * F; i += D) {
         const int t = t0 + i / F;
         s_obs[i / F][i % F] = t < R ? obs[(size_t)t * F + i % F] : 0.0f;
     }
     __syncthreads();
-    if (d < kEmbTok && t0 + d < R) {
+    if (threadIdx.x < kEmbTok && t0 + threadIdx.x < R) {
         float sum = 0.0f;
-        for (int j = 0; j < F; ++j) sum += fabsf(s_obs[d][j]);
-        pad[t0 + d] = (sum == 0.0f && (t0 + d) % S != S - 1) ? 1 : 0;
+        for (int j = 0; j < F; ++j) sum += fabsf(s_obs[threadIdx.x][j]);
+        pad[t0 + threadIdx.x] = (sum == 0.0f && (t0 + threadIdx.x) % S != S - 1) ? 1 : 0;
     }
-    float wa[F], wc[F];
+    const bool critic = threadIdx.x >= D / 2;
+    const int d = (threadIdx.x % (D / 2)) * 2;                    // features d, d+1
+    const BlockW &w = critic ? c : a;
+    __nv_bfloat16 *E = critic ? Ec : Ea;
+    float w0[F], w1[F];
 #pragma unroll
-    for (int j = 0; j < F; ++j) { wa[j] = a.emb_w[d * F + j]; wc[j] = c.emb_w[d * F + j]; }
-    const float ba = a.emb_b[d], bc = c.emb_b[d];
+    for (int j = 0; j < F; ++j) { w0[j] = w.emb_w[d * F + j]; w1[j] = w.emb_w[(d + 1) * F + j]; }
+    const float b0 = w.emb_b[d], b1 = w.emb_b[d + 1];
+    float p0[S], p1[S];
+#pragma unroll
+    for (int p = 0; p < S; ++p) { p0[p] = w.pos[p * D + d]; p1[p] = w.pos[p * D + d + 1]; }
     for (int i = 0; i < kEmbTok; ++i) {
         const int t = t0 + i;
         if (t >= R) break;
-        float xa = ba, xc = bc;
+        float x0 = b0, x1 = b1;
 #pragma unroll
-        for (int j = 0; j < F; ++j) { xa = fmaf(wa[j], s_obs[i][j], xa); xc = fmaf(wc[j], s_obs[i][j], xc); }
+        for (int j = 0; j < F; ++j) { x0 = fmaf(w0[j], s_obs[i][j], x0); x1 = fmaf(w1[j], s_obs[i][j], x1); }
         const int p = t % S;
-        Ea[(size_t)t * D + d] = __float2bfloat16(fmaxf(xa, 0.0f) + a.pos[p * D + d]);
-        Ec[(size_t)t * D + d] = __float2bfloat16(fmaxf(xc, 0.0f) + c.pos[p * D + d]);
+        float q0 = p0[0], q1 = p1[0];
+#pragma unroll
+        for (int k = 1; k < S; ++k) if (p == k) { q0 = p0[k]; q1 = p1[k]; }
+        *reinterpret_cast<__nv_bfloat162 *>(E + (size_t)t * D + d) = __floats2bfloat162_rn(fmaxf(x0, 0.0f) + q0, fmaxf(x1, 0.0f) + q1);
     }
 }
 
@@ -200,67 +210,45 @@ __device__ __forceinline__ uint4 philox4x32(uint32_t k0, uint32_t k1, uint32_t c
     return make_uint4(c0, c1, c2, c3);
 }
 
-// both heads (transformer_net.py:78-91): relu(W1 z + b1) -> W2 .. ; softmax, Categorical sample (counter RNG),
-// log-prob, entropy, value (:116-122).  One warp per sample; W1 of both heads staged in shared memory.
-__global__ void __launch_bounds__(256) heads_kernel(const __nv_bfloat16 *__restrict__ Za, const __nv_bfloat16 *__restrict__ Zc,
-                                                    HeadW ha, HeadW hc, int B, uint32_t k0, uint32_t k1, uint64_t step,
-                                                    uint64_t env_base, int64_t *__restrict__ action, float *__restrict__ logp,
-                                                    float *__restrict__ value, float *__restrict__ entropy,
-                                                    float *__restrict__ logits_out) {
-    extern __shared__ float s_w[];               // [2][64][129] padded rows
-    float *wa = s_w, *wc = s_w + HID * (D + 1);
-    for (int i = threadIdx.x; i < HID * D; i += blockDim.x) {
-        wa[(i / D) * (D + 1) + i % D] = ha.w1[i];
-        wc[(i / D) * (D + 1) + i % D] = hc.w1[i];
+// head outputs (transformer_net.py:78-91 second layers; the first layers 128 -> 64 + ReLU ran as tensor-core GEMMs):
+// logits = W2a ha + b, value = W2c hc + b; softmax, Categorical sample (counter RNG), log-prob, entropy (:116-122).
+// One thread per sample.
+__global__ void __launch_bounds__(256) heads_out_kernel(const __nv_bfloat16 *__restrict__ Ha, const __nv_bfloat16 *__restrict__ Hc,
+                                                        HeadW ha, HeadW hc, int B, uint32_t k0, uint32_t k1, uint64_t step,
+                                                        uint64_t env_base, int64_t *__restrict__ action,
+                                                        float *__restrict__ logp, float *__restrict__ value,
+                                                        float *__restrict__ entropy, float *__restrict__ logits_out) {
+    __shared__ float s_w[3][HID];
+    for (int i = threadIdx.x; i < HID; i += blockDim.x) {
+        s_w[0][i] = ha.w2[i]; s_w[1][i] = ha.w2[HID + i]; s_w[2][i] = hc.w2[i];
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    for (int b = blockIdx.x * wpb + warp; b < B; b += gridDim.x * wpb) {
-        float za[4], zc[4];
-        {
-            const uint2 a = *reinterpret_cast<const uint2 *>(Za + (size_t)b * D + lane * 4);
-            const uint2 c = *reinterpret_cast<const uint2 *>(Zc + (size_t)b * D + lane * 4);
-            const __nv_bfloat162 a0 = *reinterpret_cast<const __nv_bfloat162 *>(&a.x), a1 = *reinterpret_cast<const __nv_bfloat162 *>(&a.y);
-            const __nv_bfloat162 c0 = *reinterpret_cast<const __nv_bfloat162 *>(&c.x), c1 = *reinterpret_cast<const __nv_bfloat162 *>(&c.y);
-            za[0] = __low2float(a0); za[1] = __high2float(a0); za[2] = __low2float(a1); za[3] = __high2float(a1);
-            zc[0] = __low2float(c0); zc[1] = __high2float(c0); zc[2] = __low2float(c1); zc[3] = __high2float(c1);
-        }
-        // hidden unit j = lane, lane+32: full dot products, z broadcast lane by lane through shuffles
-        float ha0 = ha.b1[lane], ha1 = ha.b1[lane + 32], hc0 = hc.b1[lane], hc1 = hc.b1[lane + 32];
-#pragma unroll 4
-        for (int src = 0; src < 32; ++src) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float l0 = ha.b2[0], l1 = ha.b2[1], vv = hc.b2[0];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float va = __shfl_sync(0xffffffffu, za[e], src), vc = __shfl_sync(0xffffffffu, zc[e], src);
-                const int dcol = src * 4 + e;
-                ha0 = fmaf(wa[lane * (D + 1) + dcol], va, ha0); ha1 = fmaf(wa[(lane + 32) * (D + 1) + dcol], va, ha1);
-                hc0 = fmaf(wc[lane * (D + 1) + dcol], vc, hc0); hc1 = fmaf(wc[(lane + 32) * (D + 1) + dcol], vc, hc1);
-            }
-        }
-        ha0 = fmaxf(ha0, 0.0f); ha1 = fmaxf(ha1, 0.0f); hc0 = fmaxf(hc0, 0.0f); hc1 = fmaxf(hc1, 0.0f);
-        float l0 = ha.w2[lane] * ha0 + ha.w2[lane + 32] * ha1;
-        float l1 = ha.w2[HID + lane] * ha0 + ha.w2[HID + lane + 32] * ha1;
-        float vv = hc.w2[lane] * hc0 + hc.w2[lane + 32] * hc1;
-        for (int o = 16; o > 0; o >>= 1) {
-            l0 += __shfl_xor_sync(0xffffffffu, l0, o);
-            l1 += __shfl_xor_sync(0xffffffffu, l1, o);
-            vv += __shfl_xor_sync(0xffffffffu, vv, o);
-        }
-        if (lane == 0) {
-            l0 += ha.b2[0]; l1 += ha.b2[1]; vv += hc.b2[0];
-            const float m = fmaxf(l0, l1), e0 = expf(l0 - m), e1 = expf(l1 - m), lse = m + logf(e0 + e1);
-            const float lp0 = l0 - lse, lp1 = l1 - lse, p0 = expf(lp0), p1 = expf(lp1);
-            const uint64_t env = env_base + (uint64_t)b;
-            const uint4 r = philox4x32(k0, k1, (uint32_t)env, (uint32_t)step, (uint32_t)(step >> 32), 0x00B01C70u ^ (uint32_t)(env >> 32));
-            const float u = (float)(r.x >> 8) * (1.0f / 16777216.0f);   // uniform [0,1)
-            const int a = u < p1 ? 1 : 0;                               // Categorical(probs).sample(), :118-120
-            action[b] = a;
-            if (logp) logp[b] = a ? lp1 : lp0;
-            if (value) value[b] = vv;
-            if (entropy) entropy[b] = -(p0 * lp0 + p1 * lp1);
-            if (logits_out) { logits_out[2 * b] = l0; logits_out[2 * b + 1] = l1; }
+    for (int c = 0; c < HID / DH; ++c) {
+        float xa[DH], xc[DH];
+        load16(Ha + (size_t)b * HID + c * DH, xa);
+        load16(Hc + (size_t)b * HID + c * DH, xc);
+#pragma unroll
+        for (int e = 0; e < DH; ++e) {
+            l0 = fmaf(s_w[0][c * DH + e], xa[e], l0);
+            l1 = fmaf(s_w[1][c * DH + e], xa[e], l1);
+            vv = fmaf(s_w[2][c * DH + e], xc[e], vv);
         }
     }
+    const float m = fmaxf(l0, l1), e0 = expf(l0 - m), e1 = expf(l1 - m), lse = m + logf(e0 + e1);
+    const float lp0 = l0 - lse, lp1 = l1 - lse, p0 = expf(lp0), p1 = expf(lp1);
+    const uint64_t env = env_base + (uint64_t)b;
+    const uint4 r = philox4x32(k0, k1, (uint32_t)env, (uint32_t)step, (uint32_t)(step >> 32), 0x00B01C70u ^ (uint32_t)(env >> 32));
+    const float u = (float)(r.x >> 8) * (1.0f / 16777216.0f);   // uniform [0,1)
+    const int a = u < p1 ? 1 : 0;                               // Categorical(probs).sample(), :118-120
+    action[b] = a;
+    if (logp) logp[b] = a ? lp1 : lp0;
+    if (value) value[b] = vv;
+    if (entropy) entropy[b] = -(p0 * lp0 + p1 * lp1);
+    if (logits_out) { logits_out[2 * b] = l0; logits_out[2 * b + 1] = l1; }
 }
 
 }  // namespace
@@ -329,8 +317,8 @@ static size_t map_block(BlockW &b, int layers, const float *w32, const __nv_bflo
     }
     return off;
 }
-static size_t map_head(HeadW &h, int outs, const float *w32, size_t off) {
-    h.w1 = w32 + off; off += HID * D;
+static size_t map_head(HeadW &h, int outs, const float *w32, const __nv_bfloat16 *w16, size_t off) {
+    h.w1 = w16 + off; off += HID * D;
     h.b1 = w32 + off; off += HID;
     h.w2 = w32 + off; off += outs * HID;
     h.b2 = w32 + off; off += outs;
@@ -364,14 +352,14 @@ extern "C" int uavpolicy_create(int32_t device, int32_t max_batch, uavpolicy_t *
     if (e == cudaSuccess) e = palloc(p, &p->Hs, B * FF);
     if (e == cudaSuccess) e = palloc(p, &p->pad, R);
     if (e == cudaSuccess) { void *ws = nullptr; e = cudaMalloc(&ws, uavp::gemm_workspace_bytes()); if (e == cudaSuccess) { p->allocs.push_back(ws); p->gemm_ws = ws; } }
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * HID * (D + 1) * (int)sizeof(float));
     if (e != cudaSuccess) { pfail(p, -2, "uavpolicy_create: %s", cudaGetErrorString(e)); return bail(-2); }
     size_t off = map_block(p->actor, 1, p->w32, p->w16, 0);
-    off = map_head(p->actor_head, NACT, p->w32, off);
+    // (the actor head's first layer starts at element 135040: 16 B aligned in the first bf16 copy)
+    off = map_head(p->actor_head, NACT, p->w32, p->w16, off);
     // second bf16 copy, shifted so that element `off` (the critic block's first parameter) lands on a multiple of 8
     p->w16_critic = p->w16 + ((size_t)UAVPOLICY_NUM_PARAMS + 15) / 8 * 8 + (8 - off % 8) % 8;
     off = map_block(p->critic, 2, p->w32, p->w16_critic, off);
-    off = map_head(p->critic_head, 1, p->w32, off);
+    off = map_head(p->critic_head, 1, p->w32, p->w16_critic, off);   // 267520 elements later: still a multiple of 8
     if (off != (size_t)UAVPOLICY_NUM_PARAMS) { pfail(p, -1, "internal: parameter layout mismatch"); return bail(-1); }
     *out = p;
     return 0;
@@ -453,10 +441,13 @@ extern "C" int uavpolicy_get_action(uavpolicy_t *p, const float *d_obs, int32_t 
     full_layer(c, p->critic.layer[0], p->Ec, B, p->X1);             // critic: 2 layers
     last_layer(c, p->critic.layer[1], p->X1, B, p->Zc);
     if (c.rc) return c.rc;
-    const int grid = (B + 7) / 8 < 148 * 2 ? (B + 7) / 8 : 148 * 2;
-    heads_kernel<<<grid, 256, 2 * HID * (D + 1) * sizeof(float), c.s>>>(p->Za, p->Zc, p->actor_head, p->critic_head, B,
-                                                                        (uint32_t)seed, (uint32_t)(seed >> 32), step, env_id_base,
-                                                                        d_action, d_logp, d_value, d_entropy, d_logits);
+    // heads: first layers on the tensor cores (N = 64 is half a tile), second layers + sampling per sample
+    gemm(c, p->Za, D, p->actor_head.w1, p->actor_head.b1, p->T1, B, HID, D, 1);
+    gemm(c, p->Zc, D, p->critic_head.w1, p->critic_head.b1, p->T2, B, HID, D, 1);
+    if (c.rc) return c.rc;
+    heads_out_kernel<<<(B + 255) / 256, 256, 0, c.s>>>(p->T1, p->T2, p->actor_head, p->critic_head, B, (uint32_t)seed,
+                                                       (uint32_t)(seed >> 32), step, env_id_base, d_action, d_logp, d_value,
+                                                       d_entropy, d_logits);
     P_TRY(p, cudaGetLastError());
     return 0;
 }
