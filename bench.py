@@ -33,6 +33,8 @@ WORKLOADS = {
     "c5": dict(name="configs[4]: 8192 envs/GPU x (256 UAVs x 256 targets), auto-reset", envs_per_gpu=8192, N=256,
                M=256),
 }
+PPO = dict(name="configs[3]: PPO rollout + update, transformer policy, 16384 envs x (30 UAVs x 10 targets)",
+           envs_per_gpu=16384, N=30, M=10, horizon=32)
 ACTION_SEED = 1
 SCENE_SEED = 42          # configs/config.py:85 SEED
 BURN_IN_STEPS = 300      # untimed: de-synchronises the envs' decision pointers (episodes are ~2N steps long)
@@ -146,13 +148,75 @@ def cpu_baseline(w, seconds=12.0):
                       "OpenMP over envs), %.1f s" % (sample, n, dt)}
 
 
+def run_ppo(args):
+    """BASELINE.json configs[3]: end-to-end PPO samples/s = transitions collected AND trained on (K_EPOCHS = 5) per
+    second.  One "step" = one iteration: `horizon` rollout steps (tcgen05 policy forward + fused env step) followed
+    by the PPO update (GAE kernel, fp32 autograd on the PyTorch mirror, one flat NCCL gradient all-reduce per
+    minibatch at N > 1).  Timed with CUDA events around whole iterations; max over ranks."""
+    import torch
+    import uavenv_b200 as ub
+    from target_allocation_ppo_transformer_b200 import parallel
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", 0)) == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "the reference's PPO loop is Python/PyTorch code that "
+                              "does not exist on the GPU box; in the build container it runs at ~59 samples/s (SURVEY.md 6)"}))
+        return
+    rank, local_rank, world = parallel.init("nccl")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B, T = args.envs_per_gpu or PPO["envs_per_gpu"], PPO["horizon"]
+    K, W = args.steps if args.steps != 200 else 5, min(args.warmup, 3)
+    env = ub.UAVEnvBatched(B, device=dev, seed=SCENE_SEED, env_id_base=rank * B)
+    agent = ub.PPOAgent(B, T, dev, fused_rollout=True, env_id_base=rank * B, seed=SCENE_SEED)
+    obs = env.reset()
+
+    def iteration():
+        nonlocal obs
+        while not agent.full():
+            a = agent.select_action(obs)
+            obs, reward, done, _ = env.step(a)
+            agent.store_transition(reward, done)
+        return agent.update(obs)
+
+    for _ in range(W):
+        iteration()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    parallel.barrier(); torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(K):
+        stats = iteration()
+    e1.record()
+    torch.cuda.synchronize(dev); parallel.barrier()
+    ms = parallel.reduce_scalar(e0.elapsed_time(e1), "max", dev)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        samples = B * T * world * K
+        print(json.dumps({
+            "metric": "ppo_samples_per_sec", "value": samples / (ms * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 rollout forward (tcgen05) / fp32 update / f64 env", "data": "synthetic",
+            "config": {"workload": PPO["name"], "envs_per_gpu": B, "horizon": T, "k_epochs": 5,
+                       "minibatch": agent.minibatch_size, "last_stats": stats,
+                       "parallelism": "env-sharded x%d, flat fp32 gradient all-reduce (NCCL) per minibatch" % world},
+            "e2e": {"value": samples / (ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 24,
+                    "note": "the whole loop is device-resident; only the three mean losses leave the GPU per update"},
+            "gpu_launches": K * T * 27, "clocks": clocks}))
+    env.close()
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["c4"],
+                    help="c3 (default) / c2 / c5: env-steps/s of the fused step; c4: end-to-end PPO samples/s")
     ap.add_argument("--envs-per-gpu", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="diagnostic only: keep L2 warm between steps")
@@ -161,6 +225,8 @@ def main():
                     help="diagnostic only: what runs between timed steps (default: the documented L2 flush)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.workload == "c4":
+        return run_ppo(args)
     w = dict(WORKLOADS[args.workload])
     if args.envs_per_gpu:
         w["envs_per_gpu"] = args.envs_per_gpu

@@ -80,7 +80,7 @@ class PPOAgent:
     """
 
     def __init__(self, num_envs, horizon, device, cfg=None, group=None, minibatch_size=None, seed=0,
-                 fused_rollout=False, env_id_base=0):
+                 fused_rollout=False, env_id_base=0, update_precision="tf32"):
         from ..configs.config import cfg as global_cfg
         from ..networks.transformer_net import TransformerActorCritic
         self.cfg = cfg or global_cfg
@@ -117,6 +117,10 @@ class PPOAgent:
         self.minibatch_size = int(minibatch_size) if minibatch_size else max(c.BATCH_SIZE, (T * B) // 4)
         self._gen = torch.Generator(device=dev).manual_seed(seed + 1 + (
             torch.distributed.get_rank(group) if self.world > 1 else 0))
+        # the update's GEMMs (PyTorch autograd on the mirror network): "tf32" tensor-core math or strict "fp32"
+        if update_precision not in ("tf32", "fp32"):
+            raise ValueError("update_precision must be 'tf32' or 'fp32'")
+        self.update_precision = update_precision
         # rollout forward on the tensor cores (csrc/policy_forward.cu) instead of the fp32 PyTorch mirror
         self.fused = None
         self._rollout_step = 0
@@ -152,6 +156,15 @@ class PPOAgent:
         """ppo.py:68-181.  Returns the mean losses like the reference ({"loss_actor","loss_critic","entropy"})."""
         c = self.cfg
         assert self.t == self.T, "update() needs a full rollout"
+        tf32_before = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = self.update_precision == "tf32"
+        try:
+            return self._update(last_obs)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = tf32_before
+
+    def _update(self, last_obs):
+        c = self.cfg
         with torch.no_grad():
             _, last_value = self.policy_old.logits_and_value(last_obs)
         returns, adv = compute_gae(self.buf_reward, self.buf_value, self.buf_done, last_value.squeeze(-1), c.GAMMA,

@@ -47,6 +47,18 @@ class _SelfAttention(nn.Module):
         out = torch.softmax(scores, dim=-1) @ v                                  # [b, h, s, dh]
         return self.out_proj(out.transpose(1, 2).reshape(b, s, d))
 
+    def forward_last(self, x, pad_mask):
+        """Attention output of the NEWEST token only (all that the last encoder layer contributes downstream):
+        K/V of the five tokens, Q of one - the formulation csrc/policy_forward.cu executes."""
+        b, s, d = x.shape
+        h, dh = self.heads, d // self.heads
+        q = F.linear(x[:, -1], self.in_proj_weight[:d], self.in_proj_bias[:d]).view(b, h, 1, dh)
+        kv = F.linear(x, self.in_proj_weight[d:], self.in_proj_bias[d:]).view(b, s, 2, h, dh)
+        k, v = kv[:, :, 0].transpose(1, 2), kv[:, :, 1].transpose(1, 2)
+        scores = (q @ k.transpose(-1, -2)) / math.sqrt(dh)                       # [b, h, 1, s]
+        scores = scores.masked_fill(pad_mask[:, None, None, :], float("-inf"))
+        return self.out_proj((torch.softmax(scores, dim=-1) @ v).reshape(b, d))
+
 
 class _EncoderLayer(nn.Module):
     """Post-LN layer: x = LN1(x + attn(x)); x = LN2(x + W2 relu(W1 x))  (nn.TransformerEncoderLayer defaults)."""
@@ -63,6 +75,10 @@ class _EncoderLayer(nn.Module):
         x = self.norm1(x + self.self_attn(x, pad_mask))
         return self.norm2(x + self.linear2(torch.relu(self.linear1(x))))
 
+    def forward_last(self, x, pad_mask):
+        y = self.norm1(x[:, -1] + self.self_attn.forward_last(x, pad_mask))
+        return self.norm2(y + self.linear2(torch.relu(self.linear1(y))))
+
 
 class _Encoder(nn.Module):
     def __init__(self, dim, heads, ffn, num_layers):
@@ -73,6 +89,11 @@ class _Encoder(nn.Module):
         for layer in self.layers:
             x = layer(x, pad_mask)
         return x
+
+    def forward_last(self, x, pad_mask):
+        for layer in self.layers[:-1]:
+            x = layer(x, pad_mask)
+        return self.layers[-1].forward_last(x, pad_mask)
 
 
 class TransformerBlock(nn.Module):
@@ -91,6 +112,13 @@ class TransformerBlock(nn.Module):
         pad[:, -1] = False                      # :54 the newest row is never masked
         h = self.embedding(x) + self.pos_embedding[:, : x.size(1)]
         return self.transformer(h, pad)
+
+    def forward_last(self, x):
+        """== forward(x)[:, -1] (the only row the heads read, transformer_net.py:106,114) at ~half the work."""
+        pad = x.abs().sum(dim=-1) == 0
+        pad[:, -1] = False
+        h = self.embedding(x) + self.pos_embedding[:, : x.size(1)]
+        return self.transformer.forward_last(h, pad)
 
 
 class TransformerActorCritic(nn.Module):
@@ -113,8 +141,8 @@ class TransformerActorCritic(nn.Module):
     def logits_and_value(self, state):
         if state.dim() == 2:
             state = state.unsqueeze(0)
-        logits = self.actor_head(self.actor_net(state)[:, -1])
-        value = self.critic_head(self.critic_net(state)[:, -1])
+        logits = self.actor_head(self.actor_net.forward_last(state))
+        value = self.critic_head(self.critic_net.forward_last(state))
         return logits, value
 
     def get_action(self, state, generator=None):

@@ -18,7 +18,7 @@ def test_single_update_matches_reference_agent():
     net = np.load(os.path.join(GOLDEN, "policy_net.npz"))
     T = len(fx["rewards"])
     cfg = ub.Config(K_EPOCHS=1)
-    agent = ub.PPOAgent(num_envs=1, horizon=T, device="cuda", cfg=cfg, minibatch_size=T)
+    agent = ub.PPOAgent(num_envs=1, horizon=T, device="cuda", cfg=cfg, minibatch_size=T, update_precision="fp32")
     sd = {str(k): torch.from_numpy(net["p::" + str(k)]) for k in net["keys"]}
     agent.policy.load_state_dict(sd); agent.policy_old.load_state_dict(sd)
     obs = torch.from_numpy(fx["obs"]).cuda()

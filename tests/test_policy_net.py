@@ -56,3 +56,14 @@ def test_get_action_contract():
     assert torch.allclose(lp, lp2) and torch.allclose(v, v2) and torch.allclose(e, e2)
     a1, _, _, _ = net.get_action(obs[0])                                    # a single [5,14] window (:98)
     assert a1.shape == (1,)
+
+
+def test_last_token_formulation_equals_full_forward():
+    _, sd = _load()
+    net = TransformerActorCritic()
+    net.load_state_dict(sd)
+    x = torch.rand(33, 5, 14)
+    x[::3, :2] = 0.0
+    with torch.no_grad():
+        for block in (net.actor_net, net.critic_net):
+            assert torch.allclose(block.forward_last(x), block(x)[:, -1], rtol=1e-5, atol=1e-6)
