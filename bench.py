@@ -167,7 +167,8 @@ def run_ppo(args):
     B, T = args.envs_per_gpu or PPO["envs_per_gpu"], PPO["horizon"]
     K, W = args.steps if args.steps != 200 else 5, min(args.warmup, 3)
     env = ub.UAVEnvBatched(B, device=dev, seed=SCENE_SEED, env_id_base=rank * B)
-    agent = ub.PPOAgent(B, T, dev, fused_rollout=True, env_id_base=rank * B, seed=SCENE_SEED)
+    agent = ub.PPOAgent(B, T, dev, fused_rollout=True, env_id_base=rank * B, seed=SCENE_SEED,
+                        update_precision=os.environ.get("UAVENV_UPDATE_PRECISION", "tf32"))
     obs = env.reset()
 
     def iteration():

@@ -49,6 +49,10 @@ int uavpolicy_get_action(uavpolicy_t *p, const float *d_obs, int32_t B, uint64_t
                          uint64_t env_id_base, int64_t *d_action, float *d_logp, float *d_value, float *d_entropy,
                          float *d_logits, void *stream);
 
+/* self-test of the hand-written tcgen05 path: D[128,N] (f32) = A[128,K] W[N,K]^T for one 128-row tile
+ * (A, W bf16 row-major on the device; N <= 384, N % 16 == 0; K = 128 or 256). */
+int uavpolicy_selftest_gemm_tile(const void *d_A, const void *d_W, float *d_D, int32_t N, int32_t K, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

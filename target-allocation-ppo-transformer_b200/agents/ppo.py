@@ -118,8 +118,8 @@ class PPOAgent:
         self._gen = torch.Generator(device=dev).manual_seed(seed + 1 + (
             torch.distributed.get_rank(group) if self.world > 1 else 0))
         # the update's GEMMs (PyTorch autograd on the mirror network): "tf32" tensor-core math or strict "fp32"
-        if update_precision not in ("tf32", "fp32"):
-            raise ValueError("update_precision must be 'tf32' or 'fp32'")
+        if update_precision not in ("tf32", "fp32", "bf16"):
+            raise ValueError("update_precision must be 'tf32', 'fp32' or 'bf16' (autocast)")
         self.update_precision = update_precision
         # rollout forward on the tensor cores (csrc/policy_forward.cu) instead of the fp32 PyTorch mirror
         self.fused = None
@@ -157,7 +157,7 @@ class PPOAgent:
         c = self.cfg
         assert self.t == self.T, "update() needs a full rollout"
         tf32_before = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = self.update_precision == "tf32"
+        torch.backends.cuda.matmul.allow_tf32 = self.update_precision != "fp32"
         try:
             return self._update(last_obs)
         finally:
@@ -180,8 +180,9 @@ class PPOAgent:
             perm = torch.randperm(n, device=self.device, generator=self._gen)
             for i in range(0, n - mb + 1, mb):                                     # drop_last=True (:115)
                 idx = perm[i:i + mb]
-                logp, value, entropy = self.policy.evaluate(obs[idx], act[idx])
-                value = value.squeeze(-1)
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.update_precision == "bf16"):
+                    logp, value, entropy = self.policy.evaluate(obs[idx], act[idx])
+                logp, value, entropy = logp.float(), value.float().squeeze(-1), entropy.float()
                 ratio = torch.exp(logp - old_logp[idx])                             # :131
                 a = adv[idx]
                 loss_actor = -torch.min(ratio * a, torch.clamp(ratio, 1 - c.EPS_CLIP, 1 + c.EPS_CLIP) * a).mean()
