@@ -49,6 +49,11 @@ int uavpolicy_get_action(uavpolicy_t *p, const float *d_obs, int32_t B, uint64_t
                          uint64_t env_id_base, int64_t *d_action, float *d_logp, float *d_value, float *d_entropy,
                          float *d_logits, void *stream);
 
+/* 1 (default): hand-written fused encoder blocks - one CTA per 25-sample tile keeps activations in shared memory /
+ * TMEM across embedding, all layers and the first head layer (csrc/policy_fused.cu); 0: one tcgen05 GEMM launch per
+ * dense layer (csrc/policy_gemm.cu) with separate attention / LayerNorm kernels.  Same results up to bf16 rounding. */
+int uavpolicy_set_fused(uavpolicy_t *p, int32_t fused);
+
 /* self-test of the hand-written tcgen05 path: D[128,N] (f32) = A[128,K] W[N,K]^T for one 128-row tile
  * (A, W bf16 row-major on the device; N <= 384, N % 16 == 0; K = 128 or 256). */
 int uavpolicy_selftest_gemm_tile(const void *d_A, const void *d_W, float *d_D, int32_t N, int32_t K, void *stream);

@@ -152,7 +152,10 @@ def load_policy():
     L.uavpolicy_last_error.restype = C.c_char_p
     L.uavpolicy_set_weights.argtypes = [vp, vp, vp]
     L.uavpolicy_get_action.argtypes = [vp, vp, i32, u64, u64, u64, vp, vp, vp, vp, vp, vp]
-    for name in ("uavpolicy_create", "uavpolicy_destroy", "uavpolicy_set_weights", "uavpolicy_get_action"):
+    L.uavpolicy_set_fused.argtypes = [vp, i32]
+    L.uavpolicy_selftest_gemm_tile.argtypes = [vp, vp, vp, i32, i32, vp]
+    for name in ("uavpolicy_create", "uavpolicy_destroy", "uavpolicy_set_weights", "uavpolicy_get_action",
+                 "uavpolicy_set_fused", "uavpolicy_selftest_gemm_tile"):
         getattr(L, name).restype = C.c_int
     _policy_lib = L
     return L

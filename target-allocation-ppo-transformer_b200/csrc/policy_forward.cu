@@ -19,29 +19,30 @@
 #include <cuda_runtime.h>
 
 #include "policy_gemm.cuh"
+#include "policy_weights.cuh"
 
 namespace {
-
-constexpr int S = 5, F = 14, D = 128, H = 8, DH = 16, FF = 256, HID = 64, NACT = 2;
-constexpr int kLayerParams = 3 * D * D + 3 * D + D * D + D + FF * D + FF + D * FF + D + 4 * D;  // 132480
-constexpr int kBlockBase = S * D + D * F + D;                                                   // pos, emb w, emb b
-constexpr int kActorHead = HID * D + HID + NACT * HID + NACT;
-constexpr int kCriticHead = HID * D + HID + HID + 1;
-static_assert(kBlockBase + kLayerParams + kActorHead + kBlockBase + 2 * kLayerParams + kCriticHead == UAVPOLICY_NUM_PARAMS,
-              "parameter layout");
-
-struct LayerW {  // views into the fp32 copy / the bf16 copy of one encoder layer
-    const __nv_bfloat16 *in_w, *out_w, *l1_w, *l2_w;  // [384,128] [128,128] [256,128] [128,256]
-    const float *in_b, *out_b, *l1_b, *l2_b, *n1_w, *n1_b, *n2_w, *n2_b;
-};
-struct BlockW {
-    const float *pos, *emb_w, *emb_b;
-    LayerW layer[2];
-    int layers;
-};
-struct HeadW { const __nv_bfloat16 *w1; const float *b1, *w2, *b2; };  // w1 [64,128] bf16 (GEMM), the rest fp32
+using namespace uavp;
 
 // ------------------------------------------------------------------------------------------------ kernels
+
+// element offset of (row n, column k) in the UMMA canonical K-major order (tcgen05_util.cuh: 8x8 core matrices)
+__device__ __forceinline__ int canon_elem(int n, int k, int K) { return (n >> 3) * (K * 8) + (k >> 3) * 64 + (n & 7) * 8 + (k & 7); }
+
+// [128 x 14] fp32 embedding weight -> [128 x 32] bf16, canonical order, the 14 columns duplicated at 0.. and 16..
+__global__ void emb_w2_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D * 32) return;
+    const int d = i / 32, c = i % 32, j = c % 16;
+    out[canon_elem(d, c, 32)] = __float2bfloat16(j < F ? w[d * F + j] : 0.0f);
+}
+
+// row-major fp32 [N x K] -> bf16 in canonical order (one bulk TMA copy then stages a whole B operand)
+__global__ void pack_canon_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ out, int N, int K) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * K) return;
+    out[canon_elem(i / K, i % K, K)] = __float2bfloat16(w[i]);
+}
 
 __global__ void f32_to_bf16_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -259,7 +260,9 @@ struct uavpolicy {
     int device = 0, max_batch = 0;
     float *w32 = nullptr;                 // private fp32 copy of the flat parameters
     __nv_bfloat16 *w16 = nullptr;         // bf16 copies (GEMM weights are read from here): one per block, each placed so
-    __nv_bfloat16 *w16_critic = nullptr;  // that the block's first parameter is 16 B aligned (TMA needs aligned operands)
+    __nv_bfloat16 *w16_critic = nullptr;
+    __nv_bfloat16 *emb2_a = nullptr, *emb2_c = nullptr;   // [128 x 32] tensor-core form of the two embedding weights
+    __nv_bfloat16 *wpk = nullptr;         // GEMM weights pre-packed in canonical order (same element offsets as w32)  // that the block's first parameter is 16 B aligned (TMA needs aligned operands)
     BlockW actor, critic;
     HeadW actor_head, critic_head;
     // bf16 activation workspaces (R = 5 * max_batch rows)
@@ -268,6 +271,7 @@ struct uavpolicy {
     void *gemm_ws = nullptr;
     std::vector<void *> allocs;
     bool have_weights = false;
+    bool fused = true;                    // hand-written fused tcgen05 blocks (policy_fused.cu) vs one GEMM per layer
     std::string err;
 };
 
@@ -295,19 +299,26 @@ static cudaError_t palloc(uavpolicy *p, T **ptr, size_t n) {
     return e;
 }
 
-static size_t map_block(BlockW &b, int layers, const float *w32, const __nv_bfloat16 *w16, size_t off) {
+constexpr size_t UPK_SIZE = (size_t)UAVPOLICY_NUM_PARAMS + 64;   // packed copies live at (offset rounded up to 8 elements)
+static inline size_t pk(size_t off) { return (off + 7) / 8 * 8; }
+
+static size_t map_block(BlockW &b, int layers, const float *w32, const __nv_bfloat16 *w16, const __nv_bfloat16 *wpk, size_t off) {
     b.layers = layers;
     b.pos = w32 + off; off += S * D;
     b.emb_w = w32 + off; off += D * F;
     b.emb_b = w32 + off; off += D;
     for (int l = 0; l < layers; ++l) {
         LayerW &L = b.layer[l];
+        L.in_wp = wpk + pk(off);
         L.in_w = w16 + off; off += 3 * D * D;
         L.in_b = w32 + off; off += 3 * D;
+        L.out_wp = wpk + pk(off);
         L.out_w = w16 + off; off += D * D;
         L.out_b = w32 + off; off += D;
+        L.l1_wp = wpk + pk(off);
         L.l1_w = w16 + off; off += FF * D;
         L.l1_b = w32 + off; off += FF;
+        L.l2_wp = wpk + pk(off);
         L.l2_w = w16 + off; off += D * FF;
         L.l2_b = w32 + off; off += D;
         L.n1_w = w32 + off; off += D;
@@ -317,7 +328,8 @@ static size_t map_block(BlockW &b, int layers, const float *w32, const __nv_bflo
     }
     return off;
 }
-static size_t map_head(HeadW &h, int outs, const float *w32, const __nv_bfloat16 *w16, size_t off) {
+static size_t map_head(HeadW &h, int outs, const float *w32, const __nv_bfloat16 *w16, const __nv_bfloat16 *wpk, size_t off) {
+    h.w1p = wpk + pk(off);
     h.w1 = w16 + off; off += HID * D;
     h.b1 = w32 + off; off += HID;
     h.w2 = w32 + off; off += outs * HID;
@@ -351,15 +363,20 @@ extern "C" int uavpolicy_create(int32_t device, int32_t max_batch, uavpolicy_t *
     for (auto b : small) if (e == cudaSuccess) e = palloc(p, b, B * D);
     if (e == cudaSuccess) e = palloc(p, &p->Hs, B * FF);
     if (e == cudaSuccess) e = palloc(p, &p->pad, R);
+    if (e == cudaSuccess) e = palloc(p, &p->wpk, (size_t)UPK_SIZE);
+    if (e == cudaSuccess) e = palloc(p, &p->emb2_a, (size_t)D * 32);
+    if (e == cudaSuccess) e = palloc(p, &p->emb2_c, (size_t)D * 32);
     if (e == cudaSuccess) { void *ws = nullptr; e = cudaMalloc(&ws, uavp::gemm_workspace_bytes()); if (e == cudaSuccess) { p->allocs.push_back(ws); p->gemm_ws = ws; } }
     if (e != cudaSuccess) { pfail(p, -2, "uavpolicy_create: %s", cudaGetErrorString(e)); return bail(-2); }
-    size_t off = map_block(p->actor, 1, p->w32, p->w16, 0);
+    if (uavp::fused_block_prepare() != 0) { pfail(p, -2, "uavpolicy_create: cannot reserve shared memory for the fused kernel"); return bail(-2); }
+    size_t off = map_block(p->actor, 1, p->w32, p->w16, p->wpk, 0);
     // (the actor head's first layer starts at element 135040: 16 B aligned in the first bf16 copy)
-    off = map_head(p->actor_head, NACT, p->w32, p->w16, off);
+    off = map_head(p->actor_head, NACT, p->w32, p->w16, p->wpk, off);
     // second bf16 copy, shifted so that element `off` (the critic block's first parameter) lands on a multiple of 8
     p->w16_critic = p->w16 + ((size_t)UAVPOLICY_NUM_PARAMS + 15) / 8 * 8 + (8 - off % 8) % 8;
-    off = map_block(p->critic, 2, p->w32, p->w16_critic, off);
-    off = map_head(p->critic_head, 1, p->w32, p->w16_critic, off);   // 267520 elements later: still a multiple of 8
+    off = map_block(p->critic, 2, p->w32, p->w16_critic, p->wpk, off);
+    off = map_head(p->critic_head, 1, p->w32, p->w16_critic, p->wpk, off);   // 267520 elements later: still a multiple of 8
+    p->actor.emb_w2p = p->emb2_a; p->critic.emb_w2p = p->emb2_c;
     if (off != (size_t)UAVPOLICY_NUM_PARAMS) { pfail(p, -1, "internal: parameter layout mismatch"); return bail(-1); }
     *out = p;
     return 0;
@@ -381,6 +398,23 @@ extern "C" int uavpolicy_set_weights(uavpolicy_t *p, const float *d_flat_params,
     P_TRY(p, cudaMemcpyAsync(p->w32, d_flat_params, (size_t)UAVPOLICY_NUM_PARAMS * sizeof(float), cudaMemcpyDeviceToDevice, s));
     f32_to_bf16_kernel<<<(UAVPOLICY_NUM_PARAMS + 255) / 256, 256, 0, s>>>(p->w32, p->w16, UAVPOLICY_NUM_PARAMS);
     f32_to_bf16_kernel<<<(UAVPOLICY_NUM_PARAMS + 255) / 256, 256, 0, s>>>(p->w32, p->w16_critic, UAVPOLICY_NUM_PARAMS);
+    {   // canonical-order copies of every GEMM weight for the fused kernel's bulk-TMA staging
+        auto packw = [&](const __nv_bfloat16 *dst, const __nv_bfloat16 *row_major16, int N, int K) {
+            const float *src = p->w32 + (row_major16 - (row_major16 >= p->w16_critic ? p->w16_critic : p->w16));
+            pack_canon_kernel<<<(N * K + 255) / 256, 256, 0, s>>>(src, const_cast<__nv_bfloat16 *>(dst), N, K);
+        };
+        const BlockW *blocks[2] = {&p->actor, &p->critic};
+        for (const BlockW *b : blocks)
+            for (int l = 0; l < b->layers; ++l) {
+                const LayerW &L = b->layer[l];
+                packw(L.in_wp, L.in_w, 3 * D, D); packw(L.out_wp, L.out_w, D, D);
+                packw(L.l1_wp, L.l1_w, FF, D); packw(L.l2_wp, L.l2_w, D, FF);
+            }
+        packw(p->actor_head.w1p, p->actor_head.w1, HID, D);
+        packw(p->critic_head.w1p, p->critic_head.w1, HID, D);
+    }
+    emb_w2_kernel<<<(D * 32 + 255) / 256, 256, 0, s>>>(p->actor.emb_w, p->emb2_a);
+    emb_w2_kernel<<<(D * 32 + 255) / 256, 256, 0, s>>>(p->critic.emb_w, p->emb2_c);
     P_TRY(p, cudaGetLastError());
     p->have_weights = true;
     return 0;
@@ -436,6 +470,17 @@ extern "C" int uavpolicy_get_action(uavpolicy_t *p, const float *d_obs, int32_t 
     P_TRY(p, cudaSetDevice(p->device));
     Ctx c{p, (cudaStream_t)stream, 0};
     const int R = B * S;
+    if (p->fused) {
+        // two fused launches (actor block + head layer 1, critic block + head layer 1), then the per-sample outputs
+        if (uavp::launch_fused_block(d_obs, B, p->actor, p->actor_head, p->T1, c.s) ||
+            uavp::launch_fused_block(d_obs, B, p->critic, p->critic_head, p->T2, c.s))
+            return pfail(p, -2, "fused block launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        heads_out_kernel<<<(B + 255) / 256, 256, 0, c.s>>>(p->T1, p->T2, p->actor_head, p->critic_head, B, (uint32_t)seed,
+                                                           (uint32_t)(seed >> 32), step, env_id_base, d_action, d_logp, d_value,
+                                                           d_entropy, d_logits);
+        P_TRY(p, cudaGetLastError());
+        return 0;
+    }
     embed_kernel<<<(R + kEmbTok - 1) / kEmbTok, D, 0, c.s>>>(d_obs, R, p->actor, p->critic, p->Ea, p->Ec, p->pad);
     last_layer(c, p->actor.layer[0], p->Ea, B, p->Za);              // actor: 1 layer
     full_layer(c, p->critic.layer[0], p->Ec, B, p->X1);             // critic: 2 layers
@@ -449,5 +494,11 @@ extern "C" int uavpolicy_get_action(uavpolicy_t *p, const float *d_obs, int32_t 
                                                        (uint32_t)(seed >> 32), step, env_id_base, d_action, d_logp, d_value,
                                                        d_entropy, d_logits);
     P_TRY(p, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int uavpolicy_set_fused(uavpolicy_t *p, int32_t fused) {
+    if (!p) return -1;
+    p->fused = fused != 0;
     return 0;
 }

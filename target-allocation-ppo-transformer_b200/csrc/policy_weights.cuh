@@ -1,0 +1,41 @@
+// policy_weights.cuh - parameter views and dimensions of TransformerActorCritic shared by the policy kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "uavpolicy_b200.h"
+
+namespace uavp {
+
+constexpr int S = 5, F = 14, D = 128, H = 8, DH = 16, FF = 256, HID = 64, NACT = 2;
+constexpr int kLayerParams = 3 * D * D + 3 * D + D * D + D + FF * D + FF + D * FF + D + 4 * D;  // 132480
+constexpr int kBlockBase = S * D + D * F + D;                                                   // pos, emb w, emb b
+constexpr int kActorHead = HID * D + HID + NACT * HID + NACT;
+constexpr int kCriticHead = HID * D + HID + HID + 1;
+static_assert(kBlockBase + kLayerParams + kActorHead + kBlockBase + 2 * kLayerParams + kCriticHead == UAVPOLICY_NUM_PARAMS,
+              "parameter layout");
+
+struct LayerW {  // views into the fp32 copy / the bf16 copy of one encoder layer
+    const __nv_bfloat16 *in_w, *out_w, *l1_w, *l2_w;  // [384,128] [128,128] [256,128] [128,256] row-major
+    const __nv_bfloat16 *in_wp, *out_wp, *l1_wp, *l2_wp;  // the same matrices pre-packed in UMMA canonical K-major order
+    const float *in_b, *out_b, *l1_b, *l2_b, *n1_w, *n1_b, *n2_w, *n2_b;
+};
+struct BlockW {
+    const float *pos, *emb_w, *emb_b;
+    const __nv_bfloat16 *emb_w2p;  // [128 x 32] bf16, UMMA canonical order: columns 0..13 and 16..29 both hold emb_w (the fused kernel feeds the
+                                   // embedding to the tensor cores with the observation split into bf16 hi + lo parts)
+    LayerW layer[2];
+    int layers;
+};
+struct HeadW { const __nv_bfloat16 *w1, *w1p; const float *b1, *w2, *b2; };  // w1 [64,128] bf16 (+ packed), rest fp32
+
+
+// fused encoder block (policy_fused.cu): embedding + `layers` post-LN encoder layers + first head layer for a batch of
+// windows, one CTA per tile of 25 samples, every GEMM on tcgen05 with operands resident in shared memory.
+// Writes relu(W1 z_last + b1) as bf16 [B,64] to head_hidden.
+int launch_fused_block(const float *d_obs, int B, const BlockW &w, const HeadW &head, __nv_bfloat16 *head_hidden,
+                       cudaStream_t stream);
+int fused_block_prepare();   // one-time kernel attribute setup; 0 on success
+
+}  // namespace uavp

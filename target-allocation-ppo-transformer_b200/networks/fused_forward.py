@@ -14,7 +14,7 @@ from .. import _capi
 
 
 class FusedPolicyForward:
-    def __init__(self, max_batch, device, seed=0, env_id_base=0):
+    def __init__(self, max_batch, device, seed=0, env_id_base=0, fused=True):
         self._h = None
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -27,6 +27,7 @@ class FusedPolicyForward:
         if rc != 0:
             raise _capi.UavenvError(rc, (self._lib.uavpolicy_last_error(None) or b"").decode())
         self._h = h
+        self._lib.uavpolicy_set_fused(h, int(bool(fused)))   # False: one tcgen05 GEMM launch per layer (A/B reference)
         self.max_batch, self.seed, self.env_id_base = int(max_batch), int(seed), int(env_id_base)
         dev = self.device
         self.action = torch.zeros(max_batch, dtype=torch.int64, device=dev)
