@@ -123,10 +123,12 @@ __device__ __forceinline__ void epilogue_residual_ln(uint32_t tmem_lane, int row
 }
 
 __global__ void __launch_bounds__(kFusedThreads, 1)
-fused_block_kernel(const float *__restrict__ obs, int B, BlockW w, HeadW head, __nv_bfloat16 *__restrict__ head_hidden) {
+fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW head_actor, __nv_bfloat16 *__restrict__ hh_actor,
+                   BlockW w_critic, HeadW head_critic, __nv_bfloat16 *__restrict__ hh_critic, int *__restrict__ work_counter) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint64_t mbar, wbar;                       // MMA completion / weight staging (bulk TMA) barriers
     __shared__ uint32_t tmem_base_s;
+    __shared__ int s_item;
     __shared__ uint8_t s_pad[128];
     unsigned char *sX = smem, *sQ = smem + kTileBytes, *sK = sQ + kTileBytes, *sV = sK + kTileBytes;
     unsigned char *sH = sQ;                               // [128 x 256] canonical, aliases sQ + sK after attention
@@ -144,7 +146,17 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w, HeadW head, _
     uint32_t parity = 0, wparity = 0;
     const int num_tiles = (B + kTileSamples - 1) / kTileSamples;
 
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    // work items = (network, tile), handed out dynamically, the two-layer critic tiles first (longest first)
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(work_counter, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= 2 * num_tiles) break;
+        const bool is_critic = item < num_tiles;
+        const BlockW &w = is_critic ? w_critic : w_actor;
+        const HeadW &head = is_critic ? head_critic : head_actor;
+        __nv_bfloat16 *head_hidden = is_critic ? hh_critic : hh_actor;
+        const int tile = is_critic ? item : item - num_tiles;
         const int s0 = tile * kTileSamples;
         const int nsamp = min(kTileSamples, B - s0), nrows = nsamp * S;
         // ---- embedding: X = relu(obs W^T + b) + pos (transformer_net.py:24-30,57-59); key-padding mask (:52-54).
@@ -365,10 +377,13 @@ namespace uavp {
 int fused_block_prepare() {
     return cudaFuncSetAttribute(fused_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem) == cudaSuccess ? 0 : -2;
 }
-int launch_fused_block(const float *d_obs, int B, const BlockW &w, const HeadW &head, __nv_bfloat16 *head_hidden,
-                       cudaStream_t stream) {
-    const int tiles = (B + kTileSamples - 1) / kTileSamples;
-    fused_block_kernel<<<tiles < 148 ? tiles : 148, kFusedThreads, kFusedSmem, stream>>>(d_obs, B, w, head, head_hidden);
+int launch_fused_blocks(const float *d_obs, int B, const BlockW &actor, const HeadW &actor_head, __nv_bfloat16 *hh_actor,
+                        const BlockW &critic, const HeadW &critic_head, __nv_bfloat16 *hh_critic, int *d_work_counter,
+                        cudaStream_t stream) {
+    const int items = 2 * ((B + kTileSamples - 1) / kTileSamples);
+    if (cudaMemsetAsync(d_work_counter, 0, sizeof(int), stream) != cudaSuccess) return -2;
+    fused_block_kernel<<<items < 148 ? items : 148, kFusedThreads, kFusedSmem, stream>>>(
+        d_obs, B, actor, actor_head, hh_actor, critic, critic_head, hh_critic, d_work_counter);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 }  // namespace uavp

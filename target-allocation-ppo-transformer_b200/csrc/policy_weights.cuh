@@ -31,11 +31,12 @@ struct BlockW {
 struct HeadW { const __nv_bfloat16 *w1, *w1p; const float *b1, *w2, *b2; };  // w1 [64,128] bf16 (+ packed), rest fp32
 
 
-// fused encoder block (policy_fused.cu): embedding + `layers` post-LN encoder layers + first head layer for a batch of
-// windows, one CTA per tile of 25 samples, every GEMM on tcgen05 with operands resident in shared memory.
-// Writes relu(W1 z_last + b1) as bf16 [B,64] to head_hidden.
-int launch_fused_block(const float *d_obs, int B, const BlockW &w, const HeadW &head, __nv_bfloat16 *head_hidden,
-                       cudaStream_t stream);
+// fused encoder blocks (policy_fused.cu): embedding + all post-LN encoder layers + first head layer of BOTH networks
+// for a batch of windows in ONE launch; one CTA per (network, 25-sample tile) work item, every GEMM on tcgen05 with
+// operands resident in shared memory.  Writes relu(W1 z_last + b1) as bf16 [B,64] per network.
+int launch_fused_blocks(const float *d_obs, int B, const BlockW &actor, const HeadW &actor_head, __nv_bfloat16 *hh_actor,
+                        const BlockW &critic, const HeadW &critic_head, __nv_bfloat16 *hh_critic, int *d_work_counter,
+                        cudaStream_t stream);
 int fused_block_prepare();   // one-time kernel attribute setup; 0 on success
 
 }  // namespace uavp

@@ -22,11 +22,28 @@ def _net():
     return net.eval(), fx
 
 
-def test_forward_matches_fp32_network_and_reference_golden():
+def test_handwritten_tcgen05_gemm_tile_selftest():
+    """The hand-written UMMA path on its own: descriptors, canonical operand layout, TMEM lane mapping."""
+    import ctypes as C
+    from target_allocation_ppo_transformer_b200 import _capi
+    L = _capi.load_policy()
+    torch.manual_seed(0)
+    for N, K in ((128, 128), (384, 128), (128, 256), (64, 128)):
+        A = torch.randn(128, K, device="cuda").bfloat16()
+        W = (torch.randn(N, K, device="cuda") * 0.2).bfloat16()
+        Dst = torch.zeros(128, N, device="cuda")
+        assert L.uavpolicy_selftest_gemm_tile(C.c_void_p(A.data_ptr()), C.c_void_p(W.data_ptr()), C.c_void_p(Dst.data_ptr()),
+                                              N, K, None) == 0
+        torch.cuda.synchronize()
+        assert float((Dst - A.float() @ W.float().t()).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("fused_kernel", [True, False])
+def test_forward_matches_fp32_network_and_reference_golden(fused_kernel):
     from target_allocation_ppo_transformer_b200.networks.fused_forward import FusedPolicyForward
     net, fx = _net()
     obs = torch.from_numpy(fx["obs"]).cuda()
-    fused = FusedPolicyForward(256, "cuda")
+    fused = FusedPolicyForward(256, "cuda", fused=fused_kernel)
     fused.sync(net)
     a, lp, v, e = fused.get_action(obs, step=0)
     logits = fused.logits[: obs.shape[0]]
@@ -45,14 +62,15 @@ def test_forward_matches_fp32_network_and_reference_golden():
     fused.close()
 
 
-def test_padding_rows_and_batch_tails():
+@pytest.mark.parametrize("fused_kernel", [True, False])
+def test_padding_rows_and_batch_tails(fused_kernel):
     """Episode starts (leading zero rows are masked keys) and batch sizes that are not tile multiples."""
     from target_allocation_ppo_transformer_b200.networks.fused_forward import FusedPolicyForward
     net, _ = _net()
-    fused = FusedPolicyForward(1000, "cuda")
+    fused = FusedPolicyForward(1000, "cuda", fused=fused_kernel)
     fused.sync(net)
     g = torch.Generator(device="cuda").manual_seed(1)
-    for B in (1, 7, 129, 1000):
+    for B in (1, 7, 24, 26, 129, 1000):
         obs = torch.rand(B, 5, 14, device="cuda", generator=g)
         obs[:, :, 13] = 1.0
         for b in range(B):
