@@ -1,13 +1,14 @@
-import sys, os, numpy as np; sys.path.insert(0,'.')
+import sys; sys.path.insert(0,'.')
 import torch, uavenv_b200 as ub
-fx=np.load("tests/golden/policy_net.npz")
-net=ub.TransformerActorCritic().cuda().eval()
-net.load_state_dict({str(k): torch.from_numpy(fx["p::"+str(k)]) for k in fx["keys"]})
-for B in (25, 96, 1000):
-    obs=torch.rand(B,5,14,device="cuda"); obs[:,:,13]=1
-    for b in range(B): obs[b,:b%5]=0
-    f=ub.FusedPolicyForward(B,"cuda"); f.sync(net)
-    a,lp,v,e=f.get_action(obs,1); torch.cuda.synchronize()
-    with torch.no_grad(): rl,rv=net.logits_and_value(obs)
-    print(B,"logit err",float((f.logits[:B]-rl).abs().max()),"value err",float((v-rv).abs().max()), "ref v max", float(rv.abs().max()))
-    f.close()
+from torch.profiler import profile, ProfilerActivity
+net=ub.TransformerActorCritic().cuda()
+n=131072
+obs=torch.rand(n,5,14,device="cuda"); act=torch.randint(0,2,(n,),device="cuda")
+torch.backends.cuda.matmul.allow_tf32=True
+def step():
+    lp,v,e=net.evaluate(obs,act); loss=(lp.mean()+v.mean()+e.mean()); loss.backward()
+for _ in range(2): step()
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    step(); torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=22, max_name_column_width=70))

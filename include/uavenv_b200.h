@@ -180,6 +180,18 @@ int ppo_gae_advantages(const float *d_rewards, const float *d_values, const uint
 int ppo_normalize_advantages(float *d_advantages, int64_t n, const double *d_adv_stats, int32_t device,
                              void *stream);
 
+/* ---- PPO update: fused attention over the 5-token window (agents/ppo.py:126 -> the self-attention of
+ * nn.TransformerEncoderLayer, networks/transformer_net.py:34-43,63), forward and backward in fp32 ---------------------
+ * d_q: [n, num_queries, 128] rows of stride q_stride floats; d_k, d_v: [n, 5, 128] rows of stride kv_stride (views into a
+ * packed in_proj output are fine); d_pad [n,5]: 1 = the key is a padding row.  num_queries = 5 (every token attends) or 1
+ * (only the newest token, the last encoder layer).  d_out / d_grad_out: dense [n, num_queries, 128].  The gradients are
+ * written with the strides of their inputs (d_grad_k / d_grad_v: every row; d_grad_q: every query row). */
+int ppo_attn5_forward(const float *d_q, int64_t q_stride, const float *d_k, const float *d_v, int64_t kv_stride,
+                      const uint8_t *d_pad, int64_t n, int32_t num_queries, float *d_out, int32_t device, void *stream);
+int ppo_attn5_backward(const float *d_q, int64_t q_stride, const float *d_k, const float *d_v, int64_t kv_stride,
+                       const uint8_t *d_pad, int64_t n, int32_t num_queries, const float *d_grad_out, float *d_grad_q,
+                       float *d_grad_k, float *d_grad_v, int32_t device, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,6 +39,7 @@ LIBS = {
     LIB_PATH: [
         ("uavenv_capi.cu", ["-fmad=false"], ["uavenv_device.cuh", "uavenv_kernels.cuh", "../../include/uavenv_b200.h"]),
         ("ppo_gae.cu", [], ["../../include/uavenv_b200.h"]),
+        ("ppo_attn.cu", [], ["../../include/uavenv_b200.h"]),
     ],
     POLICY_LIB_PATH: [
         ("policy_gemm.cu", "CUTLASS", ["policy_gemm.cuh"]),

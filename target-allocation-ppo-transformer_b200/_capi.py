@@ -111,6 +111,10 @@ def load():
     L.uavenv_random_actions.argtypes = [vp, u64, u64, vp, vp]
     L.ppo_gae_advantages.argtypes = [vp, vp, vp, vp, i32, i32, C.c_float, C.c_float, vp, vp, i32, vp, i32, vp]
     L.ppo_normalize_advantages.argtypes = [vp, i64, vp, i32, vp]
+    L.ppo_attn5_forward.argtypes = [vp, i64, vp, vp, i64, vp, i64, i32, vp, i32, vp]
+    L.ppo_attn5_backward.argtypes = [vp, i64, vp, vp, i64, vp, i64, i32, vp, vp, vp, vp, i32, vp]
+    L.ppo_attn5_forward.restype = C.c_int
+    L.ppo_attn5_backward.restype = C.c_int
     for name in ("uavenv_create", "uavenv_destroy", "uavenv_reset", "uavenv_step", "uavenv_step_host",
                  "uavenv_load_scene", "uavenv_get_scene", "uavenv_get_state", "uavenv_score_matrix",
                  "uavenv_score_matrix_f64", "uavenv_recompute_objective", "uavenv_random_actions",

@@ -34,13 +34,20 @@ class _SelfAttention(nn.Module):
         self.in_proj_weight = nn.Parameter(torch.empty(3 * dim, dim))
         self.in_proj_bias = nn.Parameter(torch.zeros(3 * dim))
         self.out_proj = nn.Linear(dim, dim)
+        self.fused_attention = True        # use csrc/ppo_attn.cu on CUDA fp32 tensors (same math, one kernel each way)
         nn.init.xavier_uniform_(self.in_proj_weight)           # torch's MultiheadAttention._reset_parameters
         nn.init.constant_(self.out_proj.bias, 0.0)
 
     def forward(self, x, pad_mask):
         b, s, d = x.shape
         h, dh = self.heads, d // self.heads
-        qkv = F.linear(x, self.in_proj_weight, self.in_proj_bias).view(b, s, 3, h, dh)
+        qkv = F.linear(x, self.in_proj_weight, self.in_proj_bias)
+        if self.fused_attention and d == 128 and h == 8:
+            from . import attn_op                                     # fused CUDA forward/backward (csrc/ppo_attn.cu)
+            q3, k3, v3 = qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
+            if attn_op.usable(q3, k3, v3):
+                return self.out_proj(attn_op.attention5(q3, k3, v3, pad_mask))
+        qkv = qkv.view(b, s, 3, h, dh)
         q, k, v = qkv[:, :, 0].transpose(1, 2), qkv[:, :, 1].transpose(1, 2), qkv[:, :, 2].transpose(1, 2)
         scores = (q @ k.transpose(-1, -2)) / math.sqrt(dh)                       # [b, h, s, s]
         scores = scores.masked_fill(pad_mask[:, None, None, :], float("-inf"))   # keys that are padding rows
@@ -52,8 +59,15 @@ class _SelfAttention(nn.Module):
         K/V of the five tokens, Q of one - the formulation csrc/policy_forward.cu executes."""
         b, s, d = x.shape
         h, dh = self.heads, d // self.heads
-        q = F.linear(x[:, -1], self.in_proj_weight[:d], self.in_proj_bias[:d]).view(b, h, 1, dh)
-        kv = F.linear(x, self.in_proj_weight[d:], self.in_proj_bias[d:]).view(b, s, 2, h, dh)
+        q = F.linear(x[:, -1], self.in_proj_weight[:d], self.in_proj_bias[:d])
+        kv = F.linear(x, self.in_proj_weight[d:], self.in_proj_bias[d:])
+        if self.fused_attention and d == 128 and h == 8:
+            from . import attn_op
+            q3, k3, v3 = q.view(b, 1, d), kv[..., :d], kv[..., d:]
+            if attn_op.usable(q3, k3, v3):
+                return self.out_proj(attn_op.attention5(q3, k3, v3, pad_mask).view(b, d))
+        q = q.view(b, h, 1, dh)
+        kv = kv.view(b, s, 2, h, dh)
         k, v = kv[:, :, 0].transpose(1, 2), kv[:, :, 1].transpose(1, 2)
         scores = (q @ k.transpose(-1, -2)) / math.sqrt(dh)                       # [b, h, 1, s]
         scores = scores.masked_fill(pad_mask[:, None, None, :], float("-inf"))

@@ -104,3 +104,42 @@ def test_fused_rollout_forward_drives_training():
     a2 = agent.select_action(obs)                       # runs with the re-synchronised weights
     assert set(a2.tolist()) <= {0, 1}
     env.close()
+
+
+@pytest.mark.parametrize("nq", [5, 1])
+def test_fused_attention_forward_and_gradients_match_tensor_ops(nq):
+    """csrc/ppo_attn.cu against the plain tensor-op attention of the mirror network (fp32, 1e-5)."""
+    import uavenv_b200  # noqa: F401
+    from target_allocation_ppo_transformer_b200.networks import attn_op
+    torch.manual_seed(nq)
+    n = 777
+    packed = torch.randn(n, 5, 384, device="cuda", requires_grad=True)
+    qsrc = torch.randn(n, 1, 128, device="cuda", requires_grad=True)
+    pad = torch.rand(n, 5, device="cuda") < 0.3
+    pad[:, -1] = False
+
+    def run(fused):
+        pk = packed.detach().clone().requires_grad_(True)
+        qs = qsrc.detach().clone().requires_grad_(True)
+        q = pk[..., :128] if nq == 5 else qs
+        k, v = pk[..., 128:256], pk[..., 256:]
+        if fused:
+            assert attn_op.usable(q, k, v)
+            out = attn_op.attention5(q, k, v, pad)
+        else:
+            qh, kh, vh = (t.reshape(n, -1, 8, 16).transpose(1, 2) for t in (q, k, v))
+            sc = (qh @ kh.transpose(-1, -2)) / 4.0
+            sc = sc.masked_fill(pad[:, None, None, :], float("-inf"))
+            out = (torch.softmax(sc, -1) @ vh).transpose(1, 2).reshape(n, -1, 128)
+        w = torch.linspace(-1, 1, out.numel(), device="cuda").view_as(out)
+        (out * w).sum().backward()
+        return out.detach(), pk.grad, (qs.grad if nq == 1 else None)
+
+    o1, g1, q1 = run(True)
+    o0, g0, q0 = run(False)
+    assert torch.allclose(o1, o0, rtol=1e-5, atol=1e-6)
+    if nq == 5:
+        assert torch.allclose(g1, g0, rtol=1e-4, atol=1e-6)
+    else:
+        assert torch.allclose(g1[..., 128:], g0[..., 128:], rtol=1e-4, atol=1e-6)
+        assert torch.allclose(q1, q0, rtol=1e-4, atol=1e-6)
