@@ -121,11 +121,10 @@ static int create_impl(uavenv *h) {
     CU_TRY(h, cudaMemset(P.pregen_req, 0, req_bytes));
     CU_TRY(h, cudaMemset(P.pregen_ack, 0, req_bytes));
     const size_t tiles = (B + 31) / 32;
-    CU_TRY(h, dev_alloc(h, &P.hist, tiles * kRingTileElems));
     CU_TRY(h, dev_alloc(h, &P.step_ctr, 2));
-    CU_TRY(h, dev_alloc(h, &P.hdr, tiles * kHdrTileBytes));
+    CU_TRY(h, dev_alloc(h, &P.hdr, tiles * kEnvTileBytes));
     {   // headers start zeroed, with "no scene prepared" in the service-owned words
-        std::vector<unsigned char> init(tiles * kHdrTileBytes, 0);
+        std::vector<unsigned char> init(tiles * kEnvTileBytes, 0);
         for (size_t b = 0; b < tiles * 32; ++b) {
             const Hdr hv = header_at(init.data(), (int)b);
             hv.n(I_NEXT_TAG) = -1;
@@ -134,7 +133,6 @@ static int create_impl(uavenv *h) {
         CU_TRY(h, cudaMemcpy(P.hdr, init.data(), init.size(), cudaMemcpyHostToDevice));
     }
     CU_TRY(h, cudaMemset(P.step_ctr, 0, 2 * sizeof(uint32_t)));
-    CU_TRY(h, cudaMemset(P.hist, 0, tiles * kRingTileElems * sizeof(float2)));
     CU_TRY(h, cudaMemset(P.assigned, 0xff, B * N * sizeof(int32_t)));
     CU_TRY(h, dev_alloc(h, &h->obs_buf, B * kObsFloats));
     CU_TRY(h, dev_alloc(h, &h->d_actions, B));
@@ -356,7 +354,7 @@ extern "C" int uavenv_get_scene(uavenv_t *h, uavenv_scene_t *sc, int32_t first_e
     {
         const size_t t0 = fe / 32, t1 = (fe + ce + 31) / 32;
         std::vector<unsigned char> tiles;
-        CU_TRY(h, fetch(tiles, P.hdr + t0 * kHdrTileBytes, (t1 - t0) * kHdrTileBytes));
+        CU_TRY(h, fetch(tiles, P.hdr + t0 * kEnvTileBytes, (t1 - t0) * kEnvTileBytes));
         std::vector<UavRec> U2; std::vector<TgtRec> T2; std::vector<int32_t> ty2; std::vector<double2> tv2, uv2;
         std::vector<NfzRec> Z2; std::vector<IntRec> I2;
         for (int slot = 0; slot < 2; ++slot) {
@@ -425,7 +423,7 @@ extern "C" int uavenv_get_state(uavenv_t *h, uavenv_state_t *st, int32_t first_e
     // header tiles covering [first_env, first_env + count)
     const size_t t0 = f / 32, t1 = (f + c + 31) / 32;
     std::vector<unsigned char> tiles;
-    CU_TRY(h, fetch(tiles, P.hdr + t0 * kHdrTileBytes, (t1 - t0) * kHdrTileBytes));
+    CU_TRY(h, fetch(tiles, P.hdr + t0 * kEnvTileBytes, (t1 - t0) * kEnvTileBytes));
     for (size_t i = 0; i < c; ++i) {
         const Hdr hv = header_at(tiles.data(), (int)(f + i - t0 * 32));
         if (st->uav_idx) st->uav_idx[i] = hv.n(I_K);
@@ -463,9 +461,9 @@ extern "C" int uavenv_set_episode_counters(uavenv_t *h, const int32_t *h_episode
     CU_TRY(h, cudaDeviceSynchronize());
     const size_t f = (size_t)first_env, c = (size_t)count, t0 = f / 32, t1 = (f + c + 31) / 32;
     std::vector<unsigned char> tiles;
-    CU_TRY(h, fetch(tiles, P.hdr + t0 * kHdrTileBytes, (t1 - t0) * kHdrTileBytes));
+    CU_TRY(h, fetch(tiles, P.hdr + t0 * kEnvTileBytes, (t1 - t0) * kEnvTileBytes));
     for (size_t i = 0; i < c; ++i) header_at(tiles.data(), (int)(f + i - t0 * 32)).n(I_EPISODE) = h_episode[i];
-    CU_TRY(h, cudaMemcpy(P.hdr + t0 * kHdrTileBytes, tiles.data(), tiles.size(), cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaMemcpy(P.hdr + t0 * kEnvTileBytes, tiles.data(), tiles.size(), cudaMemcpyHostToDevice));
     return UAVENV_OK;
 }
 

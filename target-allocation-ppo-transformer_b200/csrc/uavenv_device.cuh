@@ -78,6 +78,9 @@ enum I32Field {
 };
 constexpr size_t kHdrTileBytes = (size_t)NF64 * 32 * sizeof(double) + (size_t)NI32 * 32 * sizeof(int32_t);
 constexpr int kRingTileElems = 5 * 7 * 32;  // float2 elements of one warp tile of the observation ring
+// header tile and ring tile of a warp are adjacent: one 13.75 KB neighbourhood (one TLB page) per warp for all of its
+// streamed per-env state
+constexpr size_t kEnvTileBytes = kHdrTileBytes + (size_t)kRingTileElems * sizeof(float2);
 
 struct Hdr {  // view of one env's header: field x lives at d[x*32] / i[x*32]
     double *d;
@@ -86,7 +89,7 @@ struct Hdr {  // view of one env's header: field x lives at d[x*32] / i[x*32]
     __host__ __device__ __forceinline__ int32_t &n(int x) const { return i[x * 32]; }
 };
 __host__ __device__ __forceinline__ Hdr header_at(unsigned char *base, int b) {
-    unsigned char *tile = base + (size_t)(b >> 5) * kHdrTileBytes;
+    unsigned char *tile = base + (size_t)(b >> 5) * kEnvTileBytes;
     Hdr h;
     h.d = reinterpret_cast<double *>(tile) + (b & 31);
     h.i = reinterpret_cast<int32_t *>(tile + (size_t)NF64 * 32 * sizeof(double)) + (b & 31);
@@ -115,14 +118,16 @@ struct Params {
     IntRec *intc;       // [2][B][K2]
     uint8_t *pregen_req;  // [B] request counter, written by the env's owner when it consumes / invalidates the next scene
     uint8_t *pregen_ack;  // [B] value of pregen_req the service has satisfied
-    float2 *hist;       // [B/32][5 slots][7 feature pairs][32 lanes] observation ring, warp-tile major
     uint32_t *step_ctr; // [0] = ring head (mod 5), [1] = CTA arrival counter of the running step
-    unsigned char *hdr; // [B/32] header tiles (kHdrTileBytes each)
+    unsigned char *hdr; // [B/32] env tiles (kEnvTileBytes each): header tile, then the observation ring tile
+                        // [5 slots][7 feature pairs][32 lanes] float2
     __host__ __device__ __forceinline__ Hdr header(int b) const { return header_at(hdr, b); }
     __host__ __device__ __forceinline__ size_t uoff(int slot, int b) const { return ((size_t)slot * B + b) * N; }
     __host__ __device__ __forceinline__ size_t toff(int slot, int b) const { return ((size_t)slot * B + b) * M; }
     // ring element (slot, feature pair f) of env b: ring(b)[slot * 224 + f * 32]
-    __host__ __device__ __forceinline__ float2 *ring(int b) const { return hist + (size_t)(b >> 5) * kRingTileElems + (b & 31); }
+    __host__ __device__ __forceinline__ float2 *ring(int b) const {
+        return reinterpret_cast<float2 *>(hdr + (size_t)(b >> 5) * kEnvTileBytes + kHdrTileBytes) + (b & 31);
+    }
 };
 
 // ------------------------------------------------------------------------------------------------

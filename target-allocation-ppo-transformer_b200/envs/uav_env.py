@@ -78,20 +78,29 @@ class UAVEnvBatched:
         self._h = h
         B, dev = self.num_envs, self.device
         self.obs = torch.zeros(B, _capi.SEQ_LEN, _capi.STATE_DIM, dtype=torch.float32, device=dev)
-        self.reward = torch.zeros(B, dtype=torch.float32, device=dev)
-        self._done_u8 = torch.zeros(B, dtype=torch.uint8, device=dev)
+        # per-step outputs are carved out of ONE allocation (8-byte aligned slices): fewer distinct pages per launch
+        Bp = (B + 7) // 8 * 8
+        self._io = torch.zeros(Bp * 30, dtype=torch.uint8, device=dev)
+        off = [0]
+
+        def carve(dtype, nbytes_per):
+            t = self._io[off[0]:off[0] + B * nbytes_per].view(dtype)
+            off[0] += Bp * nbytes_per
+            return t
+
+        reward_f64 = carve(torch.float64, 8)
+        self.reward = carve(torch.float32, 4)
+        j_val, n_asg = carve(torch.float32, 4), carve(torch.int32, 4)
+        avg_pd, avg_pf = carve(torch.float32, 4), carve(torch.float32, 4)
+        self._done_u8 = carve(torch.uint8, 1)
+        valid = carve(torch.int8, 1)
         self.done = self._done_u8.view(torch.bool)
         self.info = {}
         self._info_c = None
         if with_info:
-            self.info = {
-                "J_val": torch.zeros(B, dtype=torch.float32, device=dev),
-                "num_assigned": torch.zeros(B, dtype=torch.int32, device=dev),
-                "is_valid_action": torch.zeros(B, dtype=torch.int8, device=dev),   # -1 None / 0 False / 1 True
-                "avg_p_dmg": torch.zeros(B, dtype=torch.float32, device=dev),
-                "avg_p_final": torch.zeros(B, dtype=torch.float32, device=dev),
-                "reward_f64": torch.zeros(B, dtype=torch.float64, device=dev),
-            }
+            self.info = {"J_val": j_val, "num_assigned": n_asg,
+                         "is_valid_action": valid,                     # -1 None / 0 False / 1 True
+                         "avg_p_dmg": avg_pd, "avg_p_final": avg_pf, "reward_f64": reward_f64}
             ic = _capi.UavenvInfo()
             ic.d_J_val = self.info["J_val"].data_ptr()
             ic.d_num_assigned = self.info["num_assigned"].data_ptr()
