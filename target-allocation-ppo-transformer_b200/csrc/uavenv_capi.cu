@@ -105,7 +105,6 @@ static int create_impl(uavenv *h) {
     P.tgt_x_lo = c.target_gen_x_lo; P.tgt_x_hi = c.target_gen_x_hi; P.intercept_rad = c.intercept_rad;
     P.seed_lo = (uint32_t)h->seed; P.seed_hi = (uint32_t)(h->seed >> 32);
     P.env_id_base = (uint32_t)h->env_id_base;
-    if (const char *dbg = getenv("UAVENV_DEBUG")) P.debug = atoi(dbg);
     // scene storage is double-buffered (current scene + the pre-generated next one)
     CU_TRY(h, dev_alloc(h, &P.uav, 2 * B * N));
     CU_TRY(h, dev_alloc(h, &P.tgt, 2 * B * M));

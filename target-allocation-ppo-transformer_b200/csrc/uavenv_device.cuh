@@ -104,7 +104,6 @@ struct Params {
     double map_w, map_h, uav_x_lo, uav_x_hi, tgt_x_lo, tgt_x_hi, intercept_rad;
     uint32_t seed_lo, seed_hi;
     uint32_t env_id_base;
-    int32_t debug;      // only read when built with -DUAVENV_DEBUG_FLAGS (bandwidth attribution experiments)
     // device arrays.  Scene storage is double-buffered ([2 slots]...): the current scene of an env lives in
     // slot (I_GEN & 1); the other slot receives the env's NEXT scene ahead of time (pre-generation service),
     // so the scheduled regeneration of main_train.py:79 is a slot flip on the step's critical path.

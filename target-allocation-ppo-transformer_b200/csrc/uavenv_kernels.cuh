@@ -336,11 +336,6 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
     const int N = P.N, M = P.M;
     const Hdr H = P.header(bc);
     float *tile = s_tile[warp] + lane * kObsFloats;
-#ifdef UAVENV_DEBUG_FLAGS
-    const int dbg = P.debug;  // 1: no window store, 2: no ring loads, 4: no ring store, 8: records of env-local pair 0
-#else
-    constexpr int dbg = 0;
-#endif
 
     // ---- trip 1: everything that depends on b only (all loads issued before anything is consumed) ----
     const uint32_t head_old = P.step_ctr[0];
@@ -366,7 +361,7 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
         const float2 *src = ring + slot * (kStateDim / 2) * 32;
         float *dst = tile + (kSeqLen - 1 - a) * kStateDim;
 #pragma unroll
-        for (int f = 0; f < kStateDim / 2; ++f) if (!(dbg & 2)) cp_async_8(dst + 2 * f, src + f * 32);
+        for (int f = 0; f < kStateDim / 2; ++f) cp_async_8(dst + 2 * f, src + f * 32);
     }
     if (tid == 0) {
         // arrive; the last CTA to have READ the head publishes the new one (kept on the device so that
@@ -458,8 +453,8 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
             warp_regen_inline(P, regen_mask, b0, slot, gen >> 1, s_keys);
         }
         if (live && (pass == 0 ? (!done || soft) : inline_regen)) {
-            const UavRec u = P.uav[P.uoff(slot, b) + ((dbg & 8) ? 0 : k)];
-            TgtRec t = P.tgt[P.toff(slot, b) + ((dbg & 8) ? 0 : m)];  // sees this thread's own accept store on target m
+            const UavRec u = P.uav[P.uoff(slot, b) + k];
+            TgtRec t = P.tgt[P.toff(slot, b) + m];   // sees this thread's own accept store on target m
             if (soft) { t.nh = 1.0; t.nh_pure = 1.0; t.lock_cost = 0.0; t.lock_cnt = 0; }  // cleared below by the warp
             cp_async_wait_all();                        // ring rows have landed in the tile (gathers still in flight)
             const int nprev = age < kSeqLen - 1 ? age : kSeqLen - 1;
@@ -479,7 +474,7 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
 #pragma unroll
             for (int f = 0; f < kStateDim / 2; ++f) {
                 const float2 v = make_float2(row[2 * f], row[2 * f + 1]);
-                if (!(dbg & 4)) dsth[f * 32] = v;
+                dsth[f * 32] = v;
                 *reinterpret_cast<float2 *>(tile + (kSeqLen - 1) * kStateDim + 2 * f) = v;
             }
             H.n(I_K) = k; H.n(I_M) = m; H.n(I_NASSIGNED) = nA; H.n(I_NCOVERED) = n0; H.n(I_AGE) = nprev + 1;
@@ -502,7 +497,7 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
     __syncwarp();
     {
         const int nenv = min(32, P.B - b0);
-        if (nenv > 0 && !(dbg & 1)) {
+        if (nenv > 0) {
             float *dst = io.obs + (size_t)b0 * kObsFloats;
             const float *src = s_tile[warp];
             const uint32_t bytes = (uint32_t)nenv * kObsFloats * sizeof(float);
