@@ -58,6 +58,33 @@ int uavpolicy_set_fused(uavpolicy_t *p, int32_t fused);
  * (A, W bf16 row-major on the device; N <= 384, N % 16 == 0; K = 128 or 256). */
 int uavpolicy_selftest_gemm_tile(const void *d_A, const void *d_W, float *d_D, int32_t N, int32_t K, void *stream);
 
+/* ---- PPO update: forward + backward of the two transformer trunks (csrc/policy_train.cu) ---------------------
+ * Replaces the trunk part of policy.evaluate(state, action) (networks/transformer_net.py:124-143 -> :47-65, called
+ * from agents/ppo.py:126) and of loss.backward() (agents/ppo.py:157) for a minibatch of n windows.  bf16 activations
+ * and GEMM operands with fp32 accumulation, fp32 LayerNorm / softmax / parameter gradients.  The MLP heads and the
+ * loss stay with the caller: features out, feature gradients in. */
+typedef struct uavtrain uavtrain_t;
+
+int uavtrain_create(int32_t device, int32_t max_samples, uavtrain_t **out);
+int uavtrain_destroy(uavtrain_t *p);
+const char *uavtrain_last_error(const uavtrain_t *p);   /* p may be NULL (create failures) */
+
+/* d_flat_params: the UAVPOLICY_NUM_PARAMS fp32 parameters in uavpolicy_set_weights order (read in place; must stay
+ * valid and unchanged until the matching uavtrain_backward returned); d_obs [n,5,14] f32 (likewise);
+ * d_feat [n,2,128] f32 out: last-token features of the actor trunk ([:,0,:]) and of the critic trunk ([:,1,:]),
+ * i.e. the inputs of actor_head / critic_head (transformer_net.py:106,114). */
+int uavtrain_forward(uavtrain_t *p, const float *d_flat_params, const float *d_obs, int32_t n, float *d_feat, void *stream);
+
+/* d_dfeat [n,2,128] f32: gradient of the loss w.r.t. d_feat.  d_flat_grad [UAVPOLICY_NUM_PARAMS] f32 is OVERWRITTEN:
+ * trunk parameter gradients at their parameter offsets, zeros at the head parameters' offsets. */
+int uavtrain_backward(uavtrain_t *p, const float *d_dfeat, float *d_flat_grad, void *stream);
+
+/* self-test of the tcgen05 weight-gradient kernel (csrc/policy_wgrad.cu): d_dw[n_out,k_in] (f32) +=
+ * dY[rows,n_out]^T X[rows,k_in]; bf16 row-major inputs with row strides ld_dy / ld_x (elements, multiples of 8);
+ * n_out % 128 == 0, k_in = 128 or 256. */
+int uavpolicy_selftest_wgrad(const void *d_dy, int64_t ld_dy, const void *d_x, int64_t ld_x, int32_t rows, int32_t n_out,
+                             int32_t k_in, float *d_dw, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

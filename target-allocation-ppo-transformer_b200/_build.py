@@ -43,8 +43,10 @@ LIBS = {
     ],
     POLICY_LIB_PATH: [
         ("policy_gemm.cu", "CUTLASS", ["policy_gemm.cuh"]),
-        ("policy_forward.cu", [], ["policy_gemm.cuh", "../../include/uavpolicy_b200.h"]),
-        ("policy_fused.cu", [], ["tcgen05_util.cuh", "../../include/uavpolicy_b200.h"]),
+        ("policy_forward.cu", [], ["policy_gemm.cuh", "policy_kernels.cuh", "policy_weights.cuh", "../../include/uavpolicy_b200.h"]),
+        ("policy_train.cu", [], ["policy_gemm.cuh", "policy_kernels.cuh", "policy_weights.cuh", "../../include/uavpolicy_b200.h"]),
+        ("policy_wgrad.cu", [], ["tcgen05_util.cuh", "policy_weights.cuh", "../../include/uavpolicy_b200.h"]),
+        ("policy_fused.cu", [], ["tcgen05_util.cuh", "policy_weights.cuh", "../../include/uavpolicy_b200.h"]),
     ],
 }
 

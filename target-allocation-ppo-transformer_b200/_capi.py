@@ -158,8 +158,17 @@ def load_policy():
     L.uavpolicy_get_action.argtypes = [vp, vp, i32, u64, u64, u64, vp, vp, vp, vp, vp, vp]
     L.uavpolicy_set_fused.argtypes = [vp, i32]
     L.uavpolicy_selftest_gemm_tile.argtypes = [vp, vp, vp, i32, i32, vp]
+    i64 = C.c_int64
+    L.uavpolicy_selftest_wgrad.argtypes = [vp, i64, vp, i64, i32, i32, i32, vp, vp]
+    L.uavtrain_create.argtypes = [i32, i32, C.POINTER(vp)]
+    L.uavtrain_destroy.argtypes = [vp]
+    L.uavtrain_last_error.argtypes = [vp]
+    L.uavtrain_last_error.restype = C.c_char_p
+    L.uavtrain_forward.argtypes = [vp, vp, vp, i32, vp, vp]
+    L.uavtrain_backward.argtypes = [vp, vp, vp, vp]
     for name in ("uavpolicy_create", "uavpolicy_destroy", "uavpolicy_set_weights", "uavpolicy_get_action",
-                 "uavpolicy_set_fused", "uavpolicy_selftest_gemm_tile"):
+                 "uavpolicy_set_fused", "uavpolicy_selftest_gemm_tile", "uavpolicy_selftest_wgrad", "uavtrain_create",
+                 "uavtrain_destroy", "uavtrain_forward", "uavtrain_backward"):
         getattr(L, name).restype = C.c_int
     _policy_lib = L
     return L

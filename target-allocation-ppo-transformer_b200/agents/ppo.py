@@ -118,9 +118,15 @@ class PPOAgent:
         self._gen = torch.Generator(device=dev).manual_seed(seed + 1 + (
             torch.distributed.get_rank(group) if self.world > 1 else 0))
         # the update's GEMMs (PyTorch autograd on the mirror network): "tf32" tensor-core math or strict "fp32"
-        if update_precision not in ("tf32", "fp32", "bf16"):
-            raise ValueError("update_precision must be 'tf32', 'fp32' or 'bf16' (autocast)")
+        # or "fused": the hand-written sm_100a forward + backward of both trunks (csrc/policy_train.cu; bf16 operands,
+        # fp32 accumulation and gradients), PyTorch only for the two small heads and the loss
+        if update_precision not in ("tf32", "fp32", "bf16", "fused"):
+            raise ValueError("update_precision must be 'fused', 'tf32', 'fp32' or 'bf16' (autocast)")
         self.update_precision = update_precision
+        self.trunks = None
+        if update_precision == "fused":
+            from ..networks.fused_train import FusedTrunks
+            self.trunks = FusedTrunks(min(self.minibatch_size, T * B), dev)
         # rollout forward on the tensor cores (csrc/policy_forward.cu) instead of the fp32 PyTorch mirror
         self.fused = None
         self._rollout_step = 0
@@ -180,8 +186,11 @@ class PPOAgent:
             perm = torch.randperm(n, device=self.device, generator=self._gen)
             for i in range(0, n - mb + 1, mb):                                     # drop_last=True (:115)
                 idx = perm[i:i + mb]
-                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.update_precision == "bf16"):
-                    logp, value, entropy = self.policy.evaluate(obs[idx], act[idx])
+                if self.trunks is not None:
+                    logp, value, entropy = self.trunks.evaluate(self.policy, obs[idx], act[idx])
+                else:
+                    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.update_precision == "bf16"):
+                        logp, value, entropy = self.policy.evaluate(obs[idx], act[idx])
                 logp, value, entropy = logp.float(), value.float().squeeze(-1), entropy.float()
                 ratio = torch.exp(logp - old_logp[idx])                             # :131
                 a = adv[idx]

@@ -1,0 +1,744 @@
+// policy_train.cu - forward + backward of the two transformer trunks for the PPO update (agents/ppo.py:126-160:
+// policy.evaluate(...) and loss.backward() of networks/transformer_net.py:47-65) on sm_100a.
+//
+// Same formulation as the rollout forward (policy_forward.cu): the last encoder layer of a block computes K/V for all
+// five tokens but everything else for the newest token only.  Activations are bf16 and are KEPT for the backward;
+// LayerNorm statistics, softmax, all reductions and every parameter gradient are fp32.
+//   activation-gradient GEMMs  dX = dY W        -> uavp::gemm_bias_act on pre-transposed bf16 weights (tcgen05)
+//   weight-gradient GEMMs      dW += dY^T X     -> uavp::wgrad (policy_wgrad.cu: split-K, accumulator resident in TMEM)
+//   everything else (LayerNorm / ReLU / attention / embedding backward, bias + LayerNorm parameter gradients) is
+//   hand-written below; bias gradients are accumulated by the kernel that produces the corresponding dY.
+// The MLP heads and the PPO loss stay in PyTorch (two [n,128] feature matrices cross the boundary).
+#include "uavpolicy_b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "policy_gemm.cuh"
+#include "policy_kernels.cuh"
+#include "policy_weights.cuh"
+
+namespace uavp {
+int wgrad_prepare();
+int wgrad(const __nv_bfloat16 *dY, int64_t ld_dy, const __nv_bfloat16 *X, int64_t ld_x, int rows, int Nout, int Kin, float *dW,
+          int num_sms, cudaStream_t stream);
+}  // namespace uavp
+
+namespace {
+using bf16 = __nv_bfloat16;
+
+__device__ __forceinline__ void unpack4(uint2 v, float *o) {
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162 *>(&v.x), b = *reinterpret_cast<const __nv_bfloat162 *>(&v.y);
+    o[0] = __low2float(a); o[1] = __high2float(a); o[2] = __low2float(b); o[3] = __high2float(b);
+}
+__device__ __forceinline__ uint2 pack4(const float *v) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t *>(&a); o.y = *reinterpret_cast<const uint32_t *>(&b);
+    return o;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------- forward extras
+
+// out = LayerNorm(x + y) * g + beta (one warp per row), keeping what the backward needs: the normalised row x^ (bf16)
+// and 1/sigma.  out16 (bf16, dense) and out32 (fp32, row stride out32_stride) are both optional.
+__global__ void add_ln_train_kernel(const bf16 *__restrict__ x, int64_t x_stride, const bf16 *__restrict__ y,
+                                    const float *__restrict__ g, const float *__restrict__ beta, int rows,
+                                    bf16 *__restrict__ out16, float *__restrict__ out32, int64_t out32_stride,
+                                    bf16 *__restrict__ xhat, float *__restrict__ rstd_out) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    float a[4], b[4], v[4];
+    unpack4(*reinterpret_cast<const uint2 *>(x + (size_t)r * x_stride + lane * 4), a);
+    unpack4(*reinterpret_cast<const uint2 *>(y + (size_t)r * D + lane * 4), b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = a[i] + b[i];
+    const float mean = warp_sum(v[0] + v[1] + v[2] + v[3]) * (1.0f / D);
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[i] -= mean; q = fmaf(v[i], v[i], q); }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+    float o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[i] *= rstd; o[i] = v[i] * g[lane * 4 + i] + beta[lane * 4 + i]; }
+    *reinterpret_cast<uint2 *>(xhat + (size_t)r * D + lane * 4) = pack4(v);
+    if (lane == 0) rstd_out[r] = rstd;
+    if (out16) *reinterpret_cast<uint2 *>(out16 + (size_t)r * D + lane * 4) = pack4(o);
+    if (out32) *reinterpret_cast<float4 *>(out32 + (size_t)r * out32_stride + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// fp32 row-major [N,K] -> bf16 copy and / or bf16 transposed copy [K,N]; one launch converts every GEMM weight
+struct PrepJob { const float *src; bf16 *dst, *dst_t; int N, K; };
+constexpr int kMaxPrepJobs = 24;
+struct PrepJobs { PrepJob job[kMaxPrepJobs]; };
+__global__ void prep_weights_kernel(const __grid_constant__ PrepJobs jobs) {
+    const PrepJob &j = jobs.job[blockIdx.y];
+    const int n = j.N * j.K;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const bf16 v = __float2bfloat16(j.src[i]);
+        if (j.dst) j.dst[i] = v;
+        if (j.dst_t) j.dst_t[(size_t)(i % j.K) * j.N + i / j.K] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- backward kernels
+
+// block-level reduction of per-lane column partial sums: part[NV] of every warp (lane owns columns col(lane, i)) ->
+// one atomicAdd per column per CTA.  s_red: [warps][C] floats.
+template <int NV, int C, typename ColFn>
+__device__ __forceinline__ void block_colsum_flush(const float *part, float *s_red, float *dst, ColFn col) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s_red[warp * C + col(lane, i)] = part[i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.0f;
+        for (int w = 0; w < nwarps; ++w) s += s_red[w * C + c];
+        atomicAdd(dst + c, s);
+    }
+    __syncthreads();
+}
+
+// LayerNorm backward over 128 features.  dy = (DY32 ? fp32 rows of stride dy_stride : bf16 dense) [+ add (bf16 dense)];
+//   dz = rstd * (g*dy - mean(g*dy) - x^ * mean(g*dy*x^))       -> bf16 dense (gradient of the pre-norm sum: it flows
+//   into the residual branch and into the GEMM branch alike)
+//   g_gamma += sum_r dy*x^,  g_beta += sum_r dy,  g_bias += sum_r dz (bias of the linear layer that fed the sum)
+// A warp walks `rows_per_warp` consecutive rows with its lanes on fixed columns, so the three column sums stay in
+// registers until the end.
+template <bool DY32>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const void *__restrict__ dy_, int64_t dy_stride, const bf16 *__restrict__ add,
+                                                     const bf16 *__restrict__ xhat, const float *__restrict__ rstd,
+                                                     const float *__restrict__ gamma, int rows, int rows_per_warp,
+                                                     bf16 *__restrict__ dz, float *__restrict__ g_gamma,
+                                                     float *__restrict__ g_beta, float *__restrict__ g_bias) {
+    __shared__ float s_red[8 * D];
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int r0 = gw * rows_per_warp, r1 = min(rows, r0 + rows_per_warp);
+    float gm[4], ag[4] = {0, 0, 0, 0}, ab[4] = {0, 0, 0, 0}, az[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) gm[i] = gamma[lane * 4 + i];
+    for (int r = r0; r < r1; ++r) {
+        float dy[4], xh[4];
+        if (DY32) {
+            const float4 t = *reinterpret_cast<const float4 *>(static_cast<const float *>(dy_) + (size_t)r * dy_stride + lane * 4);
+            dy[0] = t.x; dy[1] = t.y; dy[2] = t.z; dy[3] = t.w;
+        } else {
+            unpack4(*reinterpret_cast<const uint2 *>(static_cast<const bf16 *>(dy_) + (size_t)r * D + lane * 4), dy);
+        }
+        if (add) {
+            float t[4];
+            unpack4(*reinterpret_cast<const uint2 *>(add + (size_t)r * D + lane * 4), t);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dy[i] += t[i];
+        }
+        unpack4(*reinterpret_cast<const uint2 *>(xhat + (size_t)r * D + lane * 4), xh);
+        const float rs = rstd[r];
+        float s1 = 0.0f, s2 = 0.0f, gd[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { gd[i] = gm[i] * dy[i]; s1 += gd[i]; s2 = fmaf(gd[i], xh[i], s2); }
+        for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+        s1 *= (1.0f / D); s2 *= (1.0f / D);
+        float z[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            z[i] = rs * (gd[i] - s1 - xh[i] * s2);
+            ag[i] = fmaf(dy[i], xh[i], ag[i]); ab[i] += dy[i]; az[i] += z[i];
+        }
+        *reinterpret_cast<uint2 *>(dz + (size_t)r * D + lane * 4) = pack4(z);
+    }
+    auto col = [](int l, int i) { return l * 4 + i; };
+    block_colsum_flush<4, D>(ag, s_red, g_gamma, col);
+    block_colsum_flush<4, D>(ab, s_red, g_beta, col);
+    block_colsum_flush<4, D>(az, s_red, g_bias, col);
+}
+
+// ReLU backward over 256 features, in place: dh *= (h > 0); g_bias += column sums of the masked gradient
+__global__ void __launch_bounds__(256) relu_bwd_kernel(bf16 *__restrict__ dh, const bf16 *__restrict__ h, int rows, int rows_per_warp,
+                                                       float *__restrict__ g_bias) {
+    __shared__ float s_red[8 * FF];
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int r0 = gw * rows_per_warp, r1 = min(rows, r0 + rows_per_warp);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int r = r0; r < r1; ++r) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const size_t off = (size_t)r * FF + half * 128 + lane * 4;
+            float g[4], a[4];
+            unpack4(*reinterpret_cast<const uint2 *>(dh + off), g);
+            unpack4(*reinterpret_cast<const uint2 *>(h + off), a);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { g[i] = a[i] > 0.0f ? g[i] : 0.0f; acc[half * 4 + i] += g[i]; }
+            *reinterpret_cast<uint2 *>(dh + off) = pack4(g);
+        }
+    }
+    block_colsum_flush<8, FF>(acc, s_red, g_bias, [](int l, int i) { return (i >> 2) * 128 + l * 4 + (i & 3); });
+}
+
+// g_bias[C] += column sums of a dense bf16 [rows, C] matrix, C = 128 * NB
+template <int NB>
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16 *__restrict__ m, int rows, int rows_per_warp, float *__restrict__ g_bias) {
+    __shared__ float s_red[8 * 128 * NB];
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int r0 = gw * rows_per_warp, r1 = min(rows, r0 + rows_per_warp);
+    float acc[4 * NB];
+#pragma unroll
+    for (int i = 0; i < 4 * NB; ++i) acc[i] = 0.0f;
+    for (int r = r0; r < r1; ++r) {
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+            float g[4];
+            unpack4(*reinterpret_cast<const uint2 *>(m + (size_t)r * (128 * NB) + k * 128 + lane * 4), g);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[k * 4 + i] += g[i];
+        }
+    }
+    block_colsum_flush<4 * NB, 128 * NB>(acc, s_red, g_bias, [](int l, int i) { return (i >> 2) * 128 + l * 4 + (i & 3); });
+}
+
+// attention backward.  dS_ij = p_ij (dO_i.v_j - sum_l p_il dO_i.v_l) / 4;  dQ_i = sum_j dS_ij k_j;  dK_j = sum_i dS_ij q_i;
+// dV_j = sum_i p_ij dO_i.  The softmax rows are recomputed from Q / K (nothing but Q, K, V was kept by the forward).
+struct AttnBwdArgs {
+    const bf16 *q, *k, *v, *gout;      // q rows: (b*NQ+i)*q_stride; k/v rows: (b*S+j)*kv_stride; gout rows dense 128
+    bf16 *gq, *gk, *gv;                // same strides as q / k / v
+    int64_t q_stride, kv_stride;
+    const uint8_t *pad;
+    int n;
+};
+
+// softmax row of one query over the 5 keys of (sample b, head h), and dS for that query
+__device__ __forceinline__ void attn_row_grads(const AttnBwdArgs &a, int64_t b, int h, const float *q, const float *go, float *p, float *ds) {
+    const uint8_t *pad = a.pad + b * S;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+        float kk[DH], s = 0.0f;
+        load16(a.k + (b * S + j) * a.kv_stride + h * DH, kk);
+#pragma unroll
+        for (int e = 0; e < DH; ++e) s = fmaf(q[e], kk[e], s);
+        p[j] = pad[j] ? -INFINITY : s * 0.25f;
+        mx = fmaxf(mx, p[j]);
+    }
+    float den = 0.0f;
+#pragma unroll
+    for (int j = 0; j < S; ++j) { p[j] = __expf(p[j] - mx); den += p[j]; }
+    const float inv = 1.0f / den;
+    float dot = 0.0f;
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+        float vv[DH], s = 0.0f;
+        load16(a.v + (b * S + j) * a.kv_stride + h * DH, vv);
+#pragma unroll
+        for (int e = 0; e < DH; ++e) s = fmaf(go[e], vv[e], s);
+        p[j] *= inv;
+        ds[j] = s;
+        dot = fmaf(p[j], s, dot);
+    }
+#pragma unroll
+    for (int j = 0; j < S; ++j) ds[j] = p[j] * (ds[j] - dot) * 0.25f;
+}
+
+// last layer (one query per sample): thread = (sample, head) owns dQ and all five dK / dV rows of its head
+__global__ void __launch_bounds__(256) attn_bwd_last_kernel(const AttnBwdArgs a) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)a.n * H) return;
+    const int64_t b = idx / H;
+    const int h = (int)(idx % H);
+    float q[DH], go[DH], p[S], ds[S], dq[DH];
+    load16(a.q + b * a.q_stride + h * DH, q);
+    load16(a.gout + b * D + h * DH, go);
+    attn_row_grads(a, b, h, q, go, p, ds);
+#pragma unroll
+    for (int e = 0; e < DH; ++e) dq[e] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+        float kk[DH], dk[DH], dv[DH];
+        load16(a.k + (b * S + j) * a.kv_stride + h * DH, kk);
+#pragma unroll
+        for (int e = 0; e < DH; ++e) { dq[e] = fmaf(ds[j], kk[e], dq[e]); dk[e] = ds[j] * q[e]; dv[e] = p[j] * go[e]; }
+        store16(a.gk + (b * S + j) * a.kv_stride + h * DH, dk);
+        store16(a.gv + (b * S + j) * a.kv_stride + h * DH, dv);
+    }
+    store16(a.gq + b * a.q_stride + h * DH, dq);
+}
+
+// inner layer (five queries): a warp takes 6 (sample, head) pairs, lane = pair * 5 + token.  Pass 1: the lane is query
+// i = token (its softmax row, dS row and dQ).  The 5 x 5 p / dS blocks of a pair cross lanes through shared memory.
+// Pass 2: the lane is key j = token (dK_j, dV_j).
+constexpr int kPairsPerWarp = 6;
+__global__ void __launch_bounds__(256) attn_bwd_full_kernel(const AttnBwdArgs a) {
+    __shared__ float s_p[8][kPairsPerWarp][S][S], s_ds[8][kPairsPerWarp][S][S];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pr = lane / S, t = lane % S;
+    const int64_t pair = ((int64_t)blockIdx.x * 8 + warp) * kPairsPerWarp + pr;
+    const bool live = pr < kPairsPerWarp && pair < (int64_t)a.n * H;
+    const int64_t b = live ? pair / H : 0;
+    const int h = live ? (int)(pair % H) : 0;
+    if (live) {
+        float q[DH], go[DH], p[S], ds[S], dq[DH];
+        load16(a.q + (b * S + t) * a.q_stride + h * DH, q);
+        load16(a.gout + (b * S + t) * D + h * DH, go);
+        attn_row_grads(a, b, h, q, go, p, ds);
+#pragma unroll
+        for (int e = 0; e < DH; ++e) dq[e] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+            float kk[DH];
+            load16(a.k + (b * S + j) * a.kv_stride + h * DH, kk);
+#pragma unroll
+            for (int e = 0; e < DH; ++e) dq[e] = fmaf(ds[j], kk[e], dq[e]);
+            s_p[warp][pr][t][j] = p[j];
+            s_ds[warp][pr][t][j] = ds[j];
+        }
+        store16(a.gq + (b * S + t) * a.q_stride + h * DH, dq);
+    }
+    __syncwarp();
+    if (live) {
+        float dk[DH], dv[DH];
+#pragma unroll
+        for (int e = 0; e < DH; ++e) { dk[e] = 0.0f; dv[e] = 0.0f; }
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+            float q[DH], go[DH];
+            load16(a.q + (b * S + i) * a.q_stride + h * DH, q);
+            load16(a.gout + (b * S + i) * D + h * DH, go);
+            const float dsi = s_ds[warp][pr][i][t], pi = s_p[warp][pr][i][t];
+#pragma unroll
+            for (int e = 0; e < DH; ++e) { dk[e] = fmaf(dsi, q[e], dk[e]); dv[e] = fmaf(pi, go[e], dv[e]); }
+        }
+        store16(a.gk + (b * S + t) * a.kv_stride + h * DH, dk);
+        store16(a.gv + (b * S + t) * a.kv_stride + h * DH, dv);
+    }
+}
+
+// dX[b*5+4] += t[b] + u[b]  (last layer: the newest token's row also receives the Q-projection and residual gradients)
+__global__ void scatter_add_last_kernel(bf16 *__restrict__ dX, const bf16 *__restrict__ t, const bf16 *__restrict__ u, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;       // one thread = 4 features
+    if (i >= n * (D / 4)) return;
+    const int b = i / (D / 4), c = (i % (D / 4)) * 4;
+    float x[4], y[4], z[4];
+    bf16 *dst = dX + ((size_t)b * S + S - 1) * D + c;
+    unpack4(*reinterpret_cast<const uint2 *>(dst), x);
+    unpack4(*reinterpret_cast<const uint2 *>(t + (size_t)b * D + c), y);
+    unpack4(*reinterpret_cast<const uint2 *>(u + (size_t)b * D + c), z);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) x[k] += y[k] + z[k];
+    *reinterpret_cast<uint2 *>(dst) = pack4(x);
+}
+
+// embedding backward: E = relu(obs W^T + b) + pos.  A warp walks a run of windows with lane = 4 features, keeping
+// dW[c][0..13], db[c] and dpos[0..4][c] of its features in registers; the warps of a CTA are reduced through shared
+// memory before the atomics.  dE = g1 (+ g2).
+__global__ void __launch_bounds__(256) embed_bwd_kernel(const float *__restrict__ obs, int n, int samples_per_warp,
+                                                        const bf16 *__restrict__ g1, const bf16 *__restrict__ g2,
+                                                        const float *__restrict__ emb_w, const float *__restrict__ emb_b,
+                                                        float *__restrict__ g_pos, float *__restrict__ g_w, float *__restrict__ g_b) {
+    constexpr int kAcc = F + 1 + S;                            // per feature: 14 dW, db, 5 dpos
+    __shared__ float s_obs[8][S * F + 2];
+    __shared__ float s_red[kAcc][D];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * 8 + warp;
+    for (int i = threadIdx.x; i < kAcc * D; i += blockDim.x) (&s_red[0][0])[i] = 0.0f;
+    __syncthreads();
+    const int b0 = gw * samples_per_warp, b1 = min(n, b0 + samples_per_warp);
+    float w[4][F], bias[4], acc[4][kAcc];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        bias[f] = emb_b[lane * 4 + f];
+#pragma unroll
+        for (int j = 0; j < F; ++j) w[f][j] = emb_w[(lane * 4 + f) * F + j];
+#pragma unroll
+        for (int k = 0; k < kAcc; ++k) acc[f][k] = 0.0f;
+    }
+    for (int b = b0; b < b1; ++b) {
+        __syncwarp();
+        for (int i = lane; i < S * F; i += 32) s_obs[warp][i] = obs[(size_t)b * S * F + i];
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const size_t off = ((size_t)b * S + s) * D + lane * 4;
+            float g[4];
+            unpack4(*reinterpret_cast<const uint2 *>(g1 + off), g);
+            if (g2) {
+                float t[4];
+                unpack4(*reinterpret_cast<const uint2 *>(g2 + off), t);
+#pragma unroll
+                for (int f = 0; f < 4; ++f) g[f] += t[f];
+            }
+            const float *o = s_obs[warp] + s * F;
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                float pre = bias[f];
+#pragma unroll
+                for (int j = 0; j < F; ++j) pre = fmaf(w[f][j], o[j], pre);
+                acc[f][F + 1 + s] += g[f];
+                const float gm = pre > 0.0f ? g[f] : 0.0f;
+                acc[f][F] += gm;
+#pragma unroll
+                for (int j = 0; j < F; ++j) acc[f][j] = fmaf(gm, o[j], acc[f][j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+#pragma unroll
+        for (int k = 0; k < kAcc; ++k) atomicAdd(&s_red[k][lane * 4 + f], acc[f][k]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kAcc * D; i += blockDim.x) {
+        const int k = i / D, c = i % D;
+        const float v = s_red[k][c];
+        if (k < F) atomicAdd(g_w + c * F + k, v);
+        else if (k == F) atomicAdd(g_b + c, v);
+        else atomicAdd(g_pos + (k - F - 1) * D + c, v);
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------- host side
+
+namespace {
+struct LayerT { const bf16 *in_t, *in_q_t, *in_kv_t, *out_t, *l1_t, *l2_t; };          // transposed bf16 GEMM weights
+struct LayerOff { size_t in_w, in_b, out_w, out_b, l1_w, l1_b, l2_w, l2_b, n1_w, n1_b, n2_w, n2_b; };
+struct BlockOff { size_t pos, emb_w, emb_b; LayerOff layer[2]; };
+struct FullAct { bf16 *QKV, *ATT, *XH1, *Y1, *Hf, *XH2, *Xout; float *rstd1, *rstd2; };   // inner layer, R rows
+struct LastAct { bf16 *KV, *Q, *AL, *XH1, *Y1, *Hs, *XH2; float *rstd1, *rstd2; };        // last layer
+}  // namespace
+
+struct uavtrain {
+    int device = 0, max_samples = 0, sms = 0, n = 0;
+    bf16 *arena = nullptr;                       // bf16 GEMM weights: row-major copies and transposes
+    uavp::BlockW actor, critic;                  // fp32 members point into the caller's flat parameter buffer (set per forward)
+    LayerT actor_t[1], critic_t[2];
+    BlockOff actor_off, critic_off;
+    PrepJobs jobs;
+    int n_jobs = 0;
+    size_t job_src_off[kMaxPrepJobs];
+    bf16 *Ea, *Ec;
+    LastAct la, lc;
+    FullAct fc;
+    bf16 *T, *T2;                                // forward scratch (GEMM outputs feeding add+LN)
+    bf16 *dS1, *dS2, *dH, *dQKV, *dXa, *dXb, *dQ, *tmp;   // backward scratch
+    float *zeros = nullptr;
+    uint8_t *pad = nullptr;
+    const float *obs = nullptr;                  // of the last forward (the embedding backward re-reads it)
+    void *gemm_ws = nullptr;
+    std::vector<void *> allocs;
+    std::string err;
+};
+
+namespace {
+thread_local std::string g_terr;
+int tfail(uavtrain *p, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (p) p->err = buf; else g_terr = buf;
+    return code;
+}
+#define T_TRY(p, expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess) return tfail(p, -2, "%s failed: %s", #expr, cudaGetErrorString(e_));      \
+    } while (0)
+
+template <typename T>
+cudaError_t talloc(uavtrain *p, T **ptr, size_t n) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, (n ? n : 1) * sizeof(T));
+    if (e == cudaSuccess) { p->allocs.push_back(q); *ptr = static_cast<T *>(q); }
+    return e;
+}
+
+// lays out the bf16 weight arena of one block and records the conversion jobs; returns the new flat offset
+size_t map_train_block(uavtrain *p, uavp::BlockW &b, LayerT *lt, BlockOff &bo, int layers, size_t off, size_t &arena_off) {
+    b.layers = layers;
+    bo.pos = off; off += S * D;
+    bo.emb_w = off; off += D * F;
+    bo.emb_b = off; off += D;
+    auto take = [&](size_t elems) { bf16 *q = p->arena + arena_off; arena_off += (elems + 63) / 64 * 64; return q; };
+    auto job = [&](size_t src_off, bf16 *dst, bf16 *dst_t, int N, int K) {
+        p->job_src_off[p->n_jobs] = src_off;
+        p->jobs.job[p->n_jobs++] = PrepJob{nullptr, dst, dst_t, N, K};
+    };
+    for (int l = 0; l < layers; ++l) {
+        uavp::LayerW &L = b.layer[l];
+        LayerOff &o = bo.layer[l];
+        bf16 *in_w = take(3 * D * D), *in_t = take(3 * D * D), *in_q_t = take(D * D), *in_kv_t = take(2 * D * D);
+        bf16 *out_w = take(D * D), *out_t = take(D * D), *l1_w = take(FF * D), *l1_t = take(FF * D), *l2_w = take(D * FF), *l2_t = take(D * FF);
+        L.in_w = in_w; L.out_w = out_w; L.l1_w = l1_w; L.l2_w = l2_w;
+        L.in_wp = L.out_wp = L.l1_wp = L.l2_wp = nullptr;
+        lt[l] = LayerT{in_t, in_q_t, in_kv_t, out_t, l1_t, l2_t};
+        o.in_w = off; job(off, in_w, in_t, 3 * D, D); job(off, nullptr, in_q_t, D, D); job(off + D * D, nullptr, in_kv_t, 2 * D, D);
+        off += 3 * D * D;
+        o.in_b = off; off += 3 * D;
+        o.out_w = off; job(off, out_w, out_t, D, D); off += D * D;
+        o.out_b = off; off += D;
+        o.l1_w = off; job(off, l1_w, l1_t, FF, D); off += FF * D;
+        o.l1_b = off; off += FF;
+        o.l2_w = off; job(off, l2_w, l2_t, D, FF); off += D * FF;
+        o.l2_b = off; off += D;
+        o.n1_w = off; off += D; o.n1_b = off; off += D; o.n2_w = off; off += D; o.n2_b = off; off += D;
+    }
+    return off;
+}
+
+void bind_params(uavp::BlockW &b, const BlockOff &bo, const float *w) {
+    b.pos = w + bo.pos; b.emb_w = w + bo.emb_w; b.emb_b = w + bo.emb_b; b.emb_w2p = nullptr;
+    for (int l = 0; l < b.layers; ++l) {
+        uavp::LayerW &L = b.layer[l];
+        const LayerOff &o = bo.layer[l];
+        L.in_b = w + o.in_b; L.out_b = w + o.out_b; L.l1_b = w + o.l1_b; L.l2_b = w + o.l2_b;
+        L.n1_w = w + o.n1_w; L.n1_b = w + o.n1_b; L.n2_w = w + o.n2_w; L.n2_b = w + o.n2_b;
+    }
+}
+
+struct TCtx { uavtrain *p; cudaStream_t s; int rc; };
+
+void gemm(TCtx &c, const bf16 *A, int64_t lda, const bf16 *W, const float *bias, bf16 *Dst, int M, int N, int K, int relu) {
+    if (c.rc) return;
+    const int r = uavp::gemm_bias_act(A, lda, W, bias ? bias : c.p->zeros, Dst, M, N, K, relu, c.p->gemm_ws, uavp::gemm_workspace_bytes(), c.s);
+    if (r) c.rc = tfail(c.p, -2, "tcgen05 GEMM (M=%d N=%d K=%d) failed with %d", M, N, K, r);
+}
+void wgrad(TCtx &c, const bf16 *dY, int64_t ld_dy, const bf16 *X, int64_t ld_x, int rows, int Nout, int Kin, float *dW) {
+    if (c.rc) return;
+    const int r = uavp::wgrad(dY, ld_dy, X, ld_x, rows, Nout, Kin, dW, c.p->sms, c.s);
+    if (r) c.rc = tfail(c.p, -2, "weight-gradient kernel (rows=%d Nout=%d Kin=%d) failed with %d", rows, Nout, Kin, r);
+}
+void add_ln(TCtx &c, const bf16 *x, int64_t xs, const bf16 *y, const float *g, const float *b, int rows, bf16 *out16, float *out32,
+            int64_t out32_stride, bf16 *xhat, float *rstd) {
+    if (c.rc) return;
+    add_ln_train_kernel<<<(rows * 32 + 255) / 256, 256, 0, c.s>>>(x, xs, y, g, b, rows, out16, out32, out32_stride, xhat, rstd);
+}
+// launch geometry of the "a warp walks consecutive rows" kernels: about 8 CTAs of 8 warps per SM
+inline void row_grid(const uavtrain *p, int rows, int &grid, int &rpw) {
+    const int warps = p->sms * 8 * 8;
+    rpw = (rows + warps - 1) / warps;
+    if (rpw < 4) rpw = 4;
+    grid = ((rows + rpw - 1) / rpw + 7) / 8;
+}
+void ln_bwd(TCtx &c, const float *dy32, int64_t dy_stride, const bf16 *dy16, const bf16 *add, const bf16 *xhat, const float *rstd,
+            const float *gamma, int rows, bf16 *dz, float *g_gamma, float *g_beta, float *g_bias) {
+    if (c.rc) return;
+    int grid, rpw;
+    row_grid(c.p, rows, grid, rpw);
+    if (dy32) ln_bwd_kernel<true><<<grid, 256, 0, c.s>>>(dy32, dy_stride, add, xhat, rstd, gamma, rows, rpw, dz, g_gamma, g_beta, g_bias);
+    else ln_bwd_kernel<false><<<grid, 256, 0, c.s>>>(dy16, D, add, xhat, rstd, gamma, rows, rpw, dz, g_gamma, g_beta, g_bias);
+}
+void relu_bwd(TCtx &c, bf16 *dh, const bf16 *h, int rows, float *g_bias) {
+    if (c.rc) return;
+    int grid, rpw;
+    row_grid(c.p, rows, grid, rpw);
+    relu_bwd_kernel<<<grid, 256, 0, c.s>>>(dh, h, rows, rpw, g_bias);
+}
+void colsum(TCtx &c, const bf16 *m, int rows, int C, float *g_bias) {
+    if (c.rc) return;
+    int grid, rpw;
+    row_grid(c.p, rows, grid, rpw);
+    if (C == 128) colsum_kernel<1><<<grid, 256, 0, c.s>>>(m, rows, rpw, g_bias);
+    else if (C == 256) colsum_kernel<2><<<grid, 256, 0, c.s>>>(m, rows, rpw, g_bias);
+    else colsum_kernel<3><<<grid, 256, 0, c.s>>>(m, rows, rpw, g_bias);
+}
+
+// ---- forward -----------------------------------------------------------------------------------------------
+void last_layer_fwd(TCtx &c, const uavp::LayerW &L, const bf16 *X, int n, LastAct &A, float *feat, int64_t feat_stride) {
+    uavtrain *p = c.p;
+    const int R = n * S;
+    const bf16 *Xl = X + (S - 1) * D;
+    gemm(c, X, D, L.in_w + D * D, L.in_b + D, A.KV, R, 2 * D, D, 0);
+    gemm(c, Xl, (int64_t)S * D, L.in_w, L.in_b, A.Q, n, D, D, 0);
+    if (!c.rc) attn_last_kernel<<<(n * H + 255) / 256, 256, 0, c.s>>>(A.Q, A.KV, p->pad, n, A.AL);
+    gemm(c, A.AL, D, L.out_w, L.out_b, p->T, n, D, D, 0);
+    add_ln(c, Xl, (int64_t)S * D, p->T, L.n1_w, L.n1_b, n, A.Y1, nullptr, 0, A.XH1, A.rstd1);
+    gemm(c, A.Y1, D, L.l1_w, L.l1_b, A.Hs, n, FF, D, 1);
+    gemm(c, A.Hs, FF, L.l2_w, L.l2_b, p->T2, n, D, FF, 0);
+    add_ln(c, A.Y1, D, p->T2, L.n2_w, L.n2_b, n, nullptr, feat, feat_stride, A.XH2, A.rstd2);
+}
+void full_layer_fwd(TCtx &c, const uavp::LayerW &L, const bf16 *X, int n, FullAct &A) {
+    uavtrain *p = c.p;
+    const int R = n * S;
+    gemm(c, X, D, L.in_w, L.in_b, A.QKV, R, 3 * D, D, 0);
+    if (!c.rc) attn_full_kernel<<<(n * H * S + 255) / 256, 256, 0, c.s>>>(A.QKV, p->pad, n, A.ATT);
+    gemm(c, A.ATT, D, L.out_w, L.out_b, p->T, R, D, D, 0);
+    add_ln(c, X, D, p->T, L.n1_w, L.n1_b, R, A.Y1, nullptr, 0, A.XH1, A.rstd1);
+    gemm(c, A.Y1, D, L.l1_w, L.l1_b, A.Hf, R, FF, D, 1);
+    gemm(c, A.Hf, FF, L.l2_w, L.l2_b, p->T, R, D, FF, 0);
+    add_ln(c, A.Y1, D, p->T, L.n2_w, L.n2_b, R, A.Xout, nullptr, 0, A.XH2, A.rstd2);
+}
+
+// ---- backward ----------------------------------------------------------------------------------------------
+// shared tail of both layer kinds: from the gradient of the layer output down to dS1 (gradient of x + attn-proj)
+void ffn_ln_bwd(TCtx &c, const uavp::LayerW &L, const LayerT &T, const LayerOff &o, float *g, int rows, const float *dz32,
+                int64_t dz_stride, const bf16 *dz16, const bf16 *XH2, const float *rstd2, const bf16 *Hact, const bf16 *Y1,
+                const bf16 *XH1, const float *rstd1) {
+    uavtrain *p = c.p;
+    ln_bwd(c, dz32, dz_stride, dz16, nullptr, XH2, rstd2, L.n2_w, rows, p->dS2, g + o.n2_w, g + o.n2_b, g + o.l2_b);
+    wgrad(c, p->dS2, D, Hact, FF, rows, D, FF, g + o.l2_w);
+    gemm(c, p->dS2, D, T.l2_t, nullptr, p->dH, rows, FF, D, 0);
+    relu_bwd(c, p->dH, Hact, rows, g + o.l1_b);
+    wgrad(c, p->dH, FF, Y1, D, rows, FF, D, g + o.l1_w);
+    gemm(c, p->dH, FF, T.l1_t, nullptr, p->tmp, rows, D, FF, 0);
+    ln_bwd(c, nullptr, 0, p->tmp, p->dS2, XH1, rstd1, L.n1_w, rows, p->dS1, g + o.n1_w, g + o.n1_b, g + o.out_b);
+}
+// dX [R,128] <- gradient w.r.t. the layer input (all five tokens)
+void last_layer_bwd(TCtx &c, const uavp::LayerW &L, const LayerT &T, const LayerOff &o, float *g, const bf16 *X, int n, LastAct &A,
+                    const float *dfeat, int64_t dfeat_stride, bf16 *dX) {
+    uavtrain *p = c.p;
+    const int R = n * S;
+    ffn_ln_bwd(c, L, T, o, g, n, dfeat, dfeat_stride, nullptr, A.XH2, A.rstd2, A.Hs, A.Y1, A.XH1, A.rstd1);
+    wgrad(c, p->dS1, D, A.AL, D, n, D, D, g + o.out_w);
+    gemm(c, p->dS1, D, T.out_t, nullptr, p->tmp, n, D, D, 0);                       // dAL
+    if (!c.rc) {
+        AttnBwdArgs a{A.Q, A.KV, A.KV + D, p->tmp, p->dQ, p->dQKV, p->dQKV + D, D, 2 * D, p->pad, n};
+        attn_bwd_last_kernel<<<(n * H + 255) / 256, 256, 0, c.s>>>(a);
+    }
+    colsum(c, p->dQ, n, D, g + o.in_b);
+    colsum(c, p->dQKV, R, 2 * D, g + o.in_b + D);
+    wgrad(c, p->dQ, D, X + (S - 1) * D, (int64_t)S * D, n, D, D, g + o.in_w);
+    wgrad(c, p->dQKV, 2 * D, X, D, R, 2 * D, D, g + o.in_w + D * D);
+    gemm(c, p->dQKV, 2 * D, T.in_kv_t, nullptr, dX, R, D, 2 * D, 0);
+    gemm(c, p->dQ, D, T.in_q_t, nullptr, p->tmp, n, D, D, 0);
+    if (!c.rc) scatter_add_last_kernel<<<(n * (D / 4) + 255) / 256, 256, 0, c.s>>>(dX, p->tmp, p->dS1, n);
+}
+// returns the two addends of the gradient w.r.t. the layer input: dXg (GEMM branch) and p->dS1 (residual branch)
+void full_layer_bwd(TCtx &c, const uavp::LayerW &L, const LayerT &T, const LayerOff &o, float *g, const bf16 *X, int n, FullAct &A,
+                    const bf16 *dY, bf16 *dXg) {
+    uavtrain *p = c.p;
+    const int R = n * S;
+    ffn_ln_bwd(c, L, T, o, g, R, nullptr, 0, dY, A.XH2, A.rstd2, A.Hf, A.Y1, A.XH1, A.rstd1);
+    wgrad(c, p->dS1, D, A.ATT, D, R, D, D, g + o.out_w);
+    gemm(c, p->dS1, D, T.out_t, nullptr, p->tmp, R, D, D, 0);                       // dATT
+    if (!c.rc) {
+        AttnBwdArgs a{A.QKV, A.QKV + D, A.QKV + 2 * D, p->tmp, p->dQKV, p->dQKV + D, p->dQKV + 2 * D, 3 * D, 3 * D, p->pad, n};
+        attn_bwd_full_kernel<<<(n * H + 8 * kPairsPerWarp - 1) / (8 * kPairsPerWarp), 256, 0, c.s>>>(a);
+    }
+    colsum(c, p->dQKV, R, 3 * D, g + o.in_b);
+    wgrad(c, p->dQKV, 3 * D, X, D, R, 3 * D, D, g + o.in_w);
+    gemm(c, p->dQKV, 3 * D, T.in_t, nullptr, dXg, R, D, 3 * D, 0);
+}
+void embed_bwd(TCtx &c, const BlockOff &bo, const uavp::BlockW &b, float *g, int n, const bf16 *g1, const bf16 *g2) {
+    if (c.rc) return;
+    const int warps = c.p->sms * 8 * 4;                         // 4 CTAs of 8 warps per SM
+    const int spw = max(1, (n + warps - 1) / warps);
+    const int grid = ((n + spw - 1) / spw + 7) / 8;
+    embed_bwd_kernel<<<grid, 256, 0, c.s>>>(c.p->obs, n, spw, g1, g2, b.emb_w, b.emb_b, g + bo.pos, g + bo.emb_w, g + bo.emb_b);
+}
+}  // namespace
+
+extern "C" const char *uavtrain_last_error(const uavtrain_t *p) { return p ? p->err.c_str() : g_terr.c_str(); }
+
+extern "C" int uavtrain_create(int32_t device, int32_t max_samples, uavtrain_t **out) {
+    if (!out) return tfail(nullptr, -1, "uavtrain_create: out is NULL");
+    *out = nullptr;
+    if (max_samples <= 0) return tfail(nullptr, -1, "uavtrain_create: max_samples must be > 0");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return tfail(nullptr, -2, "uavtrain_create: no CUDA device; there is no CPU fallback");
+    if (device < 0 || device >= ndev) return tfail(nullptr, -1, "uavtrain_create: device %d out of range", device);
+    uavtrain *p = new (std::nothrow) uavtrain();
+    if (!p) return tfail(nullptr, -3, "out of host memory");
+    p->device = device; p->max_samples = max_samples;
+    auto bail = [&](int rc) { g_terr = p->err; for (void *q : p->allocs) cudaFree(q); delete p; return rc; };
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&p->sms, cudaDevAttrMultiProcessorCount, device);
+    const size_t n = (size_t)max_samples, R = n * S;
+    if (e == cudaSuccess) e = talloc(p, &p->arena, (size_t)3 * (2 * 3 * D * D + 3 * D * D + 2 * D * D + 4 * FF * D) + 64 * 64);
+    bf16 **rowsR128[] = {&p->Ea, &p->Ec, &p->fc.ATT, &p->fc.XH1, &p->fc.Y1, &p->fc.XH2, &p->fc.Xout, &p->T, &p->dS1, &p->dS2, &p->dXa, &p->dXb, &p->tmp};
+    for (auto b : rowsR128) if (e == cudaSuccess) e = talloc(p, b, R * D);
+    bf16 **rowsR256[] = {&p->la.KV, &p->lc.KV, &p->fc.Hf, &p->dH};
+    for (auto b : rowsR256) if (e == cudaSuccess) e = talloc(p, b, R * FF);
+    bf16 **rowsR384[] = {&p->fc.QKV, &p->dQKV};
+    for (auto b : rowsR384) if (e == cudaSuccess) e = talloc(p, b, R * 3 * D);
+    for (LastAct *A : {&p->la, &p->lc}) {
+        bf16 **rowsN128[] = {&A->Q, &A->AL, &A->XH1, &A->Y1, &A->XH2};
+        for (auto b : rowsN128) if (e == cudaSuccess) e = talloc(p, b, n * D);
+        if (e == cudaSuccess) e = talloc(p, &A->Hs, n * FF);
+        if (e == cudaSuccess) e = talloc(p, &A->rstd1, n);
+        if (e == cudaSuccess) e = talloc(p, &A->rstd2, n);
+    }
+    if (e == cudaSuccess) e = talloc(p, &p->T2, n * D);
+    if (e == cudaSuccess) e = talloc(p, &p->dQ, n * D);
+    if (e == cudaSuccess) e = talloc(p, &p->fc.rstd1, R);
+    if (e == cudaSuccess) e = talloc(p, &p->fc.rstd2, R);
+    if (e == cudaSuccess) e = talloc(p, &p->pad, R);
+    if (e == cudaSuccess) e = talloc(p, &p->zeros, (size_t)3 * D);
+    if (e == cudaSuccess) e = cudaMemset(p->zeros, 0, 3 * D * sizeof(float));
+    if (e == cudaSuccess) { void *ws = nullptr; e = cudaMalloc(&ws, uavp::gemm_workspace_bytes()); if (e == cudaSuccess) { p->allocs.push_back(ws); p->gemm_ws = ws; } }
+    if (e != cudaSuccess) { tfail(p, -2, "uavtrain_create: %s", cudaGetErrorString(e)); return bail(-2); }
+    if (uavp::wgrad_prepare() != 0) { tfail(p, -2, "uavtrain_create: cannot reserve shared memory for the weight-gradient kernel"); return bail(-2); }
+    size_t arena_off = 0;
+    size_t off = map_train_block(p, p->actor, p->actor_t, p->actor_off, 1, 0, arena_off);
+    off += uavp::kActorHead;
+    off = map_train_block(p, p->critic, p->critic_t, p->critic_off, 2, off, arena_off);
+    off += uavp::kCriticHead;
+    if (off != (size_t)UAVPOLICY_NUM_PARAMS || p->n_jobs > kMaxPrepJobs) { tfail(p, -1, "internal: parameter layout mismatch"); return bail(-1); }
+    *out = p;
+    return 0;
+}
+
+extern "C" int uavtrain_destroy(uavtrain_t *p) {
+    if (!p) return 0;
+    cudaSetDevice(p->device);
+    cudaDeviceSynchronize();
+    for (void *q : p->allocs) cudaFree(q);
+    delete p;
+    return 0;
+}
+
+extern "C" int uavtrain_forward(uavtrain_t *p, const float *d_flat_params, const float *d_obs, int32_t n, float *d_feat, void *stream) {
+    if (!p) return -1;
+    if (!d_flat_params || !d_obs || !d_feat) return tfail(p, -1, "uavtrain_forward: NULL argument");
+    if (n <= 0 || n > p->max_samples) return tfail(p, -1, "uavtrain_forward: n=%d outside (0, %d]", n, p->max_samples);
+    T_TRY(p, cudaSetDevice(p->device));
+    TCtx c{p, (cudaStream_t)stream, 0};
+    p->n = 0;
+    p->obs = d_obs;
+    bind_params(p->actor, p->actor_off, d_flat_params);
+    bind_params(p->critic, p->critic_off, d_flat_params);
+    for (int j = 0; j < p->n_jobs; ++j) p->jobs.job[j].src = d_flat_params + p->job_src_off[j];
+    prep_weights_kernel<<<dim3(24, p->n_jobs), 256, 0, c.s>>>(p->jobs);
+    const int R = n * S;
+    embed_kernel<<<(R + kEmbTok - 1) / kEmbTok, D, 0, c.s>>>(d_obs, R, p->actor, p->critic, p->Ea, p->Ec, p->pad);
+    last_layer_fwd(c, p->actor.layer[0], p->Ea, n, p->la, d_feat, 2 * D);
+    full_layer_fwd(c, p->critic.layer[0], p->Ec, n, p->fc);
+    last_layer_fwd(c, p->critic.layer[1], p->fc.Xout, n, p->lc, d_feat + D, 2 * D);
+    if (c.rc) return c.rc;
+    T_TRY(p, cudaGetLastError());
+    p->n = n;
+    return 0;
+}
+
+extern "C" int uavtrain_backward(uavtrain_t *p, const float *d_dfeat, float *d_flat_grad, void *stream) {
+    if (!p) return -1;
+    if (!d_dfeat || !d_flat_grad) return tfail(p, -1, "uavtrain_backward: NULL argument");
+    if (p->n <= 0) return tfail(p, -4, "uavtrain_backward without a preceding uavtrain_forward");
+    T_TRY(p, cudaSetDevice(p->device));
+    TCtx c{p, (cudaStream_t)stream, 0};
+    const int n = p->n;
+    float *g = d_flat_grad;
+    T_TRY(p, cudaMemsetAsync(g, 0, (size_t)UAVPOLICY_NUM_PARAMS * sizeof(float), c.s));
+    // actor: one (last) layer on the embedding
+    last_layer_bwd(c, p->actor.layer[0], p->actor_t[0], p->actor_off.layer[0], g, p->Ea, n, p->la, d_dfeat, 2 * D, p->dXa);
+    embed_bwd(c, p->actor_off, p->actor, g, n, p->dXa, nullptr);
+    // critic: last layer, inner layer, embedding
+    last_layer_bwd(c, p->critic.layer[1], p->critic_t[1], p->critic_off.layer[1], g, p->fc.Xout, n, p->lc, d_dfeat + D, 2 * D, p->dXa);
+    full_layer_bwd(c, p->critic.layer[0], p->critic_t[0], p->critic_off.layer[0], g, p->Ec, n, p->fc, p->dXa, p->dXb);
+    embed_bwd(c, p->critic_off, p->critic, g, n, p->dXb, p->dS1);
+    if (c.rc) return c.rc;
+    T_TRY(p, cudaGetLastError());
+    return 0;
+}

@@ -35,6 +35,11 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 __host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// the same with both operands MN-major (bits 15 / 16): the contraction runs over the ROWS of the shared-memory tiles.
+// A K-major canonical tile [rows x W] read this way is an MN-major operand with MN = the W columns and K = the rows:
+// its core matrices (8 rows x 16 B) are the same, only the roles of the two strides swap - the 8-column groups
+// (128 B apart) become the stride dimension (SBO) and the 8-row groups (W * 16 B apart) the leading dimension (LBO).
+__host__ __device__ constexpr uint32_t instr_desc_bf16_mn(int M, int N) { return instr_desc_bf16(M, N) | (1u << 15) | (1u << 16); }
 
 // D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread
 __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -113,6 +118,26 @@ __device__ __forceinline__ void load_canon_async(unsigned char *smem_tile, const
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
     }
 }
+// the same copy for a tile whose tail rows may lie beyond the matrix: rows >= valid_rows are zero-filled (cp.async
+// with a source size of 0 reads nothing and writes zeros)
+__device__ __forceinline__ void load_canon_async_zfill(unsigned char *smem_tile, const __nv_bfloat16 *g, int rows, int K,
+                                                       int64_t ld, int valid_rows, int tid, int nthreads) {
+    const int cq_per_row = K >> 5;
+    const int items = rows * (K >> 3);
+    for (int i = tid; i < items; i += nthreads) {
+        const int grp = i >> 5, in = i & 31;
+        const int rg = grp / cq_per_row, cq = grp % cq_per_row;
+        const int r = rg * 8 + (in & 7), c = cq * 4 + (in >> 3);
+        const uint32_t dst = smem_u32(smem_tile + canon_off(r, c * 8, K));
+        const bool ok = r < valid_rows;
+        const __nv_bfloat16 *src = g + (int64_t)(ok ? r : 0) * ld + c * 8;
+        const uint32_t nbytes = ok ? 16u : 0u;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+    }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 // 1-D bulk TMA copy global -> shared (UBLKCP) of `bytes` (multiple of 16, both sides 16 B aligned); completion is

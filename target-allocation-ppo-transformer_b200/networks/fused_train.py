@@ -1,0 +1,93 @@
+"""The two transformer trunks of the PPO update - forward AND backward - on sm_100a (csrc/policy_train.cu,
+policy_wgrad.cu, policy_gemm.cu) as one autograd function behind `TransformerActorCritic.evaluate`
+(networks/transformer_net.py:124-143, called from agents/ppo.py:126).
+
+    trunks = FusedTrunks(max_samples, device)
+    logp, value, entropy = trunks.evaluate(policy, obs, action)      # differentiable w.r.t. policy.parameters()
+
+bf16 activations / GEMM operands with fp32 accumulation; LayerNorm, softmax, reductions and all parameter gradients
+in fp32.  The MLP heads and the loss run in PyTorch on the two [n,128] feature matrices this op returns."""
+import ctypes as C
+
+import torch
+
+from .. import _capi
+
+NUM_PARAMS = 419267
+
+
+class _TrunkFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, owner, obs, flat):
+        n = obs.shape[0]
+        feat = torch.empty(n, 2, 128, device=obs.device, dtype=torch.float32)
+        owner._chk(owner._lib.uavtrain_forward(owner._h, C.c_void_p(flat.data_ptr()), C.c_void_p(obs.data_ptr()), n,
+                                               C.c_void_p(feat.data_ptr()), owner._stream()))
+        ctx.owner = owner
+        ctx.keep = (obs, flat)              # the backward re-reads both in place
+        owner._pending = n
+        return feat
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        owner = ctx.owner
+        if owner._pending != dfeat.shape[0]:
+            raise RuntimeError("FusedTrunks keeps the activations of ONE forward: backward must follow its forward")
+        dfeat = dfeat.contiguous().float()
+        grad = torch.empty(NUM_PARAMS, device=dfeat.device, dtype=torch.float32)
+        owner._chk(owner._lib.uavtrain_backward(owner._h, C.c_void_p(dfeat.data_ptr()), C.c_void_p(grad.data_ptr()),
+                                                owner._stream()))
+        owner._pending = 0
+        return None, None, grad
+
+
+class FusedTrunks:
+    def __init__(self, max_samples, device):
+        self._h = None
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("the fused PPO update runs on a CUDA device (sm_100a) only")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self._lib = _capi.load_policy()
+        h = C.c_void_p()
+        rc = self._lib.uavtrain_create(self.device.index, int(max_samples), C.byref(h))
+        if rc != 0:
+            raise _capi.UavenvError(rc, (self._lib.uavtrain_last_error(None) or b"").decode())
+        self._h = h
+        self.max_samples = int(max_samples)
+        self._pending = 0
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise _capi.UavenvError(rc, (self._lib.uavtrain_last_error(self._h) or b"").decode())
+
+    def features(self, module, obs):
+        """[n,2,128] fp32: last-token features of actor_net / critic_net; differentiable w.r.t. module.parameters()."""
+        flat = torch.cat([p.reshape(-1) for p in module.parameters()])
+        if flat.numel() != NUM_PARAMS or flat.dtype != torch.float32:
+            raise ValueError("expected the %d fp32 parameters of TransformerActorCritic" % NUM_PARAMS)
+        return _TrunkFn.apply(self, obs.contiguous().float(), flat)
+
+    def evaluate(self, module, obs, action):
+        """== module.evaluate(obs, action) (transformer_net.py:124-143): (log_prob [n], value [n,1], entropy [n])."""
+        feat = self.features(module, obs)
+        logits = module.actor_head(feat[:, 0])
+        value = module.critic_head(feat[:, 1])
+        logp_all = torch.log_softmax(logits, dim=-1)
+        entropy = -(logp_all.exp() * logp_all).sum(-1)
+        return logp_all.gather(-1, action[:, None]).squeeze(-1), value, entropy
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.uavtrain_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -31,8 +31,8 @@ def test_policy_library_exports_every_declared_symbol_and_is_tcgen05():
     import subprocess
     from target_allocation_ppo_transformer_b200 import _build, _capi
     L = _capi.load_policy()
-    names = _declared("uavpolicy_b200.h", "uavpolicy")
-    assert len(names) == 7
+    names = _declared("uavpolicy_b200.h", "uavpolicy|uavtrain")
+    assert len(names) == 13
     for name in names:
         assert hasattr(L, name), "libuavpolicy_b200.so does not export %s" % name
     sass = subprocess.run(["cuobjdump", "-sass", _build.POLICY_LIB_PATH], capture_output=True, text=True).stdout
@@ -42,6 +42,8 @@ def test_policy_library_exports_every_declared_symbol_and_is_tcgen05():
     import torch
     if not torch.cuda.is_available():
         assert L.uavpolicy_create(0, 64, C.byref(h)) == -2 and b"no CPU fallback" in L.uavpolicy_last_error(None)
+        assert L.uavtrain_create(0, 64, C.byref(h)) == -2 and b"no CPU fallback" in L.uavtrain_last_error(None)
+    assert L.uavtrain_create(0, 0, C.byref(h)) == -1
 
 
 def test_library_is_sm100a_only():

@@ -1,0 +1,149 @@
+"""The hand-written sm_100a forward + backward of the PPO update (csrc/policy_train.cu, policy_wgrad.cu) against
+PyTorch autograd on the fp32 mirror network, and against one update of the UNMODIFIED reference agent
+(tests/golden/ppo_update.npz).  bf16 operands / fp32 accumulation: tolerances are stated per test."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def _cos(a, b):
+    return torch.nn.functional.cosine_similarity(a.flatten().double(), b.flatten().double(), dim=0).item()
+
+
+@pytest.mark.parametrize("rows,n_out,k_in,ld_x", [(128, 128, 128, 128), (1000, 128, 128, 128), (4099, 384, 128, 128),
+                                                  (3000, 256, 128, 640), (5000, 128, 256, 256), (200000, 256, 128, 128)])
+def test_tcgen05_weight_gradient_kernel(rows, n_out, k_in, ld_x):
+    """dW += dY^T X with both operands read MN-major from row-major activations; ragged tails; strided X; the
+    accumulator stays in TMEM across all slabs of a CTA.  fp32 accumulation of exact bf16 products: 1e-5 relative."""
+    import uavenv_b200  # noqa: F401
+    from target_allocation_ppo_transformer_b200 import _capi
+    L = _capi.load_policy()
+    g = torch.Generator(device="cuda").manual_seed(rows)
+    dy = (torch.randn(rows, n_out, device="cuda", generator=g) * 0.5).bfloat16()
+    xfull = (torch.randn(rows, ld_x, device="cuda", generator=g) * 0.5).bfloat16()
+    dw = torch.full((n_out, k_in), 0.25, device="cuda")                       # the kernel ACCUMULATES
+    rc = L.uavpolicy_selftest_wgrad(C.c_void_p(dy.data_ptr()), n_out, C.c_void_p(xfull.data_ptr()), ld_x, rows, n_out, k_in,
+                                    C.c_void_p(dw.data_ptr()), None)
+    torch.cuda.synchronize()
+    assert rc == 0
+    ref = dy.double().t() @ xfull[:, :k_in].double() + 0.25
+    assert (dw.double() - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+
+
+def _perturbed_net(seed=0):
+    import uavenv_b200 as ub
+    torch.manual_seed(seed)
+    net = ub.TransformerActorCritic().cuda()
+    with torch.no_grad():                    # biases / LayerNorm parameters start at 0 / 1: make every one of them matter
+        for p in net.parameters():
+            if p.dim() == 1:
+                p.add_(torch.randn_like(p) * 0.1)
+    return net
+
+
+@pytest.mark.parametrize("n", [1000, 4096 + 37])
+def test_trunk_features_and_every_parameter_gradient_match_fp32_autograd(n):
+    """features: 5e-2 absolute at a scale of ~5 (bf16 activations); gradients, per parameter tensor: relative L2 error
+    <= 8e-2 and cosine >= 0.997 (the loosest are linear1.{weight,bias}, where bf16 rounding flips a few ReLU masks;
+    everything else is ~1e-2 / 0.9998); parameters the trunks do not own (the heads) get exactly zero from this op."""
+    from target_allocation_ppo_transformer_b200.networks.fused_train import FusedTrunks
+    net = _perturbed_net()
+    obs = torch.rand(n, 5, 14, device="cuda")
+    obs[: n // 3, :3] = 0                    # padded windows as at the start of an episode
+    obs[n // 3: n // 2, :1] = 0
+    trunks = FusedTrunks(n, "cuda")
+    feat = trunks.features(net, obs)
+    ref = torch.stack([net.actor_net.forward_last(obs), net.critic_net.forward_last(obs)], 1)
+    assert feat.shape == ref.shape and (feat - ref).abs().max().item() < 5e-2
+    dfeat = torch.randn_like(ref) / n
+    net.zero_grad()
+    feat.backward(dfeat)
+    got = {k: p.grad.clone() for k, p in net.named_parameters()}
+    net.zero_grad()
+    ref.backward(dfeat)
+    for k, p in net.named_parameters():
+        if "head" in k:
+            assert p.grad is None and not got[k].any()
+            continue
+        rel = ((got[k] - p.grad).norm() / p.grad.norm()).item()
+        assert rel <= 8e-2 and _cos(got[k], p.grad) >= 0.997, (k, rel, _cos(got[k], p.grad))
+
+
+def test_evaluate_contract_and_repeatability():
+    from target_allocation_ppo_transformer_b200.networks.fused_train import FusedTrunks
+    net = _perturbed_net(1)
+    n = 777
+    obs = torch.rand(n, 5, 14, device="cuda")
+    act = torch.randint(0, 2, (n,), device="cuda")
+    trunks = FusedTrunks(1024, "cuda")
+    lp, v, e = trunks.evaluate(net, obs, act)
+    lp_ref, v_ref, e_ref = net.evaluate(obs, act)
+    assert lp.shape == (n,) and v.shape == (n, 1) and e.shape == (n,)
+    assert (lp - lp_ref).abs().max() < 3e-2 and (v - v_ref).abs().max() < 5e-2 and (e - e_ref).abs().max() < 3e-2
+    (lp.mean() + v.mean()).backward()
+    g1 = torch.cat([p.grad.flatten() for p in net.parameters()])
+    net.zero_grad()
+    lp2, v2, _ = trunks.evaluate(net, obs, act)
+    assert torch.equal(lp, lp2) and torch.equal(v, v2)          # the forward is deterministic
+    (lp2.mean() + v2.mean()).backward()
+    g2 = torch.cat([p.grad.flatten() for p in net.parameters()])
+    assert _cos(g1, g2) > 0.999999                               # backward: fp32 atomics reorder sums, nothing more
+    with pytest.raises(Exception):
+        trunks.features(net, torch.rand(2048, 5, 14, device="cuda"))   # more windows than the workspace holds
+
+
+def test_fused_update_against_the_reference_agents_update():
+    """Same buffer and initial weights as one update of the unmodified reference agent (ppo_update.npz): losses within
+    2e-2 relative / absolute, clipped gradient direction cosine >= 0.99 on the recorded stride-5 sample."""
+    import uavenv_b200 as ub
+    fx = np.load(os.path.join(GOLDEN, "ppo_update.npz"))
+    net = np.load(os.path.join(GOLDEN, "policy_net.npz"))
+    T = len(fx["rewards"])
+    agent = ub.PPOAgent(num_envs=1, horizon=T, device="cuda", cfg=ub.Config(K_EPOCHS=1), minibatch_size=T, update_precision="fused")
+    sd = {str(k): torch.from_numpy(net["p::" + str(k)]) for k in net["keys"]}
+    agent.policy.load_state_dict(sd); agent.policy_old.load_state_dict(sd)
+    obs = torch.from_numpy(fx["obs"]).cuda()
+    agent.buf_obs.copy_(obs[:, None]); agent.buf_action.copy_(torch.from_numpy(fx["actions"]).cuda()[:, None])
+    agent.buf_logp.copy_(torch.from_numpy(fx["logps"]).cuda()[:, None])
+    agent.buf_value.copy_(torch.from_numpy(fx["values"]).cuda()[:, None])
+    agent.buf_reward.copy_(torch.from_numpy(fx["rewards"]).cuda()[:, None])
+    agent.buf_done.copy_(torch.from_numpy(fx["done"]).cuda()[:, None])
+    agent.t = T
+    out = agent.update(last_obs=obs[-1:].clone())
+    assert abs(out["loss_critic"] - float(fx["loss_critic"])) <= 2e-2 * abs(float(fx["loss_critic"]))
+    assert abs(out["loss_actor"] - float(fx["loss_actor"])) <= 2e-2
+    assert abs(out["entropy"] - float(fx["entropy"])) <= 2e-2
+    g = agent._flat_grad.cpu().numpy()[::5].astype(np.float64)
+    ref = fx["grad_clipped_stride5"].astype(np.float64)
+    assert (g * ref).sum() / np.sqrt((g * g).sum() * (ref * ref).sum()) >= 0.99
+
+
+def test_fused_update_trains_like_the_tf32_update():
+    """Two agents, same seed, same rollout: after one multi-epoch update the reported losses agree and the fused agent's
+    parameters moved in the same direction."""
+    import uavenv_b200 as ub
+    B, T = 512, 16
+    agents = [ub.PPOAgent(B, T, "cuda", minibatch_size=2048, seed=3, update_precision=p) for p in ("fused", "tf32")]
+    env = ub.UAVEnvBatched(B, seed=1)
+    obs = env.reset()
+    w0 = torch.cat([p.detach().flatten() for p in agents[0].policy.parameters()]).clone()
+    while not agents[1].full():
+        a = agents[1].select_action(obs)
+        agents[0].buf_obs[agents[0].t].copy_(obs)
+        obs, reward, done, _ = env.step(a)
+        for ag in agents:
+            ag.store_transition(reward, done)
+    for name in ("buf_action", "buf_logp", "buf_value"):
+        getattr(agents[0], name).copy_(getattr(agents[1], name))
+    stats = [ag.update(obs) for ag in agents]
+    for k in ("loss_actor", "loss_critic", "entropy"):
+        assert np.isfinite(stats[0][k]) and abs(stats[0][k] - stats[1][k]) <= 2e-2 * max(1.0, abs(stats[1][k])), (k, stats)
+    d = [torch.cat([p.detach().flatten() for p in ag.policy.parameters()]) - w0 for ag in agents]
+    assert _cos(d[0], d[1]) > 0.8            # Adam's first steps are sign-like: small gradients may flip, the bulk agrees
