@@ -168,7 +168,8 @@ def run_ppo(args):
     K, W = args.steps if args.steps != 200 else 5, min(args.warmup, 3)
     env = ub.UAVEnvBatched(B, device=dev, seed=SCENE_SEED, env_id_base=rank * B)
     agent = ub.PPOAgent(B, T, dev, fused_rollout=True, env_id_base=rank * B, seed=SCENE_SEED,
-                        update_precision=os.environ.get("UAVENV_UPDATE_PRECISION", "tf32"))
+                        update_precision=os.environ.get("UAVENV_UPDATE_PRECISION", "fused"),
+                        graph_update=os.environ.get("UAVENV_GRAPH_UPDATE", "1") != "0")
     obs = env.reset()
 
     def iteration():
@@ -198,7 +199,9 @@ def run_ppo(args):
         print(json.dumps({
             "metric": "ppo_samples_per_sec", "value": samples / (ms * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16 rollout forward (tcgen05) / fp32 update / f64 env", "data": "synthetic",
+            "dtype": "bf16 rollout forward (tcgen05) / %s update%s / f64 env" % (
+                "bf16 tcgen05 (fp32 accumulation, fp32 gradients)" if agent.update_precision == "fused" else agent.update_precision,
+                ", CUDA-graph replay" if agent.graph_update else ""), "data": "synthetic",
             "config": {"workload": PPO["name"], "envs_per_gpu": B, "horizon": T, "k_epochs": 5,
                        "minibatch": agent.minibatch_size, "last_stats": stats,
                        "parallelism": "env-sharded x%d, flat fp32 gradient all-reduce (NCCL) per minibatch" % world},

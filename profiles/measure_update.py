@@ -12,8 +12,9 @@ import uavenv_b200 as ub  # noqa: E402
 
 
 def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 131072
-    prec = sys.argv[2] if len(sys.argv) > 2 else "tf32"
+    pos = [a for a in sys.argv[1:] if not a.startswith("--")]
+    n = int(pos[0]) if pos else 131072
+    prec = pos[1] if len(pos) > 1 else "tf32"
     torch.backends.cuda.matmul.allow_tf32 = prec != "fp32"
     net = ub.TransformerActorCritic().cuda()
     obs = torch.rand(n, 5, 14, device="cuda")
@@ -49,6 +50,10 @@ def main():
         step()
         torch.cuda.synchronize()
     print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=30, max_name_column_width=90))
+    if "--timeline" in sys.argv:                 # every kernel launch of the step, in launch order
+        evs = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA), key=lambda e: e.time_range.start)
+        for e in evs:
+            print("%9.1f us  %s" % (e.time_range.elapsed_us(), e.name[:110]))
 
 
 if __name__ == "__main__":

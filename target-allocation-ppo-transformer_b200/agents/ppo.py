@@ -80,7 +80,7 @@ class PPOAgent:
     """
 
     def __init__(self, num_envs, horizon, device, cfg=None, group=None, minibatch_size=None, seed=0,
-                 fused_rollout=False, env_id_base=0, update_precision="tf32"):
+                 fused_rollout=False, env_id_base=0, update_precision="tf32", graph_update=False):
         from ..configs.config import cfg as global_cfg
         from ..networks.transformer_net import TransformerActorCritic
         self.cfg = cfg or global_cfg
@@ -94,12 +94,15 @@ class PPOAgent:
         self.policy_old = TransformerActorCritic(self.cfg).to(self.device)
         self.policy_old.load_state_dict(self.policy.state_dict())
         c = self.cfg
+        # graph_update: after three eager minibatch steps the whole step is captured once and replayed as one CUDA
+        # graph launch (needs Adam's step counters on the device: capturable=True)
+        self.graph_update = bool(graph_update) and self.device.type == "cuda"
         self.optimizer = torch.optim.Adam([                                       # ppo.py:17-22
             {"params": self.policy.actor_head.parameters(), "lr": c.LR_ACTOR},
             {"params": self.policy.actor_net.parameters(), "lr": c.LR_ACTOR},
             {"params": self.policy.critic_head.parameters(), "lr": c.LR_CRITIC},
             {"params": self.policy.critic_net.parameters(), "lr": c.LR_CRITIC},
-        ])
+        ], capturable=self.graph_update)
         params = list(self.policy.parameters())
         self._flat_grad = torch.zeros(sum(p.numel() for p in params), device=self.device)
         off = 0
@@ -115,6 +118,13 @@ class PPOAgent:
         self.buf_done = torch.zeros(T, B, dtype=torch.bool, device=dev)
         self.t = 0
         self.minibatch_size = int(minibatch_size) if minibatch_size else max(c.BATCH_SIZE, (T * B) // 4)
+        mb = min(self.minibatch_size, T * B)
+        self._mb_idx = torch.zeros(mb, dtype=torch.int64, device=dev)             # persistent inputs of a minibatch step
+        self._ret = torch.zeros(T * B, device=dev)
+        self._adv = torch.zeros(T * B, device=dev)
+        self._mb_sums = torch.zeros(3, device=dev)
+        self._graph, self._graph_warm = None, 0
+        self._side = torch.cuda.Stream(device=dev) if self.graph_update else None
         self._gen = torch.Generator(device=dev).manual_seed(seed + 1 + (
             torch.distributed.get_rank(group) if self.world > 1 else 0))
         # the update's GEMMs (PyTorch autograd on the mirror network): "tf32" tensor-core math or strict "fp32"
@@ -169,6 +179,59 @@ class PPOAgent:
         finally:
             torch.backends.cuda.matmul.allow_tf32 = tf32_before
 
+    def _minibatch_step(self):
+        """One optimiser step (ppo.py:117-168) on the minibatch whose buffer indices sit in self._mb_idx.  Touches only
+        persistent tensors, so that the whole step - gather, evaluate, losses, backward, gradient all-reduce, clip,
+        Adam - can be replayed as one CUDA graph."""
+        c = self.cfg
+        n = self.T * self.B
+        idx = self._mb_idx
+        obs = self.buf_obs.view(n, c.SEQ_LEN, c.STATE_DIM)
+        act, old_logp, old_val = self.buf_action.view(n), self.buf_logp.view(n), self.buf_value.view(n)
+        if self.trunks is not None:
+            logp, value, entropy = self.trunks.evaluate(self.policy, obs[idx], act[idx])
+        else:
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.update_precision == "bf16"):
+                logp, value, entropy = self.policy.evaluate(obs[idx], act[idx])
+        logp, value, entropy = logp.float(), value.float().squeeze(-1), entropy.float()
+        ratio = torch.exp(logp - old_logp[idx])                             # :131
+        a = self._adv[idx]
+        loss_actor = -torch.min(ratio * a, torch.clamp(ratio, 1 - c.EPS_CLIP, 1 + c.EPS_CLIP) * a).mean()
+        v_clip = old_val[idx] + torch.clamp(value - old_val[idx], -c.EPS_CLIP, c.EPS_CLIP)     # :141
+        r = self._ret[idx]
+        loss_critic = torch.max(((value - r) ** 2).mean(), ((v_clip - r) ** 2).mean())           # :143-147
+        ent = entropy.mean()
+        loss = loss_actor + 0.5 * loss_critic - 0.01 * ent                  # :153
+        self._flat_grad.zero_()
+        loss.backward()
+        if self.world > 1:                                                  # the only collective of training
+            torch.distributed.all_reduce(self._flat_grad, group=self.group)
+            self._flat_grad.div_(self.world)
+        norm = self._flat_grad.norm()                                       # clip_grad_norm_ (:160) on the flat view
+        self._flat_grad.mul_(torch.clamp(c.GRAD_NORM_CLIP / (norm + 1e-6), max=1.0))
+        self.optimizer.step()
+        self._mb_sums += torch.stack([loss_actor.detach(), loss_critic.detach(), ent.detach()])
+
+    def _run_minibatch(self):
+        """Eager for the first steps (they double as the warm-up torch wants before a capture), then ONE graph launch."""
+        if not self.graph_update:
+            return self._minibatch_step()
+        if self._graph is not None:
+            return self._graph.replay()
+        cur = torch.cuda.current_stream(self.device)
+        if self._graph_warm < 3:
+            self._graph_warm += 1
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                self._minibatch_step()
+            cur.wait_stream(self._side)
+            return
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=self._side):
+            self._minibatch_step()
+        self._graph = g
+        g.replay()
+
     def _update(self, last_obs):
         c = self.cfg
         with torch.no_grad():
@@ -176,40 +239,17 @@ class PPOAgent:
         returns, adv = compute_gae(self.buf_reward, self.buf_value, self.buf_done, last_value.squeeze(-1), c.GAMMA,
                                    c.GAE_LAMBDA, normalize=True, group=self.group if self.world > 1 else None)
         n = self.T * self.B
-        obs = self.buf_obs.view(n, c.SEQ_LEN, c.STATE_DIM)
-        act, old_logp, old_val = self.buf_action.view(n), self.buf_logp.view(n), self.buf_value.view(n)
-        returns, adv = returns.view(n), adv.view(n)
-        sums = torch.zeros(3, device=self.device)
+        self._ret.copy_(returns.view(n)); self._adv.copy_(adv.view(n))
+        self._mb_sums.zero_()
         count = 0
         mb = min(self.minibatch_size, n)
         for _ in range(c.K_EPOCHS):                                                # ppo.py:112
             perm = torch.randperm(n, device=self.device, generator=self._gen)
             for i in range(0, n - mb + 1, mb):                                     # drop_last=True (:115)
-                idx = perm[i:i + mb]
-                if self.trunks is not None:
-                    logp, value, entropy = self.trunks.evaluate(self.policy, obs[idx], act[idx])
-                else:
-                    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.update_precision == "bf16"):
-                        logp, value, entropy = self.policy.evaluate(obs[idx], act[idx])
-                logp, value, entropy = logp.float(), value.float().squeeze(-1), entropy.float()
-                ratio = torch.exp(logp - old_logp[idx])                             # :131
-                a = adv[idx]
-                loss_actor = -torch.min(ratio * a, torch.clamp(ratio, 1 - c.EPS_CLIP, 1 + c.EPS_CLIP) * a).mean()
-                v_clip = old_val[idx] + torch.clamp(value - old_val[idx], -c.EPS_CLIP, c.EPS_CLIP)     # :141
-                r = returns[idx]
-                loss_critic = torch.max(((value - r) ** 2).mean(), ((v_clip - r) ** 2).mean())           # :143-147
-                ent = entropy.mean()
-                loss = loss_actor + 0.5 * loss_critic - 0.01 * ent                  # :153
-                self._flat_grad.zero_()
-                loss.backward()
-                if self.world > 1:                                                  # the only collective of training
-                    torch.distributed.all_reduce(self._flat_grad, group=self.group)
-                    self._flat_grad.div_(self.world)
-                norm = self._flat_grad.norm()                                       # clip_grad_norm_ (:160) on the flat view
-                self._flat_grad.mul_(torch.clamp(c.GRAD_NORM_CLIP / (norm + 1e-6), max=1.0))
-                self.optimizer.step()
-                sums += torch.stack([loss_actor.detach(), loss_critic.detach(), ent.detach()])
+                self._mb_idx.copy_(perm[i:i + mb])
+                self._run_minibatch()
                 count += 1
+        sums = self._mb_sums
         self.policy_old.load_state_dict(self.policy.state_dict())                  # ppo.py:172
         if self.fused is not None:
             self.fused.sync(self.policy_old)

@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(256) attn_bwd_last_kernel(const AttnBwdArgs a)
 // i = token (its softmax row, dS row and dQ).  The 5 x 5 p / dS blocks of a pair cross lanes through shared memory.
 // Pass 2: the lane is key j = token (dK_j, dV_j).
 constexpr int kPairsPerWarp = 6;
-__global__ void __launch_bounds__(256) attn_bwd_full_kernel(const AttnBwdArgs a) {
+__global__ void __launch_bounds__(256, 2) attn_bwd_full_kernel(const AttnBwdArgs a) {
     __shared__ float s_p[8][kPairsPerWarp][S][S], s_ds[8][kPairsPerWarp][S][S];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pr = lane / S, t = lane % S;
@@ -346,45 +346,66 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const float *__restrict_
                                                         const float *__restrict__ emb_w, const float *__restrict__ emb_b,
                                                         float *__restrict__ g_pos, float *__restrict__ g_w, float *__restrict__ g_b) {
     constexpr int kAcc = F + 1 + S;                            // per feature: 14 dW, db, 5 dpos
+    constexpr int kObsRegs = (S * F + 31) / 32;                // a window's 70 floats spread over the lanes
     __shared__ float s_obs[8][S * F + 2];
     __shared__ float s_red[kAcc][D];
+    __shared__ __align__(16) float s_w[F][D];                  // embedding weight, transposed: a lane reads its 4 features at once
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gw = blockIdx.x * 8 + warp;
     for (int i = threadIdx.x; i < kAcc * D; i += blockDim.x) (&s_red[0][0])[i] = 0.0f;
+    for (int i = threadIdx.x; i < F * D; i += blockDim.x) s_w[i % F][i / F] = emb_w[i];
     __syncthreads();
     const int b0 = gw * samples_per_warp, b1 = min(n, b0 + samples_per_warp);
-    float w[4][F], bias[4], acc[4][kAcc];
+    float bias[4], acc[4][kAcc];
 #pragma unroll
     for (int f = 0; f < 4; ++f) {
         bias[f] = emb_b[lane * 4 + f];
 #pragma unroll
-        for (int j = 0; j < F; ++j) w[f][j] = emb_w[(lane * 4 + f) * F + j];
-#pragma unroll
         for (int k = 0; k < kAcc; ++k) acc[f][k] = 0.0f;
     }
-    for (int b = b0; b < b1; ++b) {
-        __syncwarp();
-        for (int i = lane; i < S * F; i += 32) s_obs[warp][i] = obs[(size_t)b * S * F + i];
-        __syncwarp();
+    // software pipeline: the next window's gradient rows and observation are in flight while this one is consumed
+    uint2 nx1[S], nx2[S];
+    float nxo[kObsRegs];
+    auto fetch = [&](int b) {
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             const size_t off = ((size_t)b * S + s) * D + lane * 4;
-            float g[4];
-            unpack4(*reinterpret_cast<const uint2 *>(g1 + off), g);
-            if (g2) {
-                float t[4];
-                unpack4(*reinterpret_cast<const uint2 *>(g2 + off), t);
+            nx1[s] = *reinterpret_cast<const uint2 *>(g1 + off);
+            nx2[s] = g2 ? *reinterpret_cast<const uint2 *>(g2 + off) : make_uint2(0u, 0u);
+        }
 #pragma unroll
-                for (int f = 0; f < 4; ++f) g[f] += t[f];
-            }
+        for (int i = 0; i < kObsRegs; ++i) nxo[i] = (lane + 32 * i < S * F) ? obs[(size_t)b * S * F + lane + 32 * i] : 0.0f;
+    };
+    if (b0 < b1) fetch(b0);
+    for (int b = b0; b < b1; ++b) {
+        uint2 c1[S], c2[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) { c1[s] = nx1[s]; c2[s] = nx2[s]; }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < kObsRegs; ++i) if (lane + 32 * i < S * F) s_obs[warp][lane + 32 * i] = nxo[i];
+        __syncwarp();
+        if (b + 1 < b1) fetch(b + 1);
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            float g[4], t[4];
+            unpack4(c1[s], g);
+            unpack4(c2[s], t);
             const float *o = s_obs[warp] + s * F;
+            float pre[4];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) { g[f] += t[f]; pre[f] = bias[f]; }
+#pragma unroll
+            for (int j = 0; j < F; ++j) {
+                const float4 wj = *reinterpret_cast<const float4 *>(&s_w[j][lane * 4]);
+                const float oj = o[j];
+                pre[0] = fmaf(wj.x, oj, pre[0]); pre[1] = fmaf(wj.y, oj, pre[1]);
+                pre[2] = fmaf(wj.z, oj, pre[2]); pre[3] = fmaf(wj.w, oj, pre[3]);
+            }
 #pragma unroll
             for (int f = 0; f < 4; ++f) {
-                float pre = bias[f];
-#pragma unroll
-                for (int j = 0; j < F; ++j) pre = fmaf(w[f][j], o[j], pre);
                 acc[f][F + 1 + s] += g[f];
-                const float gm = pre > 0.0f ? g[f] : 0.0f;
+                const float gm = pre[f] > 0.0f ? g[f] : 0.0f;
                 acc[f][F] += gm;
 #pragma unroll
                 for (int j = 0; j < F; ++j) acc[f][j] = fmaf(gm, o[j], acc[f][j]);

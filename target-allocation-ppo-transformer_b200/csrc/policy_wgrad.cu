@@ -1,8 +1,8 @@
 // policy_wgrad.cu - weight gradients of the PPO update on tcgen05: dW[Nout, Kin] += dY[rows, Nout]^T X[rows, Kin].
 //
 // The contraction runs over the batch rows (hundreds of thousands) while the output is a single small matrix, so this
-// is a split-K problem: every CTA owns a strided set of 128-row slabs, streams the dY and X tiles of each slab into
-// shared memory (cp.async, double buffered) and accumulates its partial dW in TMEM across ALL its slabs - one
+// is a split-K problem: every CTA owns a strided set of 64/128-row slabs, streams the dY and X tiles of each slab into
+// shared memory (cp.async, 3-4 stage ring) and accumulates its partial dW in TMEM across ALL its slabs - one
 // tcgen05.mma chain, no intermediate traffic - then adds the partial to the fp32 gradient with coalesced RED.ADD.
 // Both operands are read MN-major straight from the row-major activations (tcgen05_util.cuh: instr_desc_bf16_mn): no
 // transposed copy of dY or X is ever made.  blockIdx.y selects a 128-column block of dY (= 128 rows of dW).
@@ -12,82 +12,93 @@
 namespace uavp {
 namespace {
 
-constexpr int kWgThreads = 256;
-constexpr int kSlab = 128;                                   // rows per slab = 8 k-steps of 16
+constexpr int kWgThreads = 512;
 
+// 64-row slabs; KIN = 128: 6 stages of 32 KB, KIN = 256: 4 stages of 48 KB (192 KB either way).  Loads run
+// kStages - 2 slabs ahead, so the stage being refilled was read by MMAs issued a whole iteration ago.
 template <int KIN>
-struct WgSmem {
-    static constexpr int kA = kSlab * 128 * 2;               // dY sub-tile [128 rows x 128 cols] bf16
-    static constexpr int kB = kSlab * KIN * 2;               // X tile [128 rows x KIN] bf16
+struct WgCfg {
+    static constexpr int kSlab = 64;                         // rows per slab = 4 k-steps of 16
+    static constexpr int kStages = KIN == 128 ? 6 : 4;
+    static constexpr int kAhead = kStages - 2;
+    static constexpr int kA = kSlab * 128 * 2;               // dY sub-tile [kSlab rows x 128 cols] bf16
+    static constexpr int kB = kSlab * KIN * 2;               // X tile [kSlab rows x KIN] bf16
     static constexpr int kStage = kA + kB;
-    static constexpr int kTotal = 2 * kStage + 64;
-    static_assert(128 * (KIN + 1) * 4 <= 2 * kStage, "the epilogue transposes through the operand buffers");
+    static constexpr int kTotal = kStages * kStage + 64;
+    static_assert(128 * (KIN + 1) * 4 <= kStages * kStage, "the epilogue transposes through the operand buffers");
 };
 
 template <int KIN>
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __nv_bfloat16 *__restrict__ dY, int64_t ld_dy,
                                                               const __nv_bfloat16 *__restrict__ X, int64_t ld_x, int rows,
                                                               float *__restrict__ dW) {
-    using SM = WgSmem<KIN>;
+    using SM = WgCfg<KIN>;
+    constexpr int kSlab = SM::kSlab, kStages = SM::kStages;
     extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + 2 * SM::kStage);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 2 * SM::kStage + 32);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + kStages * SM::kStage);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kStages * SM::kStage + 48);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int slabs = (rows + kSlab - 1) / kSlab;
     if ((int)blockIdx.x >= slabs) return;
+    const int cnt = (slabs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // slabs of this CTA
     const int nb = blockIdx.y;
 
     if (warp == 0) tc::tmem_alloc(tmem_slot, KIN);
-    if (tid == 0) { tc::mbar_init(&mbar[0], 1); tc::mbar_init(&mbar[1], 1); tc::fence_mbar_init(); }
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) tc::mbar_init(&mbar[s], 1);
+        tc::fence_mbar_init();
+    }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     constexpr uint32_t idesc = tc::instr_desc_bf16_mn(128, KIN);
 
-    auto issue_loads = [&](int stage, int slab) {
-        unsigned char *a = smem + stage * SM::kStage, *b = a + SM::kA;
-        const int r0 = slab * kSlab, valid = min(kSlab, rows - r0);
+    auto issue_loads = [&](int k) {                          // k-th slab of this CTA -> stage k % kStages
+        unsigned char *a = smem + (k % kStages) * SM::kStage, *b = a + SM::kA;
+        const int r0 = ((int)blockIdx.x + k * (int)gridDim.x) * kSlab, valid = min(kSlab, rows - r0);
         tc::load_canon_async_zfill(a, dY + (int64_t)r0 * ld_dy + nb * 128, kSlab, 128, ld_dy, valid, tid, kWgThreads);
         tc::load_canon_async_zfill(b, X + (int64_t)r0 * ld_x, kSlab, KIN, ld_x, valid, tid, kWgThreads);
     };
 
-    uint32_t phase[2] = {0, 0};
-    int it = 0;
-    issue_loads(0, blockIdx.x);
-    tc::cp_async_commit();
-    for (int slab = blockIdx.x; slab < slabs; slab += gridDim.x, ++it) {
-        const int s = it & 1, next = slab + gridDim.x;
-        if (next < slabs) {
-            if (it >= 1) { tc::mbar_wait(&mbar[s ^ 1], phase[s ^ 1]); phase[s ^ 1] ^= 1; }   // MMAs of slab it-1 done reading
-            issue_loads(s ^ 1, next);
+    constexpr int kAhead = SM::kAhead;
+    for (int k = 0; k < kAhead; ++k) {
+        if (k < cnt) issue_loads(k);
+        tc::cp_async_commit();
+    }
+    for (int it = 0; it < cnt; ++it) {
+        const int pf = it + kAhead;
+        if (pf < cnt) {                                      // refill the stage the MMAs of slab it-2 read
+            if (it >= 2) tc::mbar_wait(&mbar[(it - 2) % kStages], (uint32_t)(((it - 2) / kStages) & 1));
+            issue_loads(pf);
         }
         tc::cp_async_commit();
-        tc::cp_async_wait_group<1>();                        // this slab's tiles have landed
+        tc::cp_async_wait_group<kAhead>();                   // slab `it` has landed
         tc::fence_async_smem();
         __syncthreads();
         if (tid == 0) {
             tc::tc_fence_after();
-            const uint32_t a = tc::smem_u32(smem + s * SM::kStage), b = a + SM::kA;
+            const uint32_t a = tc::smem_u32(smem + (it % kStages) * SM::kStage), b = a + SM::kA;
 #pragma unroll
             for (int j = 0; j < kSlab / 16; ++j) {
                 const uint64_t ad = tc::smem_desc(a + j * 2 * (128 * 16), 128 * 16, 128);
                 const uint64_t bd = tc::smem_desc(b + j * 2 * (KIN * 16), KIN * 16, 128);
                 tc::mma_bf16(tmem, ad, bd, idesc, (it > 0 || j > 0) ? 1u : 0u);
             }
-            tc::mma_commit(&mbar[s]);
+            tc::mma_commit(&mbar[it % kStages]);
         }
     }
-    const int last = (it - 1) & 1;
-    tc::mbar_wait(&mbar[last], phase[last]);                 // commits complete in order: everything is in TMEM
+    tc::mbar_wait(&mbar[(cnt - 1) % kStages], (uint32_t)(((cnt - 1) / kStages) & 1));   // commits complete in order
     tc::tc_fence_after();
+    __syncthreads();
 
     // epilogue: TMEM lane = row of this dW block, columns = KIN.  Transpose through shared memory so that a warp adds
     // 32 consecutive floats of one dW row per instruction.
     float *stage_f = reinterpret_cast<float *>(smem);
-    const int lrow = (warp & 3) * 32 + lane, half = warp >> 2;
+    constexpr int kParts = kWgThreads / 128;                // column ranges: one per group of 4 warps
+    const int lrow = (warp & 3) * 32 + lane, part = warp >> 2;
 #pragma unroll 1
-    for (int c = half * (KIN / 2); c < (half + 1) * (KIN / 2); c += 32) {
+    for (int c = part * (KIN / kParts); c < (part + 1) * (KIN / kParts); c += 32) {
         float v[32];
         tc::tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c, v);
 #pragma unroll
@@ -106,8 +117,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __nv_bfloat1
 }  // namespace
 
 int wgrad_prepare() {
-    if (cudaFuncSetAttribute(wgrad_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem<128>::kTotal) != cudaSuccess) return -1;
-    if (cudaFuncSetAttribute(wgrad_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem<256>::kTotal) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(wgrad_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<128>::kTotal) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(wgrad_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<256>::kTotal) != cudaSuccess) return -1;
     return 0;
 }
 
@@ -115,10 +126,11 @@ int wgrad_prepare() {
 int wgrad(const __nv_bfloat16 *dY, int64_t ld_dy, const __nv_bfloat16 *X, int64_t ld_x, int rows, int Nout, int Kin, float *dW,
           int num_sms, cudaStream_t stream) {
     if (rows <= 0 || Nout % 128 || (Kin != 128 && Kin != 256) || ld_dy % 8 || ld_x % 8) return -1;
-    const int gy = Nout / 128, slabs = (rows + kSlab - 1) / kSlab;
+    const int slab = Kin == 128 ? WgCfg<128>::kSlab : WgCfg<256>::kSlab;
+    const int gy = Nout / 128, slabs = (rows + slab - 1) / slab;
     const int gx = max(1, min(slabs, num_sms / gy));
-    if (Kin == 128) wgrad_kernel<128><<<dim3(gx, gy), kWgThreads, WgSmem<128>::kTotal, stream>>>(dY, ld_dy, X, ld_x, rows, dW);
-    else wgrad_kernel<256><<<dim3(gx, gy), kWgThreads, WgSmem<256>::kTotal, stream>>>(dY, ld_dy, X, ld_x, rows, dW);
+    if (Kin == 128) wgrad_kernel<128><<<dim3(gx, gy), kWgThreads, WgCfg<128>::kTotal, stream>>>(dY, ld_dy, X, ld_x, rows, dW);
+    else wgrad_kernel<256><<<dim3(gx, gy), kWgThreads, WgCfg<256>::kTotal, stream>>>(dY, ld_dy, X, ld_x, rows, dW);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
