@@ -79,6 +79,13 @@ int uavtrain_forward(uavtrain_t *p, const float *d_flat_params, const float *d_o
  * trunk parameter gradients at their parameter offsets, zeros at the head parameters' offsets. */
 int uavtrain_backward(uavtrain_t *p, const float *d_dfeat, float *d_flat_grad, void *stream);
 
+/* The same with the two MLP heads inside (transformer_net.py:78-91,106-115): d_logits [n,2] f32 = actor_head(actor
+ * features), d_value [n] f32 = critic_head(critic features).  The backward takes the loss gradients w.r.t. both and
+ * OVERWRITES d_flat_grad with the gradient of every parameter, heads included. */
+int uavtrain_forward_heads(uavtrain_t *p, const float *d_flat_params, const float *d_obs, int32_t n, float *d_logits,
+                           float *d_value, void *stream);
+int uavtrain_backward_heads(uavtrain_t *p, const float *d_dlogits, const float *d_dvalue, float *d_flat_grad, void *stream);
+
 /* self-test of the tcgen05 weight-gradient kernel (csrc/policy_wgrad.cu): d_dw[n_out,k_in] (f32) +=
  * dY[rows,n_out]^T X[rows,k_in]; bf16 row-major inputs with row strides ld_dy / ld_x (elements, multiples of 8);
  * n_out % 128 == 0, k_in = 128 or 256. */

@@ -8,7 +8,9 @@
 //   weight-gradient GEMMs      dW += dY^T X     -> uavp::wgrad (policy_wgrad.cu: split-K, accumulator resident in TMEM)
 //   everything else (LayerNorm / ReLU / attention / embedding backward, bias + LayerNorm parameter gradients) is
 //   hand-written below; bias gradients are accumulated by the kernel that produces the corresponding dY.
-// The MLP heads and the PPO loss stay in PyTorch (two [n,128] feature matrices cross the boundary).
+// Two boundaries: uavtrain_forward / _backward stop at the trunks' last-token features ([n,2,128] out, their gradient
+// in); uavtrain_forward_heads / _backward_heads also run the two MLP heads (logits [n,2] + value [n] out, their
+// gradients in).  The PPO loss itself stays in PyTorch.
 #include "uavpolicy_b200.h"
 
 #include <cstdarg>
@@ -27,7 +29,7 @@
 namespace uavp {
 int wgrad_prepare();
 int wgrad(const __nv_bfloat16 *dY, int64_t ld_dy, const __nv_bfloat16 *X, int64_t ld_x, int rows, int Nout, int Kin, float *dW,
-          int num_sms, cudaStream_t stream);
+          int nout_valid, int num_sms, cudaStream_t stream);
 }  // namespace uavp
 
 namespace {
@@ -426,6 +428,83 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const float *__restrict_
     }
 }
 
+// second layers of the two heads (transformer_net.py:78-91): logits = W2a ha + b2a, value = W2c hc + b2c; one thread per sample
+__global__ void __launch_bounds__(256) head_out_kernel(const bf16 *__restrict__ Ha, const bf16 *__restrict__ Hc, const float *__restrict__ w2a,
+                                                       const float *__restrict__ b2a, const float *__restrict__ w2c,
+                                                       const float *__restrict__ b2c, int n, float *__restrict__ logits,
+                                                       float *__restrict__ value) {
+    __shared__ float s_w[3][HID];
+    for (int i = threadIdx.x; i < HID; i += blockDim.x) { s_w[0][i] = w2a[i]; s_w[1][i] = w2a[HID + i]; s_w[2][i] = w2c[i]; }
+    __syncthreads();
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    float l0 = b2a[0], l1 = b2a[1], vv = b2c[0];
+#pragma unroll
+    for (int c = 0; c < HID / DH; ++c) {
+        float xa[DH], xc[DH];
+        load16(Ha + (size_t)b * HID + c * DH, xa);
+        load16(Hc + (size_t)b * HID + c * DH, xc);
+#pragma unroll
+        for (int e = 0; e < DH; ++e) {
+            l0 = fmaf(s_w[0][c * DH + e], xa[e], l0);
+            l1 = fmaf(s_w[1][c * DH + e], xa[e], l1);
+            vv = fmaf(s_w[2][c * DH + e], xc[e], vv);
+        }
+    }
+    logits[2 * b] = l0; logits[2 * b + 1] = l1;
+    value[b] = vv;
+}
+
+// backward of both second head layers and of the ReLU in front of them.  A warp walks a run of samples, lane = 2 of
+// the 64 hidden units: dH = (W2^T dout) * (h > 0) goes out as bf16 rows of 128 (columns 64.. stay zero: the weight-
+// gradient kernel consumes 128-column blocks); dW2, db2 and db1 (column sums of dH) are reduced in registers.
+__global__ void __launch_bounds__(256) head_bwd_kernel(const bf16 *__restrict__ Ha, const bf16 *__restrict__ Hc, const float *__restrict__ w2a,
+                                                       const float *__restrict__ w2c, const float *__restrict__ dlogits,
+                                                       const float *__restrict__ dvalue, int n, int samples_per_warp,
+                                                       bf16 *__restrict__ dHa, bf16 *__restrict__ dHc, float *__restrict__ g_w2a,
+                                                       float *__restrict__ g_b2a, float *__restrict__ g_b1a, float *__restrict__ g_w2c,
+                                                       float *__restrict__ g_b2c, float *__restrict__ g_b1c) {
+    constexpr int kAcc = 10;                               // per lane: 2 x {dW2a row 0, dW2a row 1, dW2c, db1a, db1c}
+    __shared__ float s_red[kAcc / 2][HID];
+    __shared__ float s_b2[3];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < (kAcc / 2) * HID; i += blockDim.x) (&s_red[0][0])[i] = 0.0f;
+    if (threadIdx.x < 3) s_b2[threadIdx.x] = 0.0f;
+    __syncthreads();
+    const int gw = blockIdx.x * 8 + warp;
+    const int b0 = gw * samples_per_warp, b1 = min(n, b0 + samples_per_warp);
+    const int j = lane * 2;
+    const float wa0[2] = {w2a[j], w2a[j + 1]}, wa1[2] = {w2a[HID + j], w2a[HID + j + 1]}, wc[2] = {w2c[j], w2c[j + 1]};
+    float acc[5][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}}, sb[3] = {0, 0, 0};
+    for (int b = b0; b < b1; ++b) {
+        const float dl0 = dlogits[2 * b], dl1 = dlogits[2 * b + 1], dv = dvalue[b];
+        const __nv_bfloat162 ha2 = *reinterpret_cast<const __nv_bfloat162 *>(Ha + (size_t)b * HID + j);
+        const __nv_bfloat162 hc2 = *reinterpret_cast<const __nv_bfloat162 *>(Hc + (size_t)b * HID + j);
+        const float ha[2] = {__low2float(ha2), __high2float(ha2)}, hc[2] = {__low2float(hc2), __high2float(hc2)};
+        float da[2], dc[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            da[k] = ha[k] > 0.0f ? dl0 * wa0[k] + dl1 * wa1[k] : 0.0f;
+            dc[k] = hc[k] > 0.0f ? dv * wc[k] : 0.0f;
+            acc[0][k] = fmaf(dl0, ha[k], acc[0][k]); acc[1][k] = fmaf(dl1, ha[k], acc[1][k]); acc[2][k] = fmaf(dv, hc[k], acc[2][k]);
+            acc[3][k] += da[k]; acc[4][k] += dc[k];
+        }
+        sb[0] += dl0; sb[1] += dl1; sb[2] += dv;
+        *reinterpret_cast<__nv_bfloat162 *>(dHa + (size_t)b * D + j) = __floats2bfloat162_rn(da[0], da[1]);
+        *reinterpret_cast<__nv_bfloat162 *>(dHc + (size_t)b * D + j) = __floats2bfloat162_rn(dc[0], dc[1]);
+    }
+#pragma unroll
+    for (int a = 0; a < 5; ++a) { atomicAdd(&s_red[a][j], acc[a][0]); atomicAdd(&s_red[a][j + 1], acc[a][1]); }
+    if (lane == 0) { atomicAdd(&s_b2[0], sb[0]); atomicAdd(&s_b2[1], sb[1]); atomicAdd(&s_b2[2], sb[2]); }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 5 * HID; i += blockDim.x) {
+        const int a = i / HID, c = i % HID;
+        float *dst = a == 0 ? g_w2a + c : a == 1 ? g_w2a + HID + c : a == 2 ? g_w2c + c : a == 3 ? g_b1a + c : g_b1c + c;
+        atomicAdd(dst, s_red[a][c]);
+    }
+    if (threadIdx.x == 0) { atomicAdd(g_b2a, s_b2[0]); atomicAdd(g_b2a + 1, s_b2[1]); atomicAdd(g_b2c, s_b2[2]); }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------- host side
@@ -436,6 +515,8 @@ struct LayerOff { size_t in_w, in_b, out_w, out_b, l1_w, l1_b, l2_w, l2_b, n1_w,
 struct BlockOff { size_t pos, emb_w, emb_b; LayerOff layer[2]; };
 struct FullAct { bf16 *QKV, *ATT, *XH1, *Y1, *Hf, *XH2, *Xout; float *rstd1, *rstd2; };   // inner layer, R rows
 struct LastAct { bf16 *KV, *Q, *AL, *XH1, *Y1, *Hs, *XH2; float *rstd1, *rstd2; };        // last layer
+struct HeadOff { size_t w1, b1, w2, b2; };
+struct HeadT { bf16 *w1, *w1_t; bf16 *Z, *Hh, *dHh; };                                     // bf16 weights, feature / hidden / gradient rows
 }  // namespace
 
 struct uavtrain {
@@ -444,6 +525,9 @@ struct uavtrain {
     uavp::BlockW actor, critic;                  // fp32 members point into the caller's flat parameter buffer (set per forward)
     LayerT actor_t[1], critic_t[2];
     BlockOff actor_off, critic_off;
+    HeadOff ahead_off, chead_off;
+    HeadT ahead, chead;
+    bool with_heads = false;                     // the last forward also ran the heads
     PrepJobs jobs;
     int n_jobs = 0;
     size_t job_src_off[kMaxPrepJobs];
@@ -455,6 +539,7 @@ struct uavtrain {
     float *zeros = nullptr;
     uint8_t *pad = nullptr;
     const float *obs = nullptr;                  // of the last forward (the embedding backward re-reads it)
+    const float *params = nullptr;               // likewise (second head layers)
     void *gemm_ws = nullptr;
     std::vector<void *> allocs;
     std::string err;
@@ -535,9 +620,10 @@ void gemm(TCtx &c, const bf16 *A, int64_t lda, const bf16 *W, const float *bias,
     const int r = uavp::gemm_bias_act(A, lda, W, bias ? bias : c.p->zeros, Dst, M, N, K, relu, c.p->gemm_ws, uavp::gemm_workspace_bytes(), c.s);
     if (r) c.rc = tfail(c.p, -2, "tcgen05 GEMM (M=%d N=%d K=%d) failed with %d", M, N, K, r);
 }
-void wgrad(TCtx &c, const bf16 *dY, int64_t ld_dy, const bf16 *X, int64_t ld_x, int rows, int Nout, int Kin, float *dW) {
+void wgrad(TCtx &c, const bf16 *dY, int64_t ld_dy, const bf16 *X, int64_t ld_x, int rows, int Nout, int Kin, float *dW,
+           int nout_valid = -1) {
     if (c.rc) return;
-    const int r = uavp::wgrad(dY, ld_dy, X, ld_x, rows, Nout, Kin, dW, c.p->sms, c.s);
+    const int r = uavp::wgrad(dY, ld_dy, X, ld_x, rows, Nout, Kin, dW, nout_valid < 0 ? Nout : nout_valid, c.p->sms, c.s);
     if (r) c.rc = tfail(c.p, -2, "weight-gradient kernel (rows=%d Nout=%d Kin=%d) failed with %d", rows, Nout, Kin, r);
 }
 void add_ln(TCtx &c, const bf16 *x, int64_t xs, const bf16 *y, const float *g, const float *b, int rows, bf16 *out16, float *out32,
@@ -576,7 +662,7 @@ void colsum(TCtx &c, const bf16 *m, int rows, int C, float *g_bias) {
 }
 
 // ---- forward -----------------------------------------------------------------------------------------------
-void last_layer_fwd(TCtx &c, const uavp::LayerW &L, const bf16 *X, int n, LastAct &A, float *feat, int64_t feat_stride) {
+void last_layer_fwd(TCtx &c, const uavp::LayerW &L, const bf16 *X, int n, LastAct &A, float *feat, int64_t feat_stride, bf16 *feat16) {
     uavtrain *p = c.p;
     const int R = n * S;
     const bf16 *Xl = X + (S - 1) * D;
@@ -587,7 +673,7 @@ void last_layer_fwd(TCtx &c, const uavp::LayerW &L, const bf16 *X, int n, LastAc
     add_ln(c, Xl, (int64_t)S * D, p->T, L.n1_w, L.n1_b, n, A.Y1, nullptr, 0, A.XH1, A.rstd1);
     gemm(c, A.Y1, D, L.l1_w, L.l1_b, A.Hs, n, FF, D, 1);
     gemm(c, A.Hs, FF, L.l2_w, L.l2_b, p->T2, n, D, FF, 0);
-    add_ln(c, A.Y1, D, p->T2, L.n2_w, L.n2_b, n, nullptr, feat, feat_stride, A.XH2, A.rstd2);
+    add_ln(c, A.Y1, D, p->T2, L.n2_w, L.n2_b, n, feat16, feat, feat_stride, A.XH2, A.rstd2);
 }
 void full_layer_fwd(TCtx &c, const uavp::LayerW &L, const bf16 *X, int n, FullAct &A) {
     uavtrain *p = c.p;
@@ -617,10 +703,10 @@ void ffn_ln_bwd(TCtx &c, const uavp::LayerW &L, const LayerT &T, const LayerOff 
 }
 // dX [R,128] <- gradient w.r.t. the layer input (all five tokens)
 void last_layer_bwd(TCtx &c, const uavp::LayerW &L, const LayerT &T, const LayerOff &o, float *g, const bf16 *X, int n, LastAct &A,
-                    const float *dfeat, int64_t dfeat_stride, bf16 *dX) {
+                    const float *dfeat, int64_t dfeat_stride, const bf16 *dfeat16, bf16 *dX) {
     uavtrain *p = c.p;
     const int R = n * S;
-    ffn_ln_bwd(c, L, T, o, g, n, dfeat, dfeat_stride, nullptr, A.XH2, A.rstd2, A.Hs, A.Y1, A.XH1, A.rstd1);
+    ffn_ln_bwd(c, L, T, o, g, n, dfeat, dfeat_stride, dfeat16, A.XH2, A.rstd2, A.Hs, A.Y1, A.XH1, A.rstd1);
     wgrad(c, p->dS1, D, A.AL, D, n, D, D, g + o.out_w);
     gemm(c, p->dS1, D, T.out_t, nullptr, p->tmp, n, D, D, 0);                       // dAL
     if (!c.rc) {
@@ -677,7 +763,7 @@ extern "C" int uavtrain_create(int32_t device, int32_t max_samples, uavtrain_t *
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&p->sms, cudaDevAttrMultiProcessorCount, device);
     const size_t n = (size_t)max_samples, R = n * S;
-    if (e == cudaSuccess) e = talloc(p, &p->arena, (size_t)3 * (2 * 3 * D * D + 3 * D * D + 2 * D * D + 4 * FF * D) + 64 * 64);
+    if (e == cudaSuccess) e = talloc(p, &p->arena, (size_t)3 * (2 * 3 * D * D + 3 * D * D + 2 * D * D + 4 * FF * D) + 4 * HID * D + 64 * 64);
     bf16 **rowsR128[] = {&p->Ea, &p->Ec, &p->fc.ATT, &p->fc.XH1, &p->fc.Y1, &p->fc.XH2, &p->fc.Xout, &p->T, &p->dS1, &p->dS2, &p->dXa, &p->dXb, &p->tmp};
     for (auto b : rowsR128) if (e == cudaSuccess) e = talloc(p, b, R * D);
     bf16 **rowsR256[] = {&p->la.KV, &p->lc.KV, &p->fc.Hf, &p->dH};
@@ -691,6 +777,12 @@ extern "C" int uavtrain_create(int32_t device, int32_t max_samples, uavtrain_t *
         if (e == cudaSuccess) e = talloc(p, &A->rstd1, n);
         if (e == cudaSuccess) e = talloc(p, &A->rstd2, n);
     }
+    for (HeadT *Hd : {&p->ahead, &p->chead}) {
+        if (e == cudaSuccess) e = talloc(p, &Hd->Z, n * D);
+        if (e == cudaSuccess) e = talloc(p, &Hd->Hh, n * HID);
+        if (e == cudaSuccess) e = talloc(p, &Hd->dHh, n * D);
+        if (e == cudaSuccess) e = cudaMemset(Hd->dHh, 0, n * D * sizeof(bf16));      // columns 64.. are never written again
+    }
     if (e == cudaSuccess) e = talloc(p, &p->T2, n * D);
     if (e == cudaSuccess) e = talloc(p, &p->dQ, n * D);
     if (e == cudaSuccess) e = talloc(p, &p->fc.rstd1, R);
@@ -702,10 +794,22 @@ extern "C" int uavtrain_create(int32_t device, int32_t max_samples, uavtrain_t *
     if (e != cudaSuccess) { tfail(p, -2, "uavtrain_create: %s", cudaGetErrorString(e)); return bail(-2); }
     if (uavp::wgrad_prepare() != 0) { tfail(p, -2, "uavtrain_create: cannot reserve shared memory for the weight-gradient kernel"); return bail(-2); }
     size_t arena_off = 0;
+    auto map_head = [&](HeadT &Hd, HeadOff &ho, int outs, size_t off) {
+        Hd.w1 = p->arena + arena_off; arena_off += HID * D;
+        Hd.w1_t = p->arena + arena_off; arena_off += HID * D;
+        ho.w1 = off;
+        p->job_src_off[p->n_jobs] = off;
+        p->jobs.job[p->n_jobs++] = PrepJob{nullptr, Hd.w1, Hd.w1_t, HID, D};
+        off += HID * D;
+        ho.b1 = off; off += HID;
+        ho.w2 = off; off += (size_t)outs * HID;
+        ho.b2 = off; off += outs;
+        return off;
+    };
     size_t off = map_train_block(p, p->actor, p->actor_t, p->actor_off, 1, 0, arena_off);
-    off += uavp::kActorHead;
+    off = map_head(p->ahead, p->ahead_off, NACT, off);
     off = map_train_block(p, p->critic, p->critic_t, p->critic_off, 2, off, arena_off);
-    off += uavp::kCriticHead;
+    off = map_head(p->chead, p->chead_off, 1, off);
     if (off != (size_t)UAVPOLICY_NUM_PARAMS || p->n_jobs > kMaxPrepJobs) { tfail(p, -1, "internal: parameter layout mismatch"); return bail(-1); }
     *out = p;
     return 0;
@@ -720,46 +824,93 @@ extern "C" int uavtrain_destroy(uavtrain_t *p) {
     return 0;
 }
 
-extern "C" int uavtrain_forward(uavtrain_t *p, const float *d_flat_params, const float *d_obs, int32_t n, float *d_feat, void *stream) {
-    if (!p) return -1;
-    if (!d_flat_params || !d_obs || !d_feat) return tfail(p, -1, "uavtrain_forward: NULL argument");
+namespace {
+int forward_impl(uavtrain *p, const float *w, const float *d_obs, int n, float *d_feat, float *d_logits, float *d_value, void *stream) {
     if (n <= 0 || n > p->max_samples) return tfail(p, -1, "uavtrain_forward: n=%d outside (0, %d]", n, p->max_samples);
     T_TRY(p, cudaSetDevice(p->device));
     TCtx c{p, (cudaStream_t)stream, 0};
+    const bool heads = d_logits != nullptr;
     p->n = 0;
     p->obs = d_obs;
-    bind_params(p->actor, p->actor_off, d_flat_params);
-    bind_params(p->critic, p->critic_off, d_flat_params);
-    for (int j = 0; j < p->n_jobs; ++j) p->jobs.job[j].src = d_flat_params + p->job_src_off[j];
+    bind_params(p->actor, p->actor_off, w);
+    bind_params(p->critic, p->critic_off, w);
+    for (int j = 0; j < p->n_jobs; ++j) p->jobs.job[j].src = w + p->job_src_off[j];
     prep_weights_kernel<<<dim3(24, p->n_jobs), 256, 0, c.s>>>(p->jobs);
     const int R = n * S;
     embed_kernel<<<(R + kEmbTok - 1) / kEmbTok, D, 0, c.s>>>(d_obs, R, p->actor, p->critic, p->Ea, p->Ec, p->pad);
-    last_layer_fwd(c, p->actor.layer[0], p->Ea, n, p->la, d_feat, 2 * D);
+    last_layer_fwd(c, p->actor.layer[0], p->Ea, n, p->la, d_feat, 2 * D, heads ? p->ahead.Z : nullptr);
     full_layer_fwd(c, p->critic.layer[0], p->Ec, n, p->fc);
-    last_layer_fwd(c, p->critic.layer[1], p->fc.Xout, n, p->lc, d_feat + D, 2 * D);
+    last_layer_fwd(c, p->critic.layer[1], p->fc.Xout, n, p->lc, d_feat ? d_feat + D : nullptr, 2 * D, heads ? p->chead.Z : nullptr);
+    if (heads) {
+        gemm(c, p->ahead.Z, D, p->ahead.w1, w + p->ahead_off.b1, p->ahead.Hh, n, HID, D, 1);
+        gemm(c, p->chead.Z, D, p->chead.w1, w + p->chead_off.b1, p->chead.Hh, n, HID, D, 1);
+        if (!c.rc)
+            head_out_kernel<<<(n + 255) / 256, 256, 0, c.s>>>(p->ahead.Hh, p->chead.Hh, w + p->ahead_off.w2, w + p->ahead_off.b2,
+                                                              w + p->chead_off.w2, w + p->chead_off.b2, n, d_logits, d_value);
+    }
     if (c.rc) return c.rc;
     T_TRY(p, cudaGetLastError());
     p->n = n;
+    p->with_heads = heads;
+    p->params = w;
     return 0;
 }
 
-extern "C" int uavtrain_backward(uavtrain_t *p, const float *d_dfeat, float *d_flat_grad, void *stream) {
-    if (!p) return -1;
-    if (!d_dfeat || !d_flat_grad) return tfail(p, -1, "uavtrain_backward: NULL argument");
-    if (p->n <= 0) return tfail(p, -4, "uavtrain_backward without a preceding uavtrain_forward");
+int backward_impl(uavtrain *p, const float *d_dfeat, const float *d_dlogits, const float *d_dvalue, float *g, void *stream) {
     T_TRY(p, cudaSetDevice(p->device));
     TCtx c{p, (cudaStream_t)stream, 0};
     const int n = p->n;
-    float *g = d_flat_grad;
+    const bool heads = d_dlogits != nullptr;
     T_TRY(p, cudaMemsetAsync(g, 0, (size_t)UAVPOLICY_NUM_PARAMS * sizeof(float), c.s));
+    if (heads) {
+        const float *w = p->params;
+        const int warps = p->sms * 8 * 4, spw = max(1, (n + warps - 1) / warps);
+        head_bwd_kernel<<<((n + spw - 1) / spw + 7) / 8, 256, 0, c.s>>>(
+            p->ahead.Hh, p->chead.Hh, w + p->ahead_off.w2, w + p->chead_off.w2, d_dlogits, d_dvalue, n, spw, p->ahead.dHh, p->chead.dHh,
+            g + p->ahead_off.w2, g + p->ahead_off.b2, g + p->ahead_off.b1, g + p->chead_off.w2, g + p->chead_off.b2, g + p->chead_off.b1);
+        wgrad(c, p->ahead.dHh, D, p->ahead.Z, D, n, D, D, g + p->ahead_off.w1, HID);
+        wgrad(c, p->chead.dHh, D, p->chead.Z, D, n, D, D, g + p->chead_off.w1, HID);
+        gemm(c, p->ahead.dHh, D, p->ahead.w1_t, nullptr, p->ahead.Z, n, D, HID, 0);      // dZ overwrites Z (no longer needed)
+        gemm(c, p->chead.dHh, D, p->chead.w1_t, nullptr, p->chead.Z, n, D, HID, 0);
+    }
     // actor: one (last) layer on the embedding
-    last_layer_bwd(c, p->actor.layer[0], p->actor_t[0], p->actor_off.layer[0], g, p->Ea, n, p->la, d_dfeat, 2 * D, p->dXa);
+    last_layer_bwd(c, p->actor.layer[0], p->actor_t[0], p->actor_off.layer[0], g, p->Ea, n, p->la, heads ? nullptr : d_dfeat, 2 * D,
+                   heads ? p->ahead.Z : nullptr, p->dXa);
     embed_bwd(c, p->actor_off, p->actor, g, n, p->dXa, nullptr);
     // critic: last layer, inner layer, embedding
-    last_layer_bwd(c, p->critic.layer[1], p->critic_t[1], p->critic_off.layer[1], g, p->fc.Xout, n, p->lc, d_dfeat + D, 2 * D, p->dXa);
+    last_layer_bwd(c, p->critic.layer[1], p->critic_t[1], p->critic_off.layer[1], g, p->fc.Xout, n, p->lc,
+                   heads ? nullptr : d_dfeat + D, 2 * D, heads ? p->chead.Z : nullptr, p->dXa);
     full_layer_bwd(c, p->critic.layer[0], p->critic_t[0], p->critic_off.layer[0], g, p->Ec, n, p->fc, p->dXa, p->dXb);
     embed_bwd(c, p->critic_off, p->critic, g, n, p->dXb, p->dS1);
     if (c.rc) return c.rc;
     T_TRY(p, cudaGetLastError());
     return 0;
+}
+}  // namespace
+
+extern "C" int uavtrain_forward(uavtrain_t *p, const float *d_flat_params, const float *d_obs, int32_t n, float *d_feat, void *stream) {
+    if (!p) return -1;
+    if (!d_flat_params || !d_obs || !d_feat) return tfail(p, -1, "uavtrain_forward: NULL argument");
+    return forward_impl(p, d_flat_params, d_obs, n, d_feat, nullptr, nullptr, stream);
+}
+
+extern "C" int uavtrain_backward(uavtrain_t *p, const float *d_dfeat, float *d_flat_grad, void *stream) {
+    if (!p) return -1;
+    if (!d_dfeat || !d_flat_grad) return tfail(p, -1, "uavtrain_backward: NULL argument");
+    if (p->n <= 0 || p->with_heads) return tfail(p, -4, "uavtrain_backward without a preceding uavtrain_forward");
+    return backward_impl(p, d_dfeat, nullptr, nullptr, d_flat_grad, stream);
+}
+
+extern "C" int uavtrain_forward_heads(uavtrain_t *p, const float *d_flat_params, const float *d_obs, int32_t n, float *d_logits,
+                                      float *d_value, void *stream) {
+    if (!p) return -1;
+    if (!d_flat_params || !d_obs || !d_logits || !d_value) return tfail(p, -1, "uavtrain_forward_heads: NULL argument");
+    return forward_impl(p, d_flat_params, d_obs, n, nullptr, d_logits, d_value, stream);
+}
+
+extern "C" int uavtrain_backward_heads(uavtrain_t *p, const float *d_dlogits, const float *d_dvalue, float *d_flat_grad, void *stream) {
+    if (!p) return -1;
+    if (!d_dlogits || !d_dvalue || !d_flat_grad) return tfail(p, -1, "uavtrain_backward_heads: NULL argument");
+    if (p->n <= 0 || !p->with_heads) return tfail(p, -4, "uavtrain_backward_heads without a preceding uavtrain_forward_heads");
+    return backward_impl(p, nullptr, d_dlogits, d_dvalue, d_flat_grad, stream);
 }

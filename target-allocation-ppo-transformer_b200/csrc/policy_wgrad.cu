@@ -31,7 +31,7 @@ struct WgCfg {
 template <int KIN>
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __nv_bfloat16 *__restrict__ dY, int64_t ld_dy,
                                                               const __nv_bfloat16 *__restrict__ X, int64_t ld_x, int rows,
-                                                              float *__restrict__ dW) {
+                                                              float *__restrict__ dW, int nout_valid) {
     using SM = WgCfg<KIN>;
     constexpr int kSlab = SM::kSlab, kStages = SM::kStages;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __nv_bfloat1
     tc::tc_fence_before();
     __syncthreads();
     float *out = dW + (size_t)nb * 128 * KIN;
-    for (int i = tid; i < 128 * KIN; i += kWgThreads) {
+    const int rows_out = min(128, nout_valid - nb * 128);       // dW rows that exist (a 64-wide dY is padded to 128 columns)
+    for (int i = tid; i < rows_out * KIN; i += kWgThreads) {
         const int r = i / KIN, c = i % KIN;
         atomicAdd(out + i, stage_f[r * (KIN + 1) + c]);
     }
@@ -122,15 +123,16 @@ int wgrad_prepare() {
     return 0;
 }
 
-// dW[Nout, Kin] (fp32, dense) += dY[rows, Nout]^T X[rows, Kin];  Nout % 128 == 0, Kin in {128, 256}, ld % 8 == 0
+// dW[Nout, Kin] (fp32, dense) += dY[rows, Nout]^T X[rows, Kin];  Nout % 128 == 0, Kin in {128, 256}, ld % 8 == 0.
+// Only the first nout_valid rows of dW are written (dY columns beyond that are padding).
 int wgrad(const __nv_bfloat16 *dY, int64_t ld_dy, const __nv_bfloat16 *X, int64_t ld_x, int rows, int Nout, int Kin, float *dW,
-          int num_sms, cudaStream_t stream) {
+          int nout_valid, int num_sms, cudaStream_t stream) {
     if (rows <= 0 || Nout % 128 || (Kin != 128 && Kin != 256) || ld_dy % 8 || ld_x % 8) return -1;
     const int slab = Kin == 128 ? WgCfg<128>::kSlab : WgCfg<256>::kSlab;
     const int gy = Nout / 128, slabs = (rows + slab - 1) / slab;
     const int gx = max(1, min(slabs, num_sms / gy));
-    if (Kin == 128) wgrad_kernel<128><<<dim3(gx, gy), kWgThreads, WgCfg<128>::kTotal, stream>>>(dY, ld_dy, X, ld_x, rows, dW);
-    else wgrad_kernel<256><<<dim3(gx, gy), kWgThreads, WgCfg<256>::kTotal, stream>>>(dY, ld_dy, X, ld_x, rows, dW);
+    if (Kin == 128) wgrad_kernel<128><<<dim3(gx, gy), kWgThreads, WgCfg<128>::kTotal, stream>>>(dY, ld_dy, X, ld_x, rows, dW, nout_valid);
+    else wgrad_kernel<256><<<dim3(gx, gy), kWgThreads, WgCfg<256>::kTotal, stream>>>(dY, ld_dy, X, ld_x, rows, dW, nout_valid);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -143,5 +145,5 @@ extern "C" int uavpolicy_selftest_wgrad(const void *d_dy, int64_t ld_dy, const v
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -2;
     return uavp::wgrad(static_cast<const __nv_bfloat16 *>(d_dy), ld_dy, static_cast<const __nv_bfloat16 *>(d_x), ld_x, rows, n_out,
-                       k_in, d_dw, sms, (cudaStream_t)stream);
+                       k_in, d_dw, n_out, sms, (cudaStream_t)stream);
 }

@@ -41,6 +41,34 @@ class _TrunkFn(torch.autograd.Function):
         return None, None, grad
 
 
+class _PolicyFn(torch.autograd.Function):
+    """trunks + heads: (obs, flat parameters) -> (logits [n,2], value [n,1])"""
+
+    @staticmethod
+    def forward(ctx, owner, obs, flat):
+        n = obs.shape[0]
+        logits = torch.empty(n, 2, device=obs.device, dtype=torch.float32)
+        value = torch.empty(n, 1, device=obs.device, dtype=torch.float32)
+        owner._chk(owner._lib.uavtrain_forward_heads(owner._h, C.c_void_p(flat.data_ptr()), C.c_void_p(obs.data_ptr()), n,
+                                                     C.c_void_p(logits.data_ptr()), C.c_void_p(value.data_ptr()), owner._stream()))
+        ctx.owner = owner
+        ctx.keep = (obs, flat)
+        owner._pending = n
+        return logits, value
+
+    @staticmethod
+    def backward(ctx, dlogits, dvalue):
+        owner = ctx.owner
+        if owner._pending != dlogits.shape[0]:
+            raise RuntimeError("FusedTrunks keeps the activations of ONE forward: backward must follow its forward")
+        dlogits, dvalue = dlogits.contiguous().float(), dvalue.contiguous().float()
+        grad = torch.empty(NUM_PARAMS, device=dlogits.device, dtype=torch.float32)
+        owner._chk(owner._lib.uavtrain_backward_heads(owner._h, C.c_void_p(dlogits.data_ptr()), C.c_void_p(dvalue.data_ptr()),
+                                                      C.c_void_p(grad.data_ptr()), owner._stream()))
+        owner._pending = 0
+        return None, None, grad
+
+
 class FusedTrunks:
     def __init__(self, max_samples, device):
         self._h = None
@@ -72,11 +100,16 @@ class FusedTrunks:
             raise ValueError("expected the %d fp32 parameters of TransformerActorCritic" % NUM_PARAMS)
         return _TrunkFn.apply(self, obs.contiguous().float(), flat)
 
+    def logits_and_value(self, module, obs):
+        """== module.logits_and_value(obs): trunks and heads in the library, differentiable w.r.t. module.parameters()."""
+        flat = torch.cat([p.reshape(-1) for p in module.parameters()])
+        if flat.numel() != NUM_PARAMS or flat.dtype != torch.float32:
+            raise ValueError("expected the %d fp32 parameters of TransformerActorCritic" % NUM_PARAMS)
+        return _PolicyFn.apply(self, obs.contiguous().float(), flat)
+
     def evaluate(self, module, obs, action):
         """== module.evaluate(obs, action) (transformer_net.py:124-143): (log_prob [n], value [n,1], entropy [n])."""
-        feat = self.features(module, obs)
-        logits = module.actor_head(feat[:, 0])
-        value = module.critic_head(feat[:, 1])
+        logits, value = self.logits_and_value(module, obs)
         logp_all = torch.log_softmax(logits, dim=-1)
         entropy = -(logp_all.exp() * logp_all).sum(-1)
         return logp_all.gather(-1, action[:, None]).squeeze(-1), value, entropy

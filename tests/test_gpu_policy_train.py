@@ -76,6 +76,42 @@ def test_trunk_features_and_every_parameter_gradient_match_fp32_autograd(n):
         assert rel <= 8e-2 and _cos(got[k], p.grad) >= 0.997, (k, rel, _cos(got[k], p.grad))
 
 
+def test_logits_value_and_all_gradients_with_heads_inside():
+    """uavtrain_forward_heads / _backward_heads: logits / value within 3e-2 / 5e-2 of the fp32 network.  Through the heads'
+    ReLU a bf16 forward flips a few masks, which moves every upstream gradient: PyTorch's own bf16 autocast of the same
+    network is the yardstick.  Per parameter tensor: relative L2 error <= 0.15, cosine >= 0.99, and not more than
+    1.5x (+1e-2) the error autocast makes on the same inputs."""
+    from target_allocation_ppo_transformer_b200.networks.fused_train import FusedTrunks
+    net = _perturbed_net(2)
+    n = 3001
+    obs = torch.rand(n, 5, 14, device="cuda")
+    obs[: n // 4, :2] = 0
+    trunks = FusedTrunks(n, "cuda")
+    logits, value = trunks.logits_and_value(net, obs)
+    ref_l, ref_v = net.logits_and_value(obs)
+    assert logits.shape == (n, 2) and value.shape == (n, 1)
+    assert (logits - ref_l).abs().max() < 3e-2 and (value - ref_v).abs().max() < 5e-2
+    dl, dv = torch.randn_like(ref_l) / n, torch.randn_like(ref_v) / n
+
+    def grads(fn):
+        net.zero_grad()
+        l, v = fn()
+        torch.autograd.backward([l.float(), v.float()], [dl, dv])
+        return {k: p.grad.clone() for k, p in net.named_parameters()}
+
+    def autocast():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return net.logits_and_value(obs)
+
+    ref = grads(lambda: net.logits_and_value(obs))
+    got = grads(lambda: trunks.logits_and_value(net, obs))
+    lib = grads(autocast)
+    for k in ref:
+        rel = ((got[k] - ref[k]).norm() / ref[k].norm()).item()
+        rel_lib = ((lib[k] - ref[k]).norm() / ref[k].norm()).item()
+        assert rel <= 0.15 and _cos(got[k], ref[k]) >= 0.99 and rel <= 1.5 * rel_lib + 1e-2, (k, rel, rel_lib)
+
+
 def test_evaluate_contract_and_repeatability():
     from target_allocation_ppo_transformer_b200.networks.fused_train import FusedTrunks
     net = _perturbed_net(1)
