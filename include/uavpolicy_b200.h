@@ -88,9 +88,9 @@ int uavtrain_backward_heads(uavtrain_t *p, const float *d_dlogits, const float *
 
 /* self-test of the tcgen05 weight-gradient kernel (csrc/policy_wgrad.cu): d_dw[n_out,k_in] (f32) +=
  * dY[rows,n_out]^T X[rows,k_in]; bf16 row-major inputs with row strides ld_dy / ld_x (elements, multiples of 8);
- * n_out % 128 == 0, k_in = 128 or 256. */
+ * n_out % 128 == 0, k_in = 128 or 256.  d_dbias (optional, k_in = 128): d_dbias[n_out] += column sums of dY. */
 int uavpolicy_selftest_wgrad(const void *d_dy, int64_t ld_dy, const void *d_x, int64_t ld_x, int32_t rows, int32_t n_out,
-                             int32_t k_in, float *d_dw, void *stream);
+                             int32_t k_in, float *d_dw, float *d_dbias, void *stream);
 
 #ifdef __cplusplus
 }

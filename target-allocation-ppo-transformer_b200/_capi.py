@@ -159,7 +159,7 @@ def load_policy():
     L.uavpolicy_set_fused.argtypes = [vp, i32]
     L.uavpolicy_selftest_gemm_tile.argtypes = [vp, vp, vp, i32, i32, vp]
     i64 = C.c_int64
-    L.uavpolicy_selftest_wgrad.argtypes = [vp, i64, vp, i64, i32, i32, i32, vp, vp]
+    L.uavpolicy_selftest_wgrad.argtypes = [vp, i64, vp, i64, i32, i32, i32, vp, vp, vp]
     L.uavtrain_create.argtypes = [i32, i32, C.POINTER(vp)]
     L.uavtrain_destroy.argtypes = [vp]
     L.uavtrain_last_error.argtypes = [vp]

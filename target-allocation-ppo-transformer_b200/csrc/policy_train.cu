@@ -7,7 +7,8 @@
 //   activation-gradient GEMMs  dX = dY W        -> uavp::gemm_bias_act on pre-transposed bf16 weights (tcgen05)
 //   weight-gradient GEMMs      dW += dY^T X     -> uavp::wgrad (policy_wgrad.cu: split-K, accumulator resident in TMEM)
 //   everything else (LayerNorm / ReLU / attention / embedding backward, bias + LayerNorm parameter gradients) is
-//   hand-written below; bias gradients are accumulated by the kernel that produces the corresponding dY.
+//   hand-written below; bias gradients are accumulated by the kernel that produces the corresponding dY, or by the
+//   weight-gradient kernel (as dY^T 1 on the tensor cores) where dY comes out of the attention backward.
 // Two boundaries: uavtrain_forward / _backward stop at the trunks' last-token features ([n,2,128] out, their gradient
 // in); uavtrain_forward_heads / _backward_heads also run the two MLP heads (logits [n,2] + value [n] out, their
 // gradients in).  The PPO loss itself stays in PyTorch.
@@ -29,7 +30,7 @@
 namespace uavp {
 int wgrad_prepare();
 int wgrad(const __nv_bfloat16 *dY, int64_t ld_dy, const __nv_bfloat16 *X, int64_t ld_x, int rows, int Nout, int Kin, float *dW,
-          int nout_valid, int num_sms, cudaStream_t stream);
+          int nout_valid, float *dbias, int num_sms, cudaStream_t stream);
 }  // namespace uavp
 
 namespace {
@@ -186,28 +187,6 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(bf16 *__restrict__ dh, co
         }
     }
     block_colsum_flush<8, FF>(acc, s_red, g_bias, [](int l, int i) { return (i >> 2) * 128 + l * 4 + (i & 3); });
-}
-
-// g_bias[C] += column sums of a dense bf16 [rows, C] matrix, C = 128 * NB
-template <int NB>
-__global__ void __launch_bounds__(256) colsum_kernel(const bf16 *__restrict__ m, int rows, int rows_per_warp, float *__restrict__ g_bias) {
-    __shared__ float s_red[8 * 128 * NB];
-    const int lane = threadIdx.x & 31;
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int r0 = gw * rows_per_warp, r1 = min(rows, r0 + rows_per_warp);
-    float acc[4 * NB];
-#pragma unroll
-    for (int i = 0; i < 4 * NB; ++i) acc[i] = 0.0f;
-    for (int r = r0; r < r1; ++r) {
-#pragma unroll
-        for (int k = 0; k < NB; ++k) {
-            float g[4];
-            unpack4(*reinterpret_cast<const uint2 *>(m + (size_t)r * (128 * NB) + k * 128 + lane * 4), g);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[k * 4 + i] += g[i];
-        }
-    }
-    block_colsum_flush<4 * NB, 128 * NB>(acc, s_red, g_bias, [](int l, int i) { return (i >> 2) * 128 + l * 4 + (i & 3); });
 }
 
 // attention backward.  dS_ij = p_ij (dO_i.v_j - sum_l p_il dO_i.v_l) / 4;  dQ_i = sum_j dS_ij k_j;  dK_j = sum_i dS_ij q_i;
@@ -621,9 +600,9 @@ void gemm(TCtx &c, const bf16 *A, int64_t lda, const bf16 *W, const float *bias,
     if (r) c.rc = tfail(c.p, -2, "tcgen05 GEMM (M=%d N=%d K=%d) failed with %d", M, N, K, r);
 }
 void wgrad(TCtx &c, const bf16 *dY, int64_t ld_dy, const bf16 *X, int64_t ld_x, int rows, int Nout, int Kin, float *dW,
-           int nout_valid = -1) {
+           int nout_valid = -1, float *dbias = nullptr) {
     if (c.rc) return;
-    const int r = uavp::wgrad(dY, ld_dy, X, ld_x, rows, Nout, Kin, dW, nout_valid < 0 ? Nout : nout_valid, c.p->sms, c.s);
+    const int r = uavp::wgrad(dY, ld_dy, X, ld_x, rows, Nout, Kin, dW, nout_valid < 0 ? Nout : nout_valid, dbias, c.p->sms, c.s);
     if (r) c.rc = tfail(c.p, -2, "weight-gradient kernel (rows=%d Nout=%d Kin=%d) failed with %d", rows, Nout, Kin, r);
 }
 void add_ln(TCtx &c, const bf16 *x, int64_t xs, const bf16 *y, const float *g, const float *b, int rows, bf16 *out16, float *out32,
@@ -651,14 +630,6 @@ void relu_bwd(TCtx &c, bf16 *dh, const bf16 *h, int rows, float *g_bias) {
     int grid, rpw;
     row_grid(c.p, rows, grid, rpw);
     relu_bwd_kernel<<<grid, 256, 0, c.s>>>(dh, h, rows, rpw, g_bias);
-}
-void colsum(TCtx &c, const bf16 *m, int rows, int C, float *g_bias) {
-    if (c.rc) return;
-    int grid, rpw;
-    row_grid(c.p, rows, grid, rpw);
-    if (C == 128) colsum_kernel<1><<<grid, 256, 0, c.s>>>(m, rows, rpw, g_bias);
-    else if (C == 256) colsum_kernel<2><<<grid, 256, 0, c.s>>>(m, rows, rpw, g_bias);
-    else colsum_kernel<3><<<grid, 256, 0, c.s>>>(m, rows, rpw, g_bias);
 }
 
 // ---- forward -----------------------------------------------------------------------------------------------
@@ -713,10 +684,8 @@ void last_layer_bwd(TCtx &c, const uavp::LayerW &L, const LayerT &T, const Layer
         AttnBwdArgs a{A.Q, A.KV, A.KV + D, p->tmp, p->dQ, p->dQKV, p->dQKV + D, D, 2 * D, p->pad, n};
         attn_bwd_last_kernel<<<(n * H + 255) / 256, 256, 0, c.s>>>(a);
     }
-    colsum(c, p->dQ, n, D, g + o.in_b);
-    colsum(c, p->dQKV, R, 2 * D, g + o.in_b + D);
-    wgrad(c, p->dQ, D, X + (S - 1) * D, (int64_t)S * D, n, D, D, g + o.in_w);
-    wgrad(c, p->dQKV, 2 * D, X, D, R, 2 * D, D, g + o.in_w + D * D);
+    wgrad(c, p->dQ, D, X + (S - 1) * D, (int64_t)S * D, n, D, D, g + o.in_w, -1, g + o.in_b);          // + bias gradients
+    wgrad(c, p->dQKV, 2 * D, X, D, R, 2 * D, D, g + o.in_w + D * D, -1, g + o.in_b + D);
     gemm(c, p->dQKV, 2 * D, T.in_kv_t, nullptr, dX, R, D, 2 * D, 0);
     gemm(c, p->dQ, D, T.in_q_t, nullptr, p->tmp, n, D, D, 0);
     if (!c.rc) scatter_add_last_kernel<<<(n * (D / 4) + 255) / 256, 256, 0, c.s>>>(dX, p->tmp, p->dS1, n);
@@ -733,8 +702,7 @@ void full_layer_bwd(TCtx &c, const uavp::LayerW &L, const LayerT &T, const Layer
         AttnBwdArgs a{A.QKV, A.QKV + D, A.QKV + 2 * D, p->tmp, p->dQKV, p->dQKV + D, p->dQKV + 2 * D, 3 * D, 3 * D, p->pad, n};
         attn_bwd_full_kernel<<<(n * H + 8 * kPairsPerWarp - 1) / (8 * kPairsPerWarp), 256, 0, c.s>>>(a);
     }
-    colsum(c, p->dQKV, R, 3 * D, g + o.in_b);
-    wgrad(c, p->dQKV, 3 * D, X, D, R, 3 * D, D, g + o.in_w);
+    wgrad(c, p->dQKV, 3 * D, X, D, R, 3 * D, D, g + o.in_w, -1, g + o.in_b);                           // + bias gradient
     gemm(c, p->dQKV, 3 * D, T.in_t, nullptr, dXg, R, D, 3 * D, 0);
 }
 void embed_bwd(TCtx &c, const BlockOff &bo, const uavp::BlockW &b, float *g, int n, const bf16 *g1, const bf16 *g2) {

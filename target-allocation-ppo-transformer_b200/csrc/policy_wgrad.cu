@@ -24,26 +24,33 @@ struct WgCfg {
     static constexpr int kA = kSlab * 128 * 2;               // dY sub-tile [kSlab rows x 128 cols] bf16
     static constexpr int kB = kSlab * KIN * 2;               // X tile [kSlab rows x KIN] bf16
     static constexpr int kStage = kA + kB;
-    static constexpr int kTotal = kStages * kStage + 64;
+    static constexpr int kOnes = kSlab * 16 * 2;             // an all-ones [kSlab x 16] operand: dY^T 1 = the bias gradient
+    static constexpr int kTotal = kStages * kStage + kOnes + 64;
     static_assert(128 * (KIN + 1) * 4 <= kStages * kStage, "the epilogue transposes through the operand buffers");
 };
 
 template <int KIN>
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __nv_bfloat16 *__restrict__ dY, int64_t ld_dy,
                                                               const __nv_bfloat16 *__restrict__ X, int64_t ld_x, int rows,
-                                                              float *__restrict__ dW, int nout_valid) {
+                                                              float *__restrict__ dW, int nout_valid, float *__restrict__ dbias) {
     using SM = WgCfg<KIN>;
     constexpr int kSlab = SM::kSlab, kStages = SM::kStages;
     extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + kStages * SM::kStage);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kStages * SM::kStage + 48);
+    unsigned char *ones = smem + kStages * SM::kStage;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(ones + SM::kOnes);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ones + SM::kOnes + 48);
+    constexpr int kCols = KIN == 128 ? 256 : KIN;           // TMEM columns: KIN accumulators (+ 16 for the bias block)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int slabs = (rows + kSlab - 1) / kSlab;
     if ((int)blockIdx.x >= slabs) return;
     const int cnt = (slabs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // slabs of this CTA
     const int nb = blockIdx.y;
 
-    if (warp == 0) tc::tmem_alloc(tmem_slot, KIN);
+    if (warp == 0) tc::tmem_alloc(tmem_slot, kCols);
+    if (dbias) {                                             // (any operand layout of all ones is all ones)
+        for (int i = tid; i < SM::kOnes / 4; i += kWgThreads) reinterpret_cast<uint32_t *>(ones)[i] = 0x3F803F80u;
+        tc::fence_async_smem();
+    }
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) tc::mbar_init(&mbar[s], 1);
         tc::fence_mbar_init();
@@ -84,6 +91,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __nv_bfloat1
                 const uint64_t ad = tc::smem_desc(a + j * 2 * (128 * 16), 128 * 16, 128);
                 const uint64_t bd = tc::smem_desc(b + j * 2 * (KIN * 16), KIN * 16, 128);
                 tc::mma_bf16(tmem, ad, bd, idesc, (it > 0 || j > 0) ? 1u : 0u);
+                if (KIN == 128 && dbias)
+                    tc::mma_bf16(tmem + KIN, ad, tc::smem_desc(tc::smem_u32(ones), 16 * 16, 128), tc::instr_desc_bf16_mn(128, 16),
+                                 (it > 0 || j > 0) ? 1u : 0u);
             }
             tc::mma_commit(&mbar[it % kStages]);
         }
@@ -112,7 +122,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __nv_bfloat1
         const int r = i / KIN, c = i % KIN;
         atomicAdd(out + i, stage_f[r * (KIN + 1) + c]);
     }
-    if (warp == 0) { tc::tc_fence_after(); tc::tmem_free(tmem, KIN); }
+    if (KIN == 128 && dbias && warp < 4) {                   // column KIN of the accumulator block: sum over rows of dY
+        float v[32];
+        tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + KIN, v);
+        if (lrow < rows_out) atomicAdd(dbias + nb * 128 + lrow, v[0]);
+        tc::tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 0) { tc::tc_fence_after(); tc::tmem_free(tmem, kCols); }
 }
 
 }  // namespace
@@ -124,15 +141,16 @@ int wgrad_prepare() {
 }
 
 // dW[Nout, Kin] (fp32, dense) += dY[rows, Nout]^T X[rows, Kin];  Nout % 128 == 0, Kin in {128, 256}, ld % 8 == 0.
-// Only the first nout_valid rows of dW are written (dY columns beyond that are padding).
+// Only the first nout_valid rows of dW are written (dY columns beyond that are padding).  dbias (optional, Kin = 128
+// only): dbias[Nout] += column sums of dY, computed by the tensor cores as dY^T 1 alongside the main product.
 int wgrad(const __nv_bfloat16 *dY, int64_t ld_dy, const __nv_bfloat16 *X, int64_t ld_x, int rows, int Nout, int Kin, float *dW,
-          int nout_valid, int num_sms, cudaStream_t stream) {
-    if (rows <= 0 || Nout % 128 || (Kin != 128 && Kin != 256) || ld_dy % 8 || ld_x % 8) return -1;
+          int nout_valid, float *dbias, int num_sms, cudaStream_t stream) {
+    if (rows <= 0 || Nout % 128 || (Kin != 128 && Kin != 256) || ld_dy % 8 || ld_x % 8 || (dbias && Kin != 128)) return -1;
     const int slab = Kin == 128 ? WgCfg<128>::kSlab : WgCfg<256>::kSlab;
     const int gy = Nout / 128, slabs = (rows + slab - 1) / slab;
     const int gx = max(1, min(slabs, num_sms / gy));
-    if (Kin == 128) wgrad_kernel<128><<<dim3(gx, gy), kWgThreads, WgCfg<128>::kTotal, stream>>>(dY, ld_dy, X, ld_x, rows, dW, nout_valid);
-    else wgrad_kernel<256><<<dim3(gx, gy), kWgThreads, WgCfg<256>::kTotal, stream>>>(dY, ld_dy, X, ld_x, rows, dW, nout_valid);
+    if (Kin == 128) wgrad_kernel<128><<<dim3(gx, gy), kWgThreads, WgCfg<128>::kTotal, stream>>>(dY, ld_dy, X, ld_x, rows, dW, nout_valid, dbias);
+    else wgrad_kernel<256><<<dim3(gx, gy), kWgThreads, WgCfg<256>::kTotal, stream>>>(dY, ld_dy, X, ld_x, rows, dW, nout_valid, dbias);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -140,10 +158,10 @@ int wgrad(const __nv_bfloat16 *dY, int64_t ld_dy, const __nv_bfloat16 *X, int64_
 
 // self-test hook: one weight-gradient product on caller-provided device buffers
 extern "C" int uavpolicy_selftest_wgrad(const void *d_dy, int64_t ld_dy, const void *d_x, int64_t ld_x, int32_t rows, int32_t n_out,
-                                        int32_t k_in, float *d_dw, void *stream) {
+                                        int32_t k_in, float *d_dw, float *d_dbias, void *stream) {
     if (uavp::wgrad_prepare()) return -2;
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -2;
     return uavp::wgrad(static_cast<const __nv_bfloat16 *>(d_dy), ld_dy, static_cast<const __nv_bfloat16 *>(d_x), ld_x, rows, n_out,
-                       k_in, d_dw, n_out, sms, (cudaStream_t)stream);
+                       k_in, d_dw, n_out, d_dbias, sms, (cudaStream_t)stream);
 }

@@ -29,12 +29,16 @@ def test_tcgen05_weight_gradient_kernel(rows, n_out, k_in, ld_x):
     dy = (torch.randn(rows, n_out, device="cuda", generator=g) * 0.5).bfloat16()
     xfull = (torch.randn(rows, ld_x, device="cuda", generator=g) * 0.5).bfloat16()
     dw = torch.full((n_out, k_in), 0.25, device="cuda")                       # the kernel ACCUMULATES
+    db = torch.full((n_out,), -1.0, device="cuda") if k_in == 128 else None   # bias gradient = dY^T 1, same tensor-core pass
     rc = L.uavpolicy_selftest_wgrad(C.c_void_p(dy.data_ptr()), n_out, C.c_void_p(xfull.data_ptr()), ld_x, rows, n_out, k_in,
-                                    C.c_void_p(dw.data_ptr()), None)
+                                    C.c_void_p(dw.data_ptr()), C.c_void_p(db.data_ptr()) if db is not None else None, None)
     torch.cuda.synchronize()
     assert rc == 0
     ref = dy.double().t() @ xfull[:, :k_in].double() + 0.25
     assert (dw.double() - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+    if db is not None:
+        ref_b = dy.double().sum(0) - 1.0
+        assert (db.double() - ref_b).abs().max().item() <= 1e-5 * max(1.0, ref_b.abs().max().item())
 
 
 def _perturbed_net(seed=0):
