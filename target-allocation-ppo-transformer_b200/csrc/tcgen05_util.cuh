@@ -31,6 +31,11 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;
 }
 
+// the same for a 128-byte-swizzled tile (what a TMA tensor load with CU_TENSOR_MAP_SWIZZLE_128B writes): layout type 2
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return smem_desc(saddr, lbo_bytes, sbo_bytes) | ((uint64_t)2 << 61);
+}
+
 // UMMA instruction descriptor for kind::f16 (InstrDescriptor): D = f32, A = B = bf16, both K-major, M x N
 __host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -146,6 +151,16 @@ __device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, 
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
+}
+
+// 2-D TMA tensor load (UTMALDG) of one box at element coordinates (c0 = innermost, c1) of the tensor map; completion is
+// signalled on the mbarrier as a transaction count (post the expected bytes with mbar_expect_tx first).  ONE thread.
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const void *tensor_map, int c0, int c1, uint64_t *mbar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+                     smem_u32(smem_dst)), "l"(tensor_map), "r"(c0), "r"(c1), "r"(smem_u32(mbar)) : "memory");
 }
 
 // synchronous variant with zero fill of rows >= valid_rows (self-test / ragged activations)
