@@ -151,8 +151,10 @@ def cpu_baseline(w, seconds=12.0):
 def run_ppo(args):
     """BASELINE.json configs[3]: end-to-end PPO samples/s = transitions collected AND trained on (K_EPOCHS = 5) per
     second.  One "step" = one iteration: `horizon` rollout steps (tcgen05 policy forward + fused env step) followed
-    by the PPO update (GAE kernel, fp32 autograd on the PyTorch mirror, one flat NCCL gradient all-reduce per
-    minibatch at N > 1).  Timed with CUDA events around whole iterations; max over ranks."""
+    by the PPO update (GAE kernel; per minibatch the hand-written bf16 forward + backward of csrc/policy_train.cu,
+    the PPO loss in PyTorch, one flat NCCL gradient all-reduce at N > 1, clip, Adam - replayed as one CUDA graph).
+    Timed with CUDA events around whole iterations; max over ranks.  UAVENV_UPDATE_PRECISION=tf32|fp32|bf16 runs the
+    update through PyTorch autograd on the mirror network instead (A/B)."""
     import torch
     import uavenv_b200 as ub
     from target_allocation_ppo_transformer_b200 import parallel
@@ -207,7 +209,11 @@ def run_ppo(args):
                        "parallelism": "env-sharded x%d, flat fp32 gradient all-reduce (NCCL) per minibatch" % world},
             "e2e": {"value": samples / (ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 24,
                     "note": "the whole loop is device-resident; only the three mean losses leave the GPU per update"},
-            "gpu_launches": K * T * 27, "clocks": clocks}))
+            # own kernels per iteration: T x (fused policy blocks + heads + env step) + 2 GAE + per minibatch step 77
+            # (32 tcgen05 GEMMs, 16 weight-gradient, 29 LayerNorm / attention / ReLU / embedding / head kernels)
+            "gpu_launches": K * (T * 3 + 2 + (77 if agent.update_precision == "fused" else 4) * 5 * (B * T // agent.minibatch_size)),
+            "clocks": clocks}))
+    agent.close()       # drop the captured graph before the communicator it references goes away
     env.close()
     if world > 1:
         torch.distributed.destroy_process_group()

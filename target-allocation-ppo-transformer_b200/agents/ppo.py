@@ -145,6 +145,15 @@ class PPOAgent:
             self.fused = FusedPolicyForward(self.B, dev, seed=seed, env_id_base=env_id_base)
             self.fused.sync(self.policy_old)
 
+    def close(self):
+        """Release the captured update graph (it holds NCCL kernels: destroy it BEFORE destroy_process_group())."""
+        if self._graph is not None:
+            torch.cuda.synchronize(self.device)
+            self._graph = None
+            import gc
+            gc.collect()
+            torch.cuda.synchronize(self.device)
+
     # -- rollout ------------------------------------------------------------------------------------------
     @torch.no_grad()
     def select_action(self, obs):

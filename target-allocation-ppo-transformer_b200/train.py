@@ -23,7 +23,7 @@ CSV_COLUMNS = ["Episode", "Avg_Reward", "Avg_J_Val", "Max_Coverage", "Q0_Value",
 
 
 def train(num_envs=16384, horizon=32, iterations=10, cfg=None, log_dir=None, seed=None, minibatch_size=None,
-          save_every=0, verbose=True, fused_rollout=True):
+          save_every=0, verbose=True, fused_rollout=True, update_precision="fused", graph_update=True):
     """Returns a list of per-iteration stat dicts (rank 0 also writes training_stats.csv / checkpoints)."""
     cfg = cfg or global_cfg
     rank, local_rank, world = parallel.init()
@@ -32,7 +32,8 @@ def train(num_envs=16384, horizon=32, iterations=10, cfg=None, log_dir=None, see
     seed = cfg.SEED if seed is None else seed
     env = UAVEnvBatched(num_envs, device=device, seed=seed, env_id_base=rank * num_envs, config=cfg)
     agent = PPOAgent(num_envs, horizon, device, cfg=cfg, minibatch_size=minibatch_size, seed=seed,
-                     fused_rollout=fused_rollout, env_id_base=rank * num_envs)
+                     fused_rollout=fused_rollout, env_id_base=rank * num_envs, update_precision=update_precision,
+                     graph_update=graph_update)
     writer = fh = None
     if rank == 0 and log_dir:
         os.makedirs(log_dir, exist_ok=True)
@@ -89,6 +90,7 @@ def train(num_envs=16384, horizon=32, iterations=10, cfg=None, log_dir=None, see
     if rank == 0 and log_dir:
         torch.save(agent.policy.state_dict(), os.path.join(log_dir, "final_model.pth"))   # main_train.py:231-232
         fh.close()
+    agent.close()
     env.close()
     return history
 
