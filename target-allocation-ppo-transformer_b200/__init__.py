@@ -21,6 +21,12 @@ def __getattr__(name):  # torch / CUDA are only touched when the env classes are
     if name == "FusedPolicyForward":
         from .networks.fused_forward import FusedPolicyForward
         return FusedPolicyForward
+    if name == "FusedTrunks":
+        from .networks.fused_train import FusedTrunks
+        return FusedTrunks
+    if name == "train":
+        from .train import train
+        return train
     if name == "load_library":
         from ._capi import load
         return load
