@@ -174,13 +174,19 @@ def run_ppo(args):
                         graph_update=os.environ.get("UAVENV_GRAPH_UPDATE", "1") != "0")
     obs = env.reset()
 
+    split = [torch.cuda.Event(enable_timing=True) for _ in range(3)]   # rollout | update boundaries of the last iteration
+
     def iteration():
         nonlocal obs
+        split[0].record()
         while not agent.full():
             a = agent.select_action(obs)
             obs, reward, done, _ = env.step(a)
             agent.store_transition(reward, done)
-        return agent.update(obs)
+        split[1].record()
+        out = agent.update(obs)
+        split[2].record()
+        return out
 
     for _ in range(W):
         iteration()
@@ -206,6 +212,7 @@ def run_ppo(args):
                 ", CUDA-graph replay" if agent.graph_update else ""), "data": "synthetic",
             "config": {"workload": PPO["name"], "envs_per_gpu": B, "horizon": T, "k_epochs": 5,
                        "minibatch": agent.minibatch_size, "last_stats": stats,
+                       "last_iteration_ms": {"rollout": split[0].elapsed_time(split[1]), "update": split[1].elapsed_time(split[2])},
                        "parallelism": "env-sharded x%d, flat fp32 gradient all-reduce (NCCL) per minibatch" % world},
             "e2e": {"value": samples / (ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 24,
                     "note": "the whole loop is device-resident; only the three mean losses leave the GPU per update"},

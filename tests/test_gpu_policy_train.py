@@ -182,8 +182,39 @@ def test_fused_update_trains_like_the_tf32_update():
             ag.store_transition(reward, done)
     for name in ("buf_action", "buf_logp", "buf_value"):
         getattr(agents[0], name).copy_(getattr(agents[1], name))
+    agents[0]._gen.set_state(agents[1]._gen.get_state())         # same minibatch permutations
     stats = [ag.update(obs) for ag in agents]
     for k in ("loss_actor", "loss_critic", "entropy"):
         assert np.isfinite(stats[0][k]) and abs(stats[0][k] - stats[1][k]) <= 2e-2 * max(1.0, abs(stats[1][k])), (k, stats)
     d = [torch.cat([p.detach().flatten() for p in ag.policy.parameters()]) - w0 for ag in agents]
     assert _cos(d[0], d[1]) > 0.8            # Adam's first steps are sign-like: small gradients may flip, the bulk agrees
+
+
+def test_graph_replayed_update_matches_the_eager_update():
+    """graph_update=True: three eager minibatch steps, then the whole step (gather, forward, loss, backward, clip, Adam) is
+    captured once and replayed (77 of the 80 steps here).  Same weights, rollout and permutations => the same losses
+    (5e-3: Adam runs with device-side step counters in the captured variant, and fp32 atomics reorder the gradient sums)
+    and the same parameter movement (cosine of the deltas)."""
+    import uavenv_b200 as ub
+    B, T = 256, 16
+    agents = [ub.PPOAgent(B, T, "cuda", minibatch_size=256, seed=5, update_precision="fused", graph_update=g) for g in (True, False)]
+    env = ub.UAVEnvBatched(B, seed=2)
+    obs = env.reset()
+    w0 = torch.cat([p.detach().flatten() for p in agents[0].policy.parameters()]).clone()
+    while not agents[1].full():
+        a = agents[1].select_action(obs)
+        agents[0].buf_obs[agents[0].t].copy_(obs)
+        obs, reward, done, _ = env.step(a)
+        for ag in agents:
+            ag.store_transition(reward, done)
+    for name in ("buf_action", "buf_logp", "buf_value"):
+        getattr(agents[0], name).copy_(getattr(agents[1], name))
+    agents[0]._gen.set_state(agents[1]._gen.get_state())         # (sampling the actions advanced agent 1's generator)
+    stats = [ag.update(obs) for ag in agents]
+    for k in stats[0]:
+        assert abs(stats[0][k] - stats[1][k]) <= 5e-3 * max(1.0, abs(stats[1][k])), (k, stats)
+    assert agents[0]._graph is not None and agents[1]._graph is None
+    d = [torch.cat([p.detach().flatten() for p in ag.policy.parameters()]) - w0 for ag in agents]
+    assert _cos(d[0], d[1]) > 0.95
+    agents[0].close()
+    assert agents[0]._graph is None
