@@ -88,9 +88,9 @@ struct uavpolicy {
     int device = 0, max_batch = 0;
     float *w32 = nullptr;                 // private fp32 copy of the flat parameters
     __nv_bfloat16 *w16 = nullptr;         // bf16 copies (GEMM weights are read from here): one per block, each placed so
-    __nv_bfloat16 *w16_critic = nullptr;
+    __nv_bfloat16 *w16_critic = nullptr;  // that the block's first parameter is 16 B aligned (TMA needs aligned operands)
     __nv_bfloat16 *emb2_a = nullptr, *emb2_c = nullptr;   // [128 x 32] tensor-core form of the two embedding weights
-    __nv_bfloat16 *wpk = nullptr;         // GEMM weights pre-packed in canonical order (same element offsets as w32)  // that the block's first parameter is 16 B aligned (TMA needs aligned operands)
+    __nv_bfloat16 *wpk = nullptr;         // GEMM weights pre-packed in canonical order (same element offsets as w32)
     BlockW actor, critic;
     HeadW actor_head, critic_head;
     // bf16 activation workspaces (R = 5 * max_batch rows)
