@@ -176,6 +176,10 @@ class PPOAgent:
     def full(self):
         return self.t >= self.T
 
+    def clear_buffer(self):
+        """ppo.py:183: drop the collected transitions (update() does this itself)."""
+        self.t = 0
+
     # -- update -------------------------------------------------------------------------------------------
     def update(self, last_obs):
         """ppo.py:68-181.  Returns the mean losses like the reference ({"loss_actor","loss_critic","entropy"})."""
