@@ -86,6 +86,15 @@ int uavtrain_forward_heads(uavtrain_t *p, const float *d_flat_params, const floa
                            float *d_value, void *stream);
 int uavtrain_backward_heads(uavtrain_t *p, const float *d_dlogits, const float *d_dvalue, float *d_flat_grad, void *stream);
 
+/* PPO loss of agents/ppo.py:126-153 on the heads' outputs, value and gradient in one call:
+ *   L = -mean(min(r A, clip(r, 1-eps, 1+eps) A)) + c_value * max(mean((v-R)^2), mean((v_clip-R)^2)) - c_entropy * mean(H)
+ * with r = exp(log pi(a|s) - old_logp), v_clip = old_value + clip(v - old_value, -eps, eps).  All arrays [n] f32 on the
+ * device except d_logits / d_dlogits [n,2] and d_action [n] int64.  Out: d_dlogits, d_dvalue = dL/dlogits, dL/dvalue
+ * (ready for uavtrain_backward_heads); d_stats (optional) [3] = {actor loss, critic loss, mean entropy} (ppo.py:162-168). */
+int uavtrain_ppo_loss(uavtrain_t *p, const float *d_logits, const float *d_value, const int64_t *d_action, const float *d_old_logp,
+                      const float *d_adv, const float *d_ret, const float *d_old_value, int32_t n, float eps_clip, float c_value,
+                      float c_entropy, float *d_dlogits, float *d_dvalue, float *d_stats, void *stream);
+
 /* self-test of the tcgen05 weight-gradient kernel (csrc/policy_wgrad.cu): d_dw[n_out,k_in] (f32) +=
  * dY[rows,n_out]^T X[rows,k_in]; bf16 row-major inputs with row strides ld_dy / ld_x (elements, multiples of 8);
  * n_out % 128 == 0, k_in = 128 or 256.  d_dbias (optional, k_in = 128): d_dbias[n_out] += column sums of dY. */

@@ -168,10 +168,11 @@ def load_policy():
     L.uavtrain_backward.argtypes = [vp, vp, vp, vp]
     L.uavtrain_forward_heads.argtypes = [vp, vp, vp, i32, vp, vp, vp]
     L.uavtrain_backward_heads.argtypes = [vp, vp, vp, vp, vp]
+    L.uavtrain_ppo_loss.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp]
     for name in ("uavpolicy_create", "uavpolicy_destroy", "uavpolicy_set_weights", "uavpolicy_get_action",
                  "uavpolicy_set_fused", "uavpolicy_selftest_gemm_tile", "uavpolicy_selftest_wgrad", "uavtrain_create",
                  "uavtrain_destroy", "uavtrain_forward", "uavtrain_backward", "uavtrain_forward_heads",
-                 "uavtrain_backward_heads"):
+                 "uavtrain_backward_heads", "uavtrain_ppo_loss"):
         getattr(L, name).restype = C.c_int
     _policy_lib = L
     return L

@@ -123,6 +123,7 @@ class PPOAgent:
         self._ret = torch.zeros(T * B, device=dev)
         self._adv = torch.zeros(T * B, device=dev)
         self._mb_sums = torch.zeros(3, device=dev)
+        self._mb_stats = torch.zeros(3, device=dev)
         self._graph, self._graph_warm = None, 0
         self._side = torch.cuda.Stream(device=dev) if self.graph_update else None
         self._gen = torch.Generator(device=dev).manual_seed(seed + 1 + (
@@ -201,8 +202,14 @@ class PPOAgent:
         idx = self._mb_idx
         obs = self.buf_obs.view(n, c.SEQ_LEN, c.STATE_DIM)
         act, old_logp, old_val = self.buf_action.view(n), self.buf_logp.view(n), self.buf_value.view(n)
-        if self.trunks is not None:
-            logp, value, entropy = self.trunks.evaluate(self.policy, obs[idx], act[idx])
+        if self.trunks is not None:                                         # forward, loss and backward in the library
+            with torch.no_grad():
+                flat = torch.cat([p.reshape(-1) for p in self.policy.parameters()])
+            self.trunks.ppo_step(flat, obs[idx], act[idx], old_logp[idx], self._adv[idx], self._ret[idx], old_val[idx],
+                                 c.EPS_CLIP, 0.5, 0.01, self._flat_grad, self._mb_stats)
+            self._apply_gradient()
+            self._mb_sums += self._mb_stats
+            return
         else:
             with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.update_precision == "bf16"):
                 logp, value, entropy = self.policy.evaluate(obs[idx], act[idx])
@@ -217,13 +224,18 @@ class PPOAgent:
         loss = loss_actor + 0.5 * loss_critic - 0.01 * ent                  # :153
         self._flat_grad.zero_()
         loss.backward()
-        if self.world > 1:                                                  # the only collective of training
+        self._apply_gradient()
+        self._mb_sums += torch.stack([loss_actor.detach(), loss_critic.detach(), ent.detach()])
+
+    def _apply_gradient(self):
+        """all-reduce (the only collective of training), global-norm clip (ppo.py:160) on the flat view, Adam"""
+        c = self.cfg
+        if self.world > 1:
             torch.distributed.all_reduce(self._flat_grad, group=self.group)
             self._flat_grad.div_(self.world)
-        norm = self._flat_grad.norm()                                       # clip_grad_norm_ (:160) on the flat view
+        norm = self._flat_grad.norm()
         self._flat_grad.mul_(torch.clamp(c.GRAD_NORM_CLIP / (norm + 1e-6), max=1.0))
         self.optimizer.step()
-        self._mb_sums += torch.stack([loss_actor.detach(), loss_critic.detach(), ent.detach()])
 
     def _run_minibatch(self):
         """Eager for the first steps (they double as the warm-up torch wants before a capture), then ONE graph launch."""

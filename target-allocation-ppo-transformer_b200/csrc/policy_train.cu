@@ -484,6 +484,78 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const bf16 *__restrict__ 
     if (threadIdx.x == 0) { atomicAdd(g_b2a, s_b2[0]); atomicAdd(g_b2a + 1, s_b2[1]); atomicAdd(g_b2c, s_b2[2]); }
 }
 
+// PPO loss (agents/ppo.py:126-153) on the heads' outputs, forward and backward in two passes over the minibatch:
+//   L = -mean(min(r A, clip(r, 1-eps, 1+eps) A)) + c_v max(mean((v - R)^2), mean((v_clip - R)^2)) - c_e mean(entropy)
+// pass 1 accumulates the four sums; pass 2 (which needs the means to pick the value-loss branch torch.max picks)
+// writes dL/dlogits and dL/dvalue.  acc: [0] sum -surrogate, [1] sum (v-R)^2, [2] sum (v_clip-R)^2, [3] sum entropy.
+struct PpoLossArgs {
+    const float *logits, *value, *old_logp, *adv, *ret, *old_value;
+    const int64_t *action;
+    int n;
+    float eps, c_value, c_entropy;
+};
+__device__ __forceinline__ void ppo_sample(const PpoLossArgs &a, int b, float &lp0, float &lp1, float &ratio, float &adv, float &surr1,
+                                           float &surr2, float &ent, float &v, float &vclip, float &ret) {
+    const float l0 = a.logits[2 * b], l1 = a.logits[2 * b + 1];
+    const float m = fmaxf(l0, l1), lse = m + logf(expf(l0 - m) + expf(l1 - m));
+    lp0 = l0 - lse; lp1 = l1 - lse;
+    const float p0 = expf(lp0), p1 = expf(lp1);
+    ent = -(p0 * lp0 + p1 * lp1);
+    const float logp = a.action[b] == 1 ? lp1 : lp0;
+    ratio = expf(logp - a.old_logp[b]);
+    adv = a.adv[b];
+    surr1 = ratio * adv;
+    surr2 = fminf(fmaxf(ratio, 1.0f - a.eps), 1.0f + a.eps) * adv;
+    v = a.value[b]; ret = a.ret[b];
+    const float ov = a.old_value[b];
+    vclip = ov + fminf(fmaxf(v - ov, -a.eps), a.eps);
+}
+__global__ void __launch_bounds__(256) ppo_loss_sums_kernel(const PpoLossArgs a, float *__restrict__ acc) {
+    __shared__ float s_red[4][8];
+    float s[4] = {0, 0, 0, 0};
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < a.n; b += gridDim.x * blockDim.x) {
+        float lp0, lp1, ratio, adv, s1, s2, ent, v, vc, r;
+        ppo_sample(a, b, lp0, lp1, ratio, adv, s1, s2, ent, v, vc, r);
+        s[0] -= fminf(s1, s2); s[1] += (v - r) * (v - r); s[2] += (vc - r) * (vc - r); s[3] += ent;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        s[k] = warp_sum(s[k]);
+        if ((threadIdx.x & 31) == 0) s_red[k][threadIdx.x >> 5] = s[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        float t = 0.0f;
+        for (int w = 0; w < 8; ++w) t += s_red[threadIdx.x][w];
+        atomicAdd(acc + threadIdx.x, t);
+    }
+}
+__global__ void __launch_bounds__(256) ppo_loss_grad_kernel(const PpoLossArgs a, const float *__restrict__ acc, float *__restrict__ dlogits,
+                                                            float *__restrict__ dvalue, float *__restrict__ stats) {
+    const float inv_n = 1.0f / (float)a.n;
+    const bool clipped_branch = acc[2] > acc[1];          // torch.max(mean1, mean2): the larger mean carries the gradient
+    if (blockIdx.x == 0 && threadIdx.x == 0 && stats) {   // the three numbers the reference logs (ppo.py:162-168)
+        stats[0] = acc[0] * inv_n; stats[1] = fmaxf(acc[1], acc[2]) * inv_n; stats[2] = acc[3] * inv_n;
+    }
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.n) return;
+    float lp0, lp1, ratio, adv, s1, s2, ent, v, vc, r;
+    ppo_sample(a, b, lp0, lp1, ratio, adv, s1, s2, ent, v, vc, r);
+    // d(-min(s1, s2))/d ratio: A where the unclipped term is the minimum or the clamp is inactive, else 0
+    const bool inside = ratio >= 1.0f - a.eps && ratio <= 1.0f + a.eps;
+    const float dlogp = (s1 < s2 || inside) ? -adv * ratio * inv_n : 0.0f;
+    const float p0 = expf(lp0), p1 = expf(lp1);
+    const bool a1 = a.action[b] == 1;
+    const float ce = a.c_entropy * inv_n;                 // -c_e mean(H):  dH/dz_k = -p_k (log p_k + H)
+    dlogits[2 * b] = dlogp * ((a1 ? 0.0f : 1.0f) - p0) + ce * p0 * (lp0 + ent);
+    dlogits[2 * b + 1] = dlogp * ((a1 ? 1.0f : 0.0f) - p1) + ce * p1 * (lp1 + ent);
+    const float ov = a.old_value[b];
+    float dv;
+    if (!clipped_branch) dv = 2.0f * (v - r);
+    else dv = (v - ov >= -a.eps && v - ov <= a.eps) ? 2.0f * (vc - r) : 0.0f;
+    dvalue[b] = a.c_value * dv * inv_n;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------- host side
@@ -515,7 +587,7 @@ struct uavtrain {
     FullAct fc;
     bf16 *T, *T2;                                // forward scratch (GEMM outputs feeding add+LN)
     bf16 *dS1, *dS2, *dH, *dQKV, *dXa, *dXb, *dQ, *tmp;   // backward scratch
-    float *zeros = nullptr;
+    float *zeros = nullptr, *loss_acc = nullptr;
     uint8_t *pad = nullptr;
     const float *obs = nullptr;                  // of the last forward (the embedding backward re-reads it)
     const float *params = nullptr;               // likewise (second head layers)
@@ -756,6 +828,7 @@ extern "C" int uavtrain_create(int32_t device, int32_t max_samples, uavtrain_t *
     if (e == cudaSuccess) e = talloc(p, &p->fc.rstd1, R);
     if (e == cudaSuccess) e = talloc(p, &p->fc.rstd2, R);
     if (e == cudaSuccess) e = talloc(p, &p->pad, R);
+    if (e == cudaSuccess) e = talloc(p, &p->loss_acc, (size_t)4);
     if (e == cudaSuccess) e = talloc(p, &p->zeros, (size_t)3 * D);
     if (e == cudaSuccess) e = cudaMemset(p->zeros, 0, 3 * D * sizeof(float));
     if (e == cudaSuccess) { void *ws = nullptr; e = cudaMalloc(&ws, uavp::gemm_workspace_bytes()); if (e == cudaSuccess) { p->allocs.push_back(ws); p->gemm_ws = ws; } }
@@ -881,4 +954,20 @@ extern "C" int uavtrain_backward_heads(uavtrain_t *p, const float *d_dlogits, co
     if (!d_dlogits || !d_dvalue || !d_flat_grad) return tfail(p, -1, "uavtrain_backward_heads: NULL argument");
     if (p->n <= 0 || !p->with_heads) return tfail(p, -4, "uavtrain_backward_heads without a preceding uavtrain_forward_heads");
     return backward_impl(p, nullptr, d_dlogits, d_dvalue, d_flat_grad, stream);
+}
+
+extern "C" int uavtrain_ppo_loss(uavtrain_t *p, const float *d_logits, const float *d_value, const int64_t *d_action, const float *d_old_logp,
+                                 const float *d_adv, const float *d_ret, const float *d_old_value, int32_t n, float eps_clip, float c_value,
+                                 float c_entropy, float *d_dlogits, float *d_dvalue, float *d_stats, void *stream) {
+    if (!p) return -1;
+    if (!d_logits || !d_value || !d_action || !d_old_logp || !d_adv || !d_ret || !d_old_value || !d_dlogits || !d_dvalue || n <= 0)
+        return tfail(p, -1, "uavtrain_ppo_loss: NULL argument or n <= 0");
+    T_TRY(p, cudaSetDevice(p->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    PpoLossArgs a{d_logits, d_value, d_old_logp, d_adv, d_ret, d_old_value, d_action, n, eps_clip, c_value, c_entropy};
+    T_TRY(p, cudaMemsetAsync(p->loss_acc, 0, 4 * sizeof(float), s));
+    ppo_loss_sums_kernel<<<min((n + 255) / 256, p->sms * 4), 256, 0, s>>>(a, p->loss_acc);
+    ppo_loss_grad_kernel<<<(n + 255) / 256, 256, 0, s>>>(a, p->loss_acc, d_dlogits, d_dvalue, d_stats);
+    T_TRY(p, cudaGetLastError());
+    return 0;
 }

@@ -85,6 +85,7 @@ class FusedTrunks:
         self._h = h
         self.max_samples = int(max_samples)
         self._pending = 0
+        self._work = None
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -113,6 +114,28 @@ class FusedTrunks:
         logp_all = torch.log_softmax(logits, dim=-1)
         entropy = -(logp_all.exp() * logp_all).sum(-1)
         return logp_all.gather(-1, action[:, None]).squeeze(-1), value, entropy
+
+    @torch.no_grad()
+    def ppo_step(self, flat_params, obs, action, old_logp, adv, ret, old_value, eps_clip, c_value, c_entropy, grad_out, stats_out=None):
+        """One PPO minibatch gradient without autograd: forward (trunks + heads) -> PPO loss value and gradient
+        (agents/ppo.py:126-153) -> backward, all in the library.  grad_out [NUM_PARAMS] fp32 is OVERWRITTEN with dL/dparams;
+        stats_out (optional, [3]) receives {actor loss, critic loss, mean entropy}.  Inputs are [n]-shaped device tensors."""
+        n = obs.shape[0]
+        if self._work is None or self._work.shape[0] < n:
+            self._work = torch.empty(self.max_samples, 6, device=self.device, dtype=torch.float32)
+        w = self._work
+        p = lambda t: C.c_void_p(t.data_ptr())
+        obs, action = obs.contiguous().float(), action.contiguous()
+        old_logp, adv, ret, old_value = (t.contiguous().float() for t in (old_logp, adv, ret, old_value))
+        base, n6 = w.data_ptr(), self.max_samples * 4      # [logits 2n | value n | dlogits 2n | dvalue n] carved from one buffer
+        logits, value, dlogits, dvalue = base, base + 2 * n6, base + 3 * n6, base + 5 * n6
+        s = self._stream()
+        self._chk(self._lib.uavtrain_forward_heads(self._h, p(flat_params), p(obs), n, C.c_void_p(logits), C.c_void_p(value), s))
+        self._chk(self._lib.uavtrain_ppo_loss(self._h, C.c_void_p(logits), C.c_void_p(value), p(action), p(old_logp), p(adv), p(ret),
+                                              p(old_value), n, float(eps_clip), float(c_value), float(c_entropy),
+                                              C.c_void_p(dlogits), C.c_void_p(dvalue), p(stats_out) if stats_out is not None else None, s))
+        self._chk(self._lib.uavtrain_backward_heads(self._h, C.c_void_p(dlogits), C.c_void_p(dvalue), p(grad_out), s))
+        self._pending = 0
 
     def close(self):
         if getattr(self, "_h", None):

@@ -218,3 +218,41 @@ def test_graph_replayed_update_matches_the_eager_update():
     assert _cos(d[0], d[1]) > 0.95
     agents[0].close()
     assert agents[0]._graph is None
+
+
+@pytest.mark.parametrize("n", [1, 257, 5000])
+def test_ppo_loss_kernel_value_and_gradient_match_autograd(n):
+    """uavtrain_ppo_loss against the PyTorch expression of agents/ppo.py:126-153 (both value-loss branches are hit by
+    scaling old_value): the three statistics to 1e-5, dL/dlogits and dL/dvalue to 1e-6 absolute at a scale of 1/n."""
+    import uavenv_b200 as ub
+    from target_allocation_ppo_transformer_b200 import _capi
+    from target_allocation_ppo_transformer_b200.networks.fused_train import FusedTrunks
+    L = _capi.load_policy()
+    tr = FusedTrunks(8, "cuda")
+    g = torch.Generator(device="cuda").manual_seed(n)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    for spread in (0.05, 1.0):
+        logits = torch.randn(n, 2, device="cuda", generator=g).requires_grad_()
+        value = torch.randn(n, device="cuda", generator=g).requires_grad_()
+        act = torch.randint(0, 2, (n,), device="cuda", generator=g)
+        old_logp = torch.log_softmax(logits.detach() + 0.3 * torch.randn(n, 2, device="cuda", generator=g), -1).gather(-1, act[:, None]).squeeze(-1)
+        adv = torch.randn(n, device="cuda", generator=g)
+        ret = torch.randn(n, device="cuda", generator=g)
+        old_v = value.detach() + spread * torch.randn(n, device="cuda", generator=g)
+        eps = 0.2
+        logp_all = torch.log_softmax(logits, -1)
+        logp = logp_all.gather(-1, act[:, None]).squeeze(-1)
+        ratio = torch.exp(logp - old_logp)
+        la = -torch.min(ratio * adv, torch.clamp(ratio, 1 - eps, 1 + eps) * adv).mean()
+        vclip = old_v + torch.clamp(value - old_v, -eps, eps)
+        lc = torch.max(((value - ret) ** 2).mean(), ((vclip - ret) ** 2).mean())
+        ent = (-(logp_all.exp() * logp_all).sum(-1)).mean()
+        (la + 0.5 * lc - 0.01 * ent).backward()
+        dl, dv, st = torch.empty(n, 2, device="cuda"), torch.empty(n, device="cuda"), torch.empty(3, device="cuda")
+        rc = L.uavtrain_ppo_loss(tr._h, p(logits.detach()), p(value.detach()), p(act), p(old_logp), p(adv), p(ret), p(old_v), n, eps, 0.5, 0.01,
+                                 p(dl), p(dv), p(st), None)
+        torch.cuda.synchronize()
+        assert rc == 0
+        ref = torch.stack([la, lc, ent]).detach()
+        assert torch.allclose(st, ref, rtol=1e-5, atol=1e-6), (st, ref)
+        assert (dl - logits.grad).abs().max().item() <= 1e-6 + 1e-5 / n and (dv - value.grad).abs().max().item() <= 1e-6 + 1e-5 / n
