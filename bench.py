@@ -216,9 +216,9 @@ def run_ppo(args):
                        "parallelism": "env-sharded x%d, flat fp32 gradient all-reduce (NCCL) per minibatch" % world},
             "e2e": {"value": samples / (ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 24,
                     "note": "the whole loop is device-resident; only the three mean losses leave the GPU per update"},
-            # own kernels per iteration: T x (fused policy blocks + heads + env step) + 2 GAE + per minibatch step 77
-            # (32 tcgen05 GEMMs, 16 weight-gradient, 29 LayerNorm / attention / ReLU / embedding / head kernels)
-            "gpu_launches": K * (T * 3 + 2 + (77 if agent.update_precision == "fused" else 4) * 5 * (B * T // agent.minibatch_size)),
+            # own kernels per iteration: T x (fused policy blocks + heads + env step) + 2 GAE + per minibatch step 79
+            # (32 tcgen05 GEMMs, 16 weight-gradient, 29 LayerNorm / attention / ReLU / embedding / head kernels, 2 loss)
+            "gpu_launches": K * (T * 3 + 2 + (79 if agent.update_precision == "fused" else 4) * 5 * (B * T // agent.minibatch_size)),
             "clocks": clocks}))
     agent.close()       # drop the captured graph before the communicator it references goes away
     env.close()
