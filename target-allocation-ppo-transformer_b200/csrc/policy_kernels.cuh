@@ -40,7 +40,11 @@ __global__ void f32_to_bf16_kernel(const float *__restrict__ src, __nv_bfloat16 
 constexpr int kEmbTok = 64;
 __global__ void __launch_bounds__(D) embed_kernel(const float *__restrict__ obs, int R, BlockW a, BlockW c,
                                                   __nv_bfloat16 *__restrict__ Ea, __nv_bfloat16 *__restrict__ Ec,
-                                                  uint8_t *__restrict__ pad) {
+                                                  uint8_t *__restrict__ pad, __nv_bfloat16 *__restrict__ obs16 = nullptr,
+                                                  uint32_t *__restrict__ relu_mask = nullptr) {
+    // obs16 / relu_mask (training only): a bf16 copy of the observation rows zero-padded to 64 columns (the B operand of
+    // the embedding's weight-gradient product) and the ReLU activity bits of both networks, [R][net][4 words]:
+    // word 2h + parity, bit l  <->  feature 64 h + 2 l + parity
     __shared__ float s_obs[kEmbTok][F];
     const int t0 = blockIdx.x * kEmbTok;
     for (int i = threadIdx.x; i < kEmbTok * F; i += D) {
@@ -52,6 +56,14 @@ __global__ void __launch_bounds__(D) embed_kernel(const float *__restrict__ obs,
         float sum = 0.0f;
         for (int j = 0; j < F; ++j) sum += fabsf(s_obs[threadIdx.x][j]);
         pad[t0 + threadIdx.x] = (sum == 0.0f && (t0 + threadIdx.x) % S != S - 1) ? 1 : 0;
+    }
+    if (obs16) {
+        for (int i = threadIdx.x; i < kEmbTok * 32; i += D) {
+            const int tok = i >> 5, c2 = (i & 31) * 2;
+            if (t0 + tok < R)
+                *reinterpret_cast<__nv_bfloat162 *>(obs16 + (size_t)(t0 + tok) * 64 + c2) =
+                    __floats2bfloat162_rn(c2 < F ? s_obs[tok][c2] : 0.0f, c2 + 1 < F ? s_obs[tok][c2 + 1] : 0.0f);
+        }
     }
     const bool critic = threadIdx.x >= D / 2;
     const int d = (threadIdx.x % (D / 2)) * 2;                    // features d, d+1
@@ -70,6 +82,13 @@ __global__ void __launch_bounds__(D) embed_kernel(const float *__restrict__ obs,
         float x0 = b0, x1 = b1;
 #pragma unroll
         for (int j = 0; j < F; ++j) { x0 = fmaf(w0[j], s_obs[i][j], x0); x1 = fmaf(w1[j], s_obs[i][j], x1); }
+        if (relu_mask) {
+            const unsigned m0 = __ballot_sync(0xffffffffu, x0 > 0.0f), m1 = __ballot_sync(0xffffffffu, x1 > 0.0f);
+            if ((threadIdx.x & 31) == 0) {
+                uint32_t *dst = relu_mask + ((size_t)t * 2 + (critic ? 1 : 0)) * 4 + ((threadIdx.x >> 5) & 1) * 2;
+                dst[0] = m0; dst[1] = m1;
+            }
+        }
         const int p = t % S;
         float q0 = p0[0], q1 = p1[0];
 #pragma unroll

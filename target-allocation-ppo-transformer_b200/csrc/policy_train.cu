@@ -30,7 +30,7 @@
 namespace uavp {
 int wgrad_prepare();
 int wgrad(const __nv_bfloat16 *dY, int64_t ld_dy, const __nv_bfloat16 *X, int64_t ld_x, int rows, int Nout, int Kin, float *dW,
-          int nout_valid, float *dbias, int num_sms, cudaStream_t stream);
+          int nout_valid, float *dbias, int num_sms, cudaStream_t stream, int out_ld, int kin_valid);
 }  // namespace uavp
 
 namespace {
@@ -319,92 +319,53 @@ __global__ void scatter_add_last_kernel(bf16 *__restrict__ dX, const bf16 *__res
     *reinterpret_cast<uint2 *>(dst) = pack4(x);
 }
 
-// embedding backward: E = relu(obs W^T + b) + pos.  A warp walks a run of windows with lane = 4 features, keeping
-// dW[c][0..13], db[c] and dpos[0..4][c] of its features in registers; the warps of a CTA are reduced through shared
-// memory before the atomics.  dE = g1 (+ g2).
-__global__ void __launch_bounds__(256) embed_bwd_kernel(const float *__restrict__ obs, int n, int samples_per_warp,
-                                                        const bf16 *__restrict__ g1, const bf16 *__restrict__ g2,
-                                                        const float *__restrict__ emb_w, const float *__restrict__ emb_b,
-                                                        float *__restrict__ g_pos, float *__restrict__ g_w, float *__restrict__ g_b) {
-    constexpr int kAcc = F + 1 + S;                            // per feature: 14 dW, db, 5 dpos
-    constexpr int kObsRegs = (S * F + 31) / 32;                // a window's 70 floats spread over the lanes
-    __shared__ float s_obs[8][S * F + 2];
-    __shared__ float s_red[kAcc][D];
-    __shared__ __align__(16) float s_w[F][D];                  // embedding weight, transposed: a lane reads its 4 features at once
+// embedding backward: E = relu(obs W^T + b) + pos.  The forward left the ReLU activity bits (policy_kernels.cuh:
+// embed_kernel) and a bf16 copy of the observations padded to 64 columns, so what remains here is elementwise:
+// dPre = (g1 [+ g2]) masked -> bf16 rows, dpos = per-position column sums of the unmasked gradient (registers, lane = 4
+// features).  dW = dPre^T obs16 and db = dPre^T 1 then come from the tensor-core weight-gradient kernel (Kin = 64).
+__global__ void __launch_bounds__(256) embed_mask_kernel(const bf16 *__restrict__ g1, const bf16 *__restrict__ g2,
+                                                         const uint32_t *__restrict__ mask /* this net's 4 words of row 0; row stride 8 */,
+                                                         int n, int samples_per_warp, bf16 *__restrict__ dpre, float *__restrict__ g_pos) {
+    __shared__ float s_red[S][D];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int gw = blockIdx.x * 8 + warp;
-    for (int i = threadIdx.x; i < kAcc * D; i += blockDim.x) (&s_red[0][0])[i] = 0.0f;
-    for (int i = threadIdx.x; i < F * D; i += blockDim.x) s_w[i % F][i / F] = emb_w[i];
+    for (int i = threadIdx.x; i < S * D; i += blockDim.x) (&s_red[0][0])[i] = 0.0f;
     __syncthreads();
+    const int gw = blockIdx.x * 8 + warp;
     const int b0 = gw * samples_per_warp, b1 = min(n, b0 + samples_per_warp);
-    float bias[4], acc[4][kAcc];
+    const int wsel = (lane >> 4) * 2, l0 = 2 * (lane & 15);      // word pair and bit of feature 4 * lane
+    float dpos[S][4];
 #pragma unroll
-    for (int f = 0; f < 4; ++f) {
-        bias[f] = emb_b[lane * 4 + f];
+    for (int s = 0; s < S; ++s)
 #pragma unroll
-        for (int k = 0; k < kAcc; ++k) acc[f][k] = 0.0f;
-    }
-    // software pipeline: the next window's gradient rows and observation are in flight while this one is consumed
-    uint2 nx1[S], nx2[S];
-    float nxo[kObsRegs];
-    auto fetch = [&](int b) {
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-            const size_t off = ((size_t)b * S + s) * D + lane * 4;
-            nx1[s] = *reinterpret_cast<const uint2 *>(g1 + off);
-            nx2[s] = g2 ? *reinterpret_cast<const uint2 *>(g2 + off) : make_uint2(0u, 0u);
-        }
-#pragma unroll
-        for (int i = 0; i < kObsRegs; ++i) nxo[i] = (lane + 32 * i < S * F) ? obs[(size_t)b * S * F + lane + 32 * i] : 0.0f;
-    };
-    if (b0 < b1) fetch(b0);
+        for (int f = 0; f < 4; ++f) dpos[s][f] = 0.0f;
     for (int b = b0; b < b1; ++b) {
-        uint2 c1[S], c2[S];
-#pragma unroll
-        for (int s = 0; s < S; ++s) { c1[s] = nx1[s]; c2[s] = nx2[s]; }
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < kObsRegs; ++i) if (lane + 32 * i < S * F) s_obs[warp][lane + 32 * i] = nxo[i];
-        __syncwarp();
-        if (b + 1 < b1) fetch(b + 1);
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            float g[4], t[4];
-            unpack4(c1[s], g);
-            unpack4(c2[s], t);
-            const float *o = s_obs[warp] + s * F;
-            float pre[4];
+            const size_t row = (size_t)b * S + s, off = row * D + lane * 4;
+            float g[4];
+            unpack4(*reinterpret_cast<const uint2 *>(g1 + off), g);
+            if (g2) {
+                float t[4];
+                unpack4(*reinterpret_cast<const uint2 *>(g2 + off), t);
 #pragma unroll
-            for (int f = 0; f < 4; ++f) { g[f] += t[f]; pre[f] = bias[f]; }
-#pragma unroll
-            for (int j = 0; j < F; ++j) {
-                const float4 wj = *reinterpret_cast<const float4 *>(&s_w[j][lane * 4]);
-                const float oj = o[j];
-                pre[0] = fmaf(wj.x, oj, pre[0]); pre[1] = fmaf(wj.y, oj, pre[1]);
-                pre[2] = fmaf(wj.z, oj, pre[2]); pre[3] = fmaf(wj.w, oj, pre[3]);
+                for (int f = 0; f < 4; ++f) g[f] += t[f];
             }
+            const uint2 m = *reinterpret_cast<const uint2 *>(mask + row * 8 + wsel);       // (even-feature word, odd-feature word)
 #pragma unroll
             for (int f = 0; f < 4; ++f) {
-                acc[f][F + 1 + s] += g[f];
-                const float gm = pre[f] > 0.0f ? g[f] : 0.0f;
-                acc[f][F] += gm;
-#pragma unroll
-                for (int j = 0; j < F; ++j) acc[f][j] = fmaf(gm, o[j], acc[f][j]);
+                dpos[s][f] += g[f];
+                const unsigned bit = (((f & 1) ? m.y : m.x) >> (l0 + (f >> 1))) & 1u;
+                g[f] = bit ? g[f] : 0.0f;
             }
+            *reinterpret_cast<uint2 *>(dpre + off) = pack4(g);
         }
     }
 #pragma unroll
-    for (int f = 0; f < 4; ++f)
+    for (int s = 0; s < S; ++s)
 #pragma unroll
-        for (int k = 0; k < kAcc; ++k) atomicAdd(&s_red[k][lane * 4 + f], acc[f][k]);
+        for (int f = 0; f < 4; ++f) atomicAdd(&s_red[s][lane * 4 + f], dpos[s][f]);
     __syncthreads();
-    for (int i = threadIdx.x; i < kAcc * D; i += blockDim.x) {
-        const int k = i / D, c = i % D;
-        const float v = s_red[k][c];
-        if (k < F) atomicAdd(g_w + c * F + k, v);
-        else if (k == F) atomicAdd(g_b + c, v);
-        else atomicAdd(g_pos + (k - F - 1) * D + c, v);
-    }
+    for (int i = threadIdx.x; i < S * D; i += blockDim.x) atomicAdd(g_pos + i, (&s_red[0][0])[i]);
 }
 
 // second layers of the two heads (transformer_net.py:78-91): logits = W2a ha + b2a, value = W2c hc + b2c; one thread per sample
@@ -588,8 +549,9 @@ struct uavtrain {
     bf16 *T, *T2;                                // forward scratch (GEMM outputs feeding add+LN)
     bf16 *dS1, *dS2, *dH, *dQKV, *dXa, *dXb, *dQ, *tmp;   // backward scratch
     float *zeros = nullptr, *loss_acc = nullptr;
+    bf16 *obs16 = nullptr;                       // [R,64] bf16 observations (zero-padded): B operand of the embedding weight gradient
+    uint32_t *relu_mask = nullptr;               // [R][2 nets][4 words] ReLU activity bits of the two embeddings
     uint8_t *pad = nullptr;
-    const float *obs = nullptr;                  // of the last forward (the embedding backward re-reads it)
     const float *params = nullptr;               // likewise (second head layers)
     void *gemm_ws = nullptr;
     std::vector<void *> allocs;
@@ -672,9 +634,10 @@ void gemm(TCtx &c, const bf16 *A, int64_t lda, const bf16 *W, const float *bias,
     if (r) c.rc = tfail(c.p, -2, "tcgen05 GEMM (M=%d N=%d K=%d) failed with %d", M, N, K, r);
 }
 void wgrad(TCtx &c, const bf16 *dY, int64_t ld_dy, const bf16 *X, int64_t ld_x, int rows, int Nout, int Kin, float *dW,
-           int nout_valid = -1, float *dbias = nullptr) {
+           int nout_valid = -1, float *dbias = nullptr, int out_ld = 0, int kin_valid = 0) {
     if (c.rc) return;
-    const int r = uavp::wgrad(dY, ld_dy, X, ld_x, rows, Nout, Kin, dW, nout_valid < 0 ? Nout : nout_valid, dbias, c.p->sms, c.s);
+    const int r = uavp::wgrad(dY, ld_dy, X, ld_x, rows, Nout, Kin, dW, nout_valid < 0 ? Nout : nout_valid, dbias, c.p->sms, c.s, out_ld,
+                              kin_valid);
     if (r) c.rc = tfail(c.p, -2, "weight-gradient kernel (rows=%d Nout=%d Kin=%d) failed with %d", rows, Nout, Kin, r);
 }
 void add_ln(TCtx &c, const bf16 *x, int64_t xs, const bf16 *y, const float *g, const float *b, int rows, bf16 *out16, float *out32,
@@ -777,12 +740,13 @@ void full_layer_bwd(TCtx &c, const uavp::LayerW &L, const LayerT &T, const Layer
     wgrad(c, p->dQKV, 3 * D, X, D, R, 3 * D, D, g + o.in_w, -1, g + o.in_b);                           // + bias gradient
     gemm(c, p->dQKV, 3 * D, T.in_t, nullptr, dXg, R, D, 3 * D, 0);
 }
-void embed_bwd(TCtx &c, const BlockOff &bo, const uavp::BlockW &b, float *g, int n, const bf16 *g1, const bf16 *g2) {
+void embed_bwd(TCtx &c, const BlockOff &bo, int net, float *g, int n, const bf16 *g1, const bf16 *g2) {
     if (c.rc) return;
-    const int warps = c.p->sms * 8 * 4;                         // 4 CTAs of 8 warps per SM
-    const int spw = max(1, (n + warps - 1) / warps);
-    const int grid = ((n + spw - 1) / spw + 7) / 8;
-    embed_bwd_kernel<<<grid, 256, 0, c.s>>>(c.p->obs, n, spw, g1, g2, b.emb_w, b.emb_b, g + bo.pos, g + bo.emb_w, g + bo.emb_b);
+    uavtrain *p = c.p;
+    int grid, rpw;
+    row_grid(p, n, grid, rpw);                                  // (here a "row" is a window of 5 token rows)
+    embed_mask_kernel<<<grid, 256, 0, c.s>>>(g1, g2, p->relu_mask + net * 4, n, rpw, p->tmp, g + bo.pos);
+    wgrad(c, p->tmp, D, p->obs16, 64, n * S, D, 64, g + bo.emb_w, -1, g + bo.emb_b, F, F);
 }
 }  // namespace
 
@@ -829,6 +793,8 @@ extern "C" int uavtrain_create(int32_t device, int32_t max_samples, uavtrain_t *
     if (e == cudaSuccess) e = talloc(p, &p->fc.rstd2, R);
     if (e == cudaSuccess) e = talloc(p, &p->pad, R);
     if (e == cudaSuccess) e = talloc(p, &p->loss_acc, (size_t)4);
+    if (e == cudaSuccess) e = talloc(p, &p->obs16, R * 64);
+    if (e == cudaSuccess) e = talloc(p, &p->relu_mask, R * 8);
     if (e == cudaSuccess) e = talloc(p, &p->zeros, (size_t)3 * D);
     if (e == cudaSuccess) e = cudaMemset(p->zeros, 0, 3 * D * sizeof(float));
     if (e == cudaSuccess) { void *ws = nullptr; e = cudaMalloc(&ws, uavp::gemm_workspace_bytes()); if (e == cudaSuccess) { p->allocs.push_back(ws); p->gemm_ws = ws; } }
@@ -872,13 +838,12 @@ int forward_impl(uavtrain *p, const float *w, const float *d_obs, int n, float *
     TCtx c{p, (cudaStream_t)stream, 0};
     const bool heads = d_logits != nullptr;
     p->n = 0;
-    p->obs = d_obs;
     bind_params(p->actor, p->actor_off, w);
     bind_params(p->critic, p->critic_off, w);
     for (int j = 0; j < p->n_jobs; ++j) p->jobs.job[j].src = w + p->job_src_off[j];
     prep_weights_kernel<<<dim3(24, p->n_jobs), 256, 0, c.s>>>(p->jobs);
     const int R = n * S;
-    embed_kernel<<<(R + kEmbTok - 1) / kEmbTok, D, 0, c.s>>>(d_obs, R, p->actor, p->critic, p->Ea, p->Ec, p->pad);
+    embed_kernel<<<(R + kEmbTok - 1) / kEmbTok, D, 0, c.s>>>(d_obs, R, p->actor, p->critic, p->Ea, p->Ec, p->pad, p->obs16, p->relu_mask);
     last_layer_fwd(c, p->actor.layer[0], p->Ea, n, p->la, d_feat, 2 * D, heads ? p->ahead.Z : nullptr);
     full_layer_fwd(c, p->critic.layer[0], p->Ec, n, p->fc);
     last_layer_fwd(c, p->critic.layer[1], p->fc.Xout, n, p->lc, d_feat ? d_feat + D : nullptr, 2 * D, heads ? p->chead.Z : nullptr);
@@ -917,12 +882,12 @@ int backward_impl(uavtrain *p, const float *d_dfeat, const float *d_dlogits, con
     // actor: one (last) layer on the embedding
     last_layer_bwd(c, p->actor.layer[0], p->actor_t[0], p->actor_off.layer[0], g, p->Ea, n, p->la, heads ? nullptr : d_dfeat, 2 * D,
                    heads ? p->ahead.Z : nullptr, p->dXa);
-    embed_bwd(c, p->actor_off, p->actor, g, n, p->dXa, nullptr);
+    embed_bwd(c, p->actor_off, 0, g, n, p->dXa, nullptr);
     // critic: last layer, inner layer, embedding
     last_layer_bwd(c, p->critic.layer[1], p->critic_t[1], p->critic_off.layer[1], g, p->fc.Xout, n, p->lc,
                    heads ? nullptr : d_dfeat + D, 2 * D, heads ? p->chead.Z : nullptr, p->dXa);
     full_layer_bwd(c, p->critic.layer[0], p->critic_t[0], p->critic_off.layer[0], g, p->Ec, n, p->fc, p->dXa, p->dXb);
-    embed_bwd(c, p->critic_off, p->critic, g, n, p->dXb, p->dS1);
+    embed_bwd(c, p->critic_off, 1, g, n, p->dXb, p->dS1);
     if (c.rc) return c.rc;
     T_TRY(p, cudaGetLastError());
     return 0;

@@ -29,7 +29,7 @@ struct WgTma {
     static constexpr int kSlab = 64;
     static constexpr int kBox = kSlab * 128;                 // bytes of one [64 x 64] bf16 box
     static constexpr int kA = 2 * kBox, kB = (KIN / 64) * kBox, kStage = kA + kB;
-    static constexpr int kStages = KIN == 128 ? 6 : 4;
+    static constexpr int kStages = KIN == 64 ? 8 : KIN == 128 ? 6 : 4;
     static constexpr int kOnes = kSlab * 16 * 2;
     static constexpr int kTotal = kStages * kStage + kOnes + 256 + 1024;    // + barriers + alignment slack
     static_assert(4 * 32 * (KIN + 1) * 4 <= kStages * kStage, "the epilogue transposes through the operand buffers");
@@ -38,7 +38,8 @@ struct WgTma {
 template <int KIN>
 __global__ void __launch_bounds__(kTmaThreads, 1) wgrad_tma_kernel(const __grid_constant__ CUtensorMap tm_dy,
                                                                    const __grid_constant__ CUtensorMap tm_x, int rows,
-                                                                   float *__restrict__ dW, int nout_valid, float *__restrict__ dbias) {
+                                                                   float *__restrict__ dW, int nout_valid, float *__restrict__ dbias,
+                                                                   int out_ld, int kin_valid) {
     using SM = WgTma<KIN>;
     constexpr int kSlab = SM::kSlab, kStages = SM::kStages;
     extern __shared__ unsigned char smem_raw[];
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) wgrad_tma_kernel(const __grid_
     if ((int)blockIdx.x >= slabs) return;
     const int cnt = (slabs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int nb = blockIdx.y;
-    constexpr int kCols = KIN == 128 ? 256 : KIN;
+    constexpr int kCols = KIN <= 128 ? 2 * KIN : KIN;        // accumulators (+ 16 columns for the bias block when KIN <= 128)
 
     if (warp == 1) tc::tmem_alloc(tmem_slot, kCols);
     if (dbias) {
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) wgrad_tma_kernel(const __grid_
                     const uint64_t ad = tc::smem_desc_sw128(a + j * 2048, SM::kBox, 1024);
                     const uint64_t bd = tc::smem_desc_sw128(b + j * 2048, SM::kBox, 1024);
                     tc::mma_bf16(tmem, ad, bd, idesc, (it > 0 || j > 0) ? 1u : 0u);
-                    if (KIN == 128 && dbias)
+                    if (KIN <= 128 && dbias)
                         tc::mma_bf16(tmem + KIN, ad, tc::smem_desc(tc::smem_u32(ones), 16 * 16, 128), tc::instr_desc_bf16_mn(128, 16),
                                      (it > 0 || j > 0) ? 1u : 0u);
                 }
@@ -117,11 +118,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1) wgrad_tma_kernel(const __grid_
             for (int i = 0; i < 32; ++i) stage_f[lane * (KIN + 1) + c + i] = v[i];
         }
         __syncwarp();
-        float *out = dW + ((size_t)nb * 128 + q * 32) * KIN;
+        float *out = dW + ((size_t)nb * 128 + q * 32) * out_ld;
         for (int r = 0; r < min(32, rows_out); ++r)
-#pragma unroll
-            for (int c = lane; c < KIN; c += 32) atomicAdd(out + r * KIN + c, stage_f[r * (KIN + 1) + c]);
-        if (KIN == 128 && dbias) {
+            for (int c = lane; c < kin_valid; c += 32) atomicAdd(out + r * out_ld + c, stage_f[r * (KIN + 1) + c]);
+        if (KIN <= 128 && dbias) {
             float v[32];
             tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + KIN, v);
             if (lane < rows_out) atomicAdd(dbias + nb * 128 + q * 32 + lane, v[0]);
@@ -160,22 +160,27 @@ int wgrad_prepare() {
     }
     if (cudaFuncSetAttribute(wgrad_tma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgTma<128>::kTotal) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(wgrad_tma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgTma<256>::kTotal) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(wgrad_tma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgTma<64>::kTotal) != cudaSuccess) return -1;
     return 0;
 }
 
 // dW[Nout, Kin] (fp32, dense) += dY[rows, Nout]^T X[rows, Kin];  Nout % 128 == 0, Kin in {128, 256}, ld % 8 == 0.
-// Only the first nout_valid rows of dW are written (dY columns beyond that are padding).  dbias (optional, Kin = 128
-// only): dbias[Nout] += column sums of dY, computed by the tensor cores as dY^T 1 alongside the main product.
+// Only the first nout_valid rows of dW are written (dY columns beyond that are padding).  dbias (optional, Kin <= 128):
+// dbias[Nout] += column sums of dY, computed by the tensor cores as dY^T 1 alongside the main product.
+// Kin = 64: X is padded to 64 columns; the first kin_valid columns go out with row stride out_ld (the embedding's [128,14]).
 int wgrad(const __nv_bfloat16 *dY, int64_t ld_dy, const __nv_bfloat16 *X, int64_t ld_x, int rows, int Nout, int Kin, float *dW,
-          int nout_valid, float *dbias, int num_sms, cudaStream_t stream) {
-    if (rows <= 0 || Nout % 128 || (Kin != 128 && Kin != 256) || ld_dy % 8 || ld_x % 8 || (dbias && Kin != 128)) return -1;
+          int nout_valid, float *dbias, int num_sms, cudaStream_t stream, int out_ld, int kin_valid) {
+    if (rows <= 0 || Nout % 128 || (Kin != 64 && Kin != 128 && Kin != 256) || ld_dy % 8 || ld_x % 8 || (dbias && Kin > 128)) return -1;
+    if (out_ld <= 0) out_ld = Kin;
+    if (kin_valid <= 0) kin_valid = Kin;
     const int slab = WgTma<128>::kSlab;
     const int gy = Nout / 128, slabs = (rows + slab - 1) / slab;
     const int gx = max(1, min(slabs, num_sms / gy));
     CUtensorMap tm_dy, tm_x;
     if (!g_encode || !make_map(&tm_dy, dY, ld_dy, rows, Nout) || !make_map(&tm_x, X, ld_x, rows, Kin)) return -3;
-    if (Kin == 128) wgrad_tma_kernel<128><<<dim3(gx, gy), kTmaThreads, WgTma<128>::kTotal, stream>>>(tm_dy, tm_x, rows, dW, nout_valid, dbias);
-    else wgrad_tma_kernel<256><<<dim3(gx, gy), kTmaThreads, WgTma<256>::kTotal, stream>>>(tm_dy, tm_x, rows, dW, nout_valid, dbias);
+    if (Kin == 64) wgrad_tma_kernel<64><<<dim3(gx, gy), kTmaThreads, WgTma<64>::kTotal, stream>>>(tm_dy, tm_x, rows, dW, nout_valid, dbias, out_ld, kin_valid);
+    else if (Kin == 128) wgrad_tma_kernel<128><<<dim3(gx, gy), kTmaThreads, WgTma<128>::kTotal, stream>>>(tm_dy, tm_x, rows, dW, nout_valid, dbias, out_ld, kin_valid);
+    else wgrad_tma_kernel<256><<<dim3(gx, gy), kTmaThreads, WgTma<256>::kTotal, stream>>>(tm_dy, tm_x, rows, dW, nout_valid, dbias, out_ld, kin_valid);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -188,5 +193,5 @@ extern "C" int uavpolicy_selftest_wgrad(const void *d_dy, int64_t ld_dy, const v
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -2;
     return uavp::wgrad(static_cast<const __nv_bfloat16 *>(d_dy), ld_dy, static_cast<const __nv_bfloat16 *>(d_x), ld_x, rows, n_out,
-                       k_in, d_dw, n_out, d_dbias, sms, (cudaStream_t)stream);
+                       k_in, d_dw, n_out, d_dbias, sms, (cudaStream_t)stream, 0, 0);
 }
