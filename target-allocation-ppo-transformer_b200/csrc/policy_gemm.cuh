@@ -10,5 +10,9 @@ namespace uavp {
 // relu != 0 applies max(0, .).  Returns 0 or a negative code.  workspace: device scratch of workspace_bytes.
 int gemm_bias_act(const void *A, int64_t lda, const void *W, const float *bias, void *D, int M, int N, int K, int relu,
                   void *workspace, size_t workspace_bytes, cudaStream_t stream);
+// D[M,N] = (A[M,K] W[N,K]^T) where aux[M,N] != 0, else 0 (aux: bf16, row stride ld_aux): ReLU backward fused into the
+// epilogue of the activation-gradient GEMM.
+int gemm_drelu(const void *A, int64_t lda, const void *W, const void *aux, int64_t ld_aux, void *D, int M, int N, int K, void *workspace,
+               size_t workspace_bytes, cudaStream_t stream);
 size_t gemm_workspace_bytes();
 }  // namespace uavp

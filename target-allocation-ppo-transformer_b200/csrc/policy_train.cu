@@ -6,7 +6,8 @@
 // LayerNorm statistics, softmax, all reductions and every parameter gradient are fp32.
 //   activation-gradient GEMMs  dX = dY W        -> uavp::gemm_bias_act on pre-transposed bf16 weights (tcgen05)
 //   weight-gradient GEMMs      dW += dY^T X     -> uavp::wgrad (policy_wgrad.cu: split-K, accumulator resident in TMEM)
-//   everything else (LayerNorm / ReLU / attention / embedding backward, bias + LayerNorm parameter gradients) is
+//   ReLU backward                           -> fused into the epilogue of the activation-gradient GEMM (uavp::gemm_drelu)
+//   everything else (LayerNorm / attention / embedding backward, bias + LayerNorm parameter gradients) is
 //   hand-written below; bias gradients are accumulated by the kernel that produces the corresponding dY, or by the
 //   weight-gradient kernel (as dY^T 1 on the tensor cores) where dY comes out of the attention backward.
 // Two boundaries: uavtrain_forward / _backward stop at the trunks' last-token features ([n,2,128] out, their gradient
@@ -164,29 +165,6 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void *__restrict__ dy
     block_colsum_flush<4, D>(ag, s_red, g_gamma, col);
     block_colsum_flush<4, D>(ab, s_red, g_beta, col);
     block_colsum_flush<4, D>(az, s_red, g_bias, col);
-}
-
-// ReLU backward over 256 features, in place: dh *= (h > 0); g_bias += column sums of the masked gradient
-__global__ void __launch_bounds__(256) relu_bwd_kernel(bf16 *__restrict__ dh, const bf16 *__restrict__ h, int rows, int rows_per_warp,
-                                                       float *__restrict__ g_bias) {
-    __shared__ float s_red[8 * FF];
-    const int lane = threadIdx.x & 31;
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int r0 = gw * rows_per_warp, r1 = min(rows, r0 + rows_per_warp);
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int r = r0; r < r1; ++r) {
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const size_t off = (size_t)r * FF + half * 128 + lane * 4;
-            float g[4], a[4];
-            unpack4(*reinterpret_cast<const uint2 *>(dh + off), g);
-            unpack4(*reinterpret_cast<const uint2 *>(h + off), a);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { g[i] = a[i] > 0.0f ? g[i] : 0.0f; acc[half * 4 + i] += g[i]; }
-            *reinterpret_cast<uint2 *>(dh + off) = pack4(g);
-        }
-    }
-    block_colsum_flush<8, FF>(acc, s_red, g_bias, [](int l, int i) { return (i >> 2) * 128 + l * 4 + (i & 3); });
 }
 
 // attention backward.  dS_ij = p_ij (dO_i.v_j - sum_l p_il dO_i.v_l) / 4;  dQ_i = sum_j dS_ij k_j;  dK_j = sum_i dS_ij q_i;
@@ -660,12 +638,6 @@ void ln_bwd(TCtx &c, const float *dy32, int64_t dy_stride, const bf16 *dy16, con
     if (dy32) ln_bwd_kernel<true><<<grid, 256, 0, c.s>>>(dy32, dy_stride, add, xhat, rstd, gamma, rows, rpw, dz, g_gamma, g_beta, g_bias);
     else ln_bwd_kernel<false><<<grid, 256, 0, c.s>>>(dy16, D, add, xhat, rstd, gamma, rows, rpw, dz, g_gamma, g_beta, g_bias);
 }
-void relu_bwd(TCtx &c, bf16 *dh, const bf16 *h, int rows, float *g_bias) {
-    if (c.rc) return;
-    int grid, rpw;
-    row_grid(c.p, rows, grid, rpw);
-    relu_bwd_kernel<<<grid, 256, 0, c.s>>>(dh, h, rows, rpw, g_bias);
-}
 
 // ---- forward -----------------------------------------------------------------------------------------------
 void last_layer_fwd(TCtx &c, const uavp::LayerW &L, const bf16 *X, int n, LastAct &A, float *feat, int64_t feat_stride, bf16 *feat16) {
@@ -701,9 +673,11 @@ void ffn_ln_bwd(TCtx &c, const uavp::LayerW &L, const LayerT &T, const LayerOff 
     uavtrain *p = c.p;
     ln_bwd(c, dz32, dz_stride, dz16, nullptr, XH2, rstd2, L.n2_w, rows, p->dS2, g + o.n2_w, g + o.n2_b, g + o.l2_b);
     wgrad(c, p->dS2, D, Hact, FF, rows, D, FF, g + o.l2_w);
-    gemm(c, p->dS2, D, T.l2_t, nullptr, p->dH, rows, FF, D, 0);
-    relu_bwd(c, p->dH, Hact, rows, g + o.l1_b);
-    wgrad(c, p->dH, FF, Y1, D, rows, FF, D, g + o.l1_w);
+    if (!c.rc) {                                              // dH = (dS2 W2) masked by the forward's ReLU, in one GEMM
+        const int r = uavp::gemm_drelu(p->dS2, D, T.l2_t, Hact, FF, p->dH, rows, FF, D, p->gemm_ws, uavp::gemm_workspace_bytes(), c.s);
+        if (r) c.rc = tfail(p, -2, "tcgen05 GEMM with ReLU-backward epilogue (M=%d) failed with %d", rows, r);
+    }
+    wgrad(c, p->dH, FF, Y1, D, rows, FF, D, g + o.l1_w, -1, g + o.l1_b);                  // + bias gradient dH^T 1
     gemm(c, p->dH, FF, T.l1_t, nullptr, p->tmp, rows, D, FF, 0);
     ln_bwd(c, nullptr, 0, p->tmp, p->dS2, XH1, rstd1, L.n1_w, rows, p->dS1, g + o.n1_w, g + o.n1_b, g + o.out_b);
 }
