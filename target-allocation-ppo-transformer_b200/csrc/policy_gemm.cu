@@ -16,10 +16,10 @@
 namespace uavp {
 using namespace cute;
 
-template <template <class> class Act>
+template <template <class> class Act, class TileN = _128>
 struct GemmT {
     using Elt = cutlass::bfloat16_t;
-    using TileShape = Shape<_128, _128, _64>;
+    using TileShape = Shape<_128, TileN, _64>;
     using ClusterShape = Shape<_1, _1, _1>;
     using Fusion = cutlass::epilogue::fusion::LinCombPerColBiasEltAct<Act, Elt, float, float>;
     using Epilogue = typename cutlass::epilogue::collective::CollectiveBuilder<
@@ -129,6 +129,13 @@ size_t gemm_workspace_bytes() { return 1 << 20; }
 
 int gemm_bias_act(const void *A, int64_t lda, const void *W, const float *bias, void *D, int M, int N, int K, int relu,
                   void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+    // wide outputs: 128 x 256 tiles read every A tile once per 256 output columns instead of once per 128
+    if (N % 256 == 0 && M >= 16384) {
+        if (relu) return GemmT<cutlass::epilogue::thread::ReLu, _256>::run(A, lda, W, bias, D, M, N, K, workspace, workspace_bytes, stream);
+        return GemmT<cutlass::epilogue::thread::Identity, _256>::run(A, lda, W, bias, D, M, N, K, workspace, workspace_bytes, stream);
+    }
+    if (N % 192 == 0 && M >= 16384 && !relu)      // the packed Q|K|V projection (N = 384): two 192-column tiles
+        return GemmT<cutlass::epilogue::thread::Identity, _192>::run(A, lda, W, bias, D, M, N, K, workspace, workspace_bytes, stream);
     if (relu) return GemmT<cutlass::epilogue::thread::ReLu>::run(A, lda, W, bias, D, M, N, K, workspace, workspace_bytes, stream);
     return GemmT<cutlass::epilogue::thread::Identity>::run(A, lda, W, bias, D, M, N, K, workspace, workspace_bytes, stream);
 }
