@@ -42,7 +42,9 @@ LIBS = {
         ("ppo_attn.cu", [], ["../../include/uavenv_b200.h"]),
     ],
     POLICY_LIB_PATH: [
-        ("policy_gemm.cu", "CUTLASS", ["policy_gemm.cuh"]),
+        ("policy_gemm.cu", "CUTLASS", ["policy_gemm.cuh", "policy_gemm_impl.cuh"]),
+        ("policy_gemm_wide.cu", "CUTLASS", ["policy_gemm.cuh", "policy_gemm_impl.cuh"]),
+        ("policy_gemm_drelu.cu", "CUTLASS", ["policy_gemm.cuh"]),
         ("policy_forward.cu", [], ["policy_gemm.cuh", "policy_kernels.cuh", "policy_weights.cuh", "../../include/uavpolicy_b200.h"]),
         ("policy_train.cu", [], ["policy_gemm.cuh", "policy_kernels.cuh", "policy_weights.cuh", "../../include/uavpolicy_b200.h"]),
         ("policy_wgrad.cu", [], ["tcgen05_util.cuh", "policy_weights.cuh", "../../include/uavpolicy_b200.h"]),
@@ -84,7 +86,7 @@ def build(force=False, verbose=False, lib=None):
             continue
         nvcc = _nvcc()
         os.makedirs(OBJ_DIR, exist_ok=True)
-        objs = []
+        objs, jobs = [], []
         for src, extra, headers in LIBS[target]:
             obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
             objs.append(obj)
@@ -92,9 +94,13 @@ def build(force=False, verbose=False, lib=None):
                 continue
             flags = (_cutlass_includes() + ["--expt-relaxed-constexpr"]) if extra == "CUTLASS" else list(extra)
             flags += os.environ.get("UAVENV_EXTRA_NVCC_FLAGS", "").split()
-            cmd = [nvcc] + ARCH + COMMON + flags + (["-Xptxas", "-v"] if verbose else []) + [
-                "-c", os.path.join(CSRC, src), "-o", obj]
-            r = subprocess.run(cmd, capture_output=True, text=True)
+            jobs.append((src, [nvcc] + ARCH + COMMON + flags + (["-Xptxas", "-v"] if verbose else []) + [
+                "-c", os.path.join(CSRC, src), "-o", obj]))
+        # the CUTLASS instantiations take minutes each: compile the translation units side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as pool:
+            results = list(pool.map(lambda j: (j[0], subprocess.run(j[1], capture_output=True, text=True)), jobs))
+        for src, r in results:
             if verbose or r.returncode != 0:
                 sys.stderr.write(r.stdout + r.stderr)
             if r.returncode != 0:

@@ -3,139 +3,23 @@
 // memory ring, a single elected thread issues tcgen05.mma into a TMEM accumulator, the epilogue warps read it back
 // with tcgen05.ld, add the per-column bias, apply ReLU and store bf16 through TMA.  The pipeline is CUTLASS 4.x's
 // sm100 collective (cutlass/gemm/collective/builders/sm100_umma_builder.inl), instantiated here for our shapes.
-#include "policy_gemm.cuh"
-
-#include "cute/tensor.hpp"
-#include "cutlass/cutlass.h"
-#include "cutlass/epilogue/collective/collective_builder.hpp"
-#include "cutlass/epilogue/fusion/operations.hpp"
-#include "cutlass/gemm/collective/collective_builder.hpp"
-#include "cutlass/gemm/device/gemm_universal_adapter.h"
-#include "cutlass/gemm/kernel/gemm_universal.hpp"
+#include "policy_gemm_impl.cuh"
 
 namespace uavp {
-using namespace cute;
-
-template <template <class> class Act, class TileN = _128>
-struct GemmT {
-    using Elt = cutlass::bfloat16_t;
-    using TileShape = Shape<_128, TileN, _64>;
-    using ClusterShape = Shape<_1, _1, _1>;
-    using Fusion = cutlass::epilogue::fusion::LinCombPerColBiasEltAct<Act, Elt, float, float>;
-    using Epilogue = typename cutlass::epilogue::collective::CollectiveBuilder<
-        cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, TileShape, ClusterShape,
-        cutlass::epilogue::collective::EpilogueTileAuto, float, float, Elt, cutlass::layout::RowMajor, 8, Elt,
-        cutlass::layout::RowMajor, 8, cutlass::epilogue::collective::EpilogueScheduleAuto, Fusion>::CollectiveOp;
-    using Mainloop = typename cutlass::gemm::collective::CollectiveBuilder<
-        cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, Elt, cutlass::layout::RowMajor, 8, Elt,
-        cutlass::layout::ColumnMajor, 8, float, TileShape, ClusterShape,
-        cutlass::gemm::collective::StageCountAutoCarveout<static_cast<int>(sizeof(typename Epilogue::SharedStorage))>,
-        cutlass::gemm::collective::KernelScheduleAuto>::CollectiveOp;
-    using Kernel = cutlass::gemm::kernel::GemmUniversal<Shape<int, int, int, int>, Mainloop, Epilogue, void>;
-    using Gemm = cutlass::gemm::device::GemmUniversalAdapter<Kernel>;
-
-    static int run(const void *A, int64_t lda, const void *W, const float *bias, void *D, int M, int N, int K, void *ws,
-                   size_t ws_bytes, cudaStream_t stream) {
-        typename Kernel::StrideA sa;   // (lda, 1, batch)
-        typename Kernel::StrideB sb;   // W [N,K] row-major == B [K,N] column-major: (K, 1, batch)
-        typename Kernel::StrideC sc;
-        typename Kernel::StrideD sd;
-        get<0>(sa) = lda; get<2>(sa) = 0;
-        get<0>(sb) = (int64_t)K; get<2>(sb) = 0;
-        get<0>(sc) = (int64_t)N; get<2>(sc) = 0;
-        get<0>(sd) = (int64_t)N; get<2>(sd) = 0;
-        typename Gemm::Arguments args{cutlass::gemm::GemmUniversalMode::kGemm,
-                                      {M, N, K, 1},
-                                      {static_cast<const Elt *>(A), sa, static_cast<const Elt *>(W), sb},
-                                      {{}, nullptr, sc, static_cast<Elt *>(D), sd}};
-        args.epilogue.thread.alpha = 1.0f;
-        args.epilogue.thread.beta = 0.0f;
-        args.epilogue.thread.bias_ptr = bias;
-        Gemm gemm;
-        if (gemm.can_implement(args) != cutlass::Status::kSuccess) return -1;
-        if (Gemm::get_workspace_size(args) > ws_bytes) return -3;
-        if (gemm.initialize(args, ws, stream) != cutlass::Status::kSuccess) return -2;
-        return gemm.run(stream) == cutlass::Status::kSuccess ? 0 : -2;
-    }
-};
-
-// gradient of ReLU given its OUTPUT z: d where z > 0, else 0 (element and fragment forms, as the epilogue visitor calls them)
-template <class T>
-struct ReluGradByOutput {
-    CUTLASS_HOST_DEVICE T operator()(T d, T z) const { return z > T(0) ? d : T(0); }
-};
-template <class T, int N>
-struct ReluGradByOutput<cutlass::Array<T, N>> {
-    template <class U>
-    CUTLASS_HOST_DEVICE cutlass::Array<T, N> operator()(cutlass::Array<T, N> const &d, cutlass::Array<U, N> const &z) const {
-        cutlass::Array<T, N> y;
-        CUTLASS_PRAGMA_UNROLL
-        for (int i = 0; i < N; ++i) y[i] = float(static_cast<U>(z[i])) > 0.0f ? static_cast<T>(d[i]) : T(0);
-        return y;
-    }
-};
-
-// D[M,N] = (A[M,K] W[N,K]^T) masked by aux[M,N] != 0: the activation-gradient GEMM in front of a ReLU with the ReLU's
-// backward fused into the epilogue (aux = the forward's post-ReLU activations, loaded by TMA next to the accumulator)
-struct GemmDRelu {
-    using Elt = cutlass::bfloat16_t;
-    using TileShape = Shape<_128, _128, _64>;
-    using ClusterShape = Shape<_1, _1, _1>;
-    using Fusion = cutlass::epilogue::fusion::LinCombDeEltAct<cutlass::layout::RowMajor, ReluGradByOutput, Elt, float, Elt>;
-    using Epilogue = typename cutlass::epilogue::collective::CollectiveBuilder<
-        cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, TileShape, ClusterShape,
-        cutlass::epilogue::collective::EpilogueTileAuto, float, float, Elt, cutlass::layout::RowMajor, 8, Elt,
-        cutlass::layout::RowMajor, 8, cutlass::epilogue::collective::EpilogueScheduleAuto, Fusion>::CollectiveOp;
-    using Mainloop = typename cutlass::gemm::collective::CollectiveBuilder<
-        cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, Elt, cutlass::layout::RowMajor, 8, Elt,
-        cutlass::layout::ColumnMajor, 8, float, TileShape, ClusterShape,
-        cutlass::gemm::collective::StageCountAutoCarveout<static_cast<int>(sizeof(typename Epilogue::SharedStorage))>,
-        cutlass::gemm::collective::KernelScheduleAuto>::CollectiveOp;
-    using Kernel = cutlass::gemm::kernel::GemmUniversal<Shape<int, int, int, int>, Mainloop, Epilogue, void>;
-    using Gemm = cutlass::gemm::device::GemmUniversalAdapter<Kernel>;
-
-    static int run(const void *A, int64_t lda, const void *W, const void *aux, int64_t ld_aux, void *D, int M, int N, int K, void *ws,
-                   size_t ws_bytes, cudaStream_t stream) {
-        typename Kernel::StrideA sa;
-        typename Kernel::StrideB sb;
-        typename Kernel::StrideC sc;
-        typename Kernel::StrideD sd;
-        get<0>(sa) = lda; get<2>(sa) = 0;
-        get<0>(sb) = (int64_t)K; get<2>(sb) = 0;
-        get<0>(sc) = (int64_t)N; get<2>(sc) = 0;
-        get<0>(sd) = (int64_t)N; get<2>(sd) = 0;
-        typename Gemm::Arguments args{cutlass::gemm::GemmUniversalMode::kGemm,
-                                      {M, N, K, 1},
-                                      {static_cast<const Elt *>(A), sa, static_cast<const Elt *>(W), sb},
-                                      {{}, nullptr, sc, static_cast<Elt *>(D), sd}};
-        args.epilogue.thread.alpha = 1.0f;
-        args.epilogue.thread.beta = 0.0f;
-        args.epilogue.thread.aux_ptr = static_cast<const Elt *>(aux);
-        get<0>(args.epilogue.thread.dAux) = ld_aux; get<2>(args.epilogue.thread.dAux) = 0;
-        Gemm gemm;
-        if (gemm.can_implement(args) != cutlass::Status::kSuccess) return -1;
-        if (Gemm::get_workspace_size(args) > ws_bytes) return -3;
-        if (gemm.initialize(args, ws, stream) != cutlass::Status::kSuccess) return -2;
-        return gemm.run(stream) == cutlass::Status::kSuccess ? 0 : -2;
-    }
-};
-
-int gemm_drelu(const void *A, int64_t lda, const void *W, const void *aux, int64_t ld_aux, void *D, int M, int N, int K, void *workspace,
-               size_t workspace_bytes, cudaStream_t stream) {
-    return GemmDRelu::run(A, lda, W, aux, ld_aux, D, M, N, K, workspace, workspace_bytes, stream);
-}
+// wide-tile variants live in policy_gemm_wide.cu
+int gemm_bias_act_256(const void *A, int64_t lda, const void *W, const float *bias, void *D, int M, int N, int K, int relu, void *workspace,
+                      size_t workspace_bytes, cudaStream_t stream);
+int gemm_bias_act_192(const void *A, int64_t lda, const void *W, const float *bias, void *D, int M, int N, int K, void *workspace,
+                      size_t workspace_bytes, cudaStream_t stream);
 
 size_t gemm_workspace_bytes() { return 1 << 20; }
 
 int gemm_bias_act(const void *A, int64_t lda, const void *W, const float *bias, void *D, int M, int N, int K, int relu,
                   void *workspace, size_t workspace_bytes, cudaStream_t stream) {
-    // wide outputs: 128 x 256 tiles read every A tile once per 256 output columns instead of once per 128
-    if (N % 256 == 0 && M >= 16384) {
-        if (relu) return GemmT<cutlass::epilogue::thread::ReLu, _256>::run(A, lda, W, bias, D, M, N, K, workspace, workspace_bytes, stream);
-        return GemmT<cutlass::epilogue::thread::Identity, _256>::run(A, lda, W, bias, D, M, N, K, workspace, workspace_bytes, stream);
-    }
-    if (N % 192 == 0 && M >= 16384 && !relu)      // the packed Q|K|V projection (N = 384): two 192-column tiles
-        return GemmT<cutlass::epilogue::thread::Identity, _192>::run(A, lda, W, bias, D, M, N, K, workspace, workspace_bytes, stream);
+    // wide outputs: 128 x 256 (or 2 x 192 for the packed Q|K|V projection) tiles read every A tile once per output block
+    // instead of once per 128 columns
+    if (N % 256 == 0 && M >= 16384) return gemm_bias_act_256(A, lda, W, bias, D, M, N, K, relu, workspace, workspace_bytes, stream);
+    if (N % 192 == 0 && M >= 16384 && !relu) return gemm_bias_act_192(A, lda, W, bias, D, M, N, K, workspace, workspace_bytes, stream);
     if (relu) return GemmT<cutlass::epilogue::thread::ReLu>::run(A, lda, W, bias, D, M, N, K, workspace, workspace_bytes, stream);
     return GemmT<cutlass::epilogue::thread::Identity>::run(A, lda, W, bias, D, M, N, K, workspace, workspace_bytes, stream);
 }
