@@ -54,31 +54,52 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ---------------------------------------------------------------------------------------------- forward extras
 
-// out = LayerNorm(x + y) * g + beta (one warp per row), keeping what the backward needs: the normalised row x^ (bf16)
-// and 1/sigma.  out16 (bf16, dense) and out32 (fp32, row stride out32_stride) are both optional.
-__global__ void add_ln_train_kernel(const bf16 *__restrict__ x, int64_t x_stride, const bf16 *__restrict__ y,
-                                    const float *__restrict__ g, const float *__restrict__ beta, int rows,
-                                    bf16 *__restrict__ out16, float *__restrict__ out32, int64_t out32_stride,
-                                    bf16 *__restrict__ xhat, float *__restrict__ rstd_out) {
-    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (r >= rows) return;
-    float a[4], b[4], v[4];
-    unpack4(*reinterpret_cast<const uint2 *>(x + (size_t)r * x_stride + lane * 4), a);
-    unpack4(*reinterpret_cast<const uint2 *>(y + (size_t)r * D + lane * 4), b);
+__device__ __forceinline__ void unpack8(uint4 v, float *o) {
+    unpack4(make_uint2(v.x, v.y), o);
+    unpack4(make_uint2(v.z, v.w), o + 4);
+}
+__device__ __forceinline__ uint4 pack8(const float *v) {
+    const uint2 a = pack4(v), b = pack4(v + 4);
+    return make_uint4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float half_warp_sum(float v) {           // over the 16 lanes that share a row
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// out = LayerNorm(x + y) * g + beta, keeping what the backward needs: the normalised row x^ (bf16) and 1/sigma.
+// Half a warp per row, 8 features (16 bytes) per lane.  out16 (bf16, dense) and out32 (fp32, row stride out32_stride)
+// are both optional.
+__global__ void __launch_bounds__(256) add_ln_train_kernel(const bf16 *__restrict__ x, int64_t x_stride, const bf16 *__restrict__ y,
+                                                           const float *__restrict__ g, const float *__restrict__ beta, int rows,
+                                                           bf16 *__restrict__ out16, float *__restrict__ out32, int64_t out32_stride,
+                                                           bf16 *__restrict__ xhat, float *__restrict__ rstd_out) {
+    const int hl = threadIdx.x & 15;
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const bool live = r < rows;
+    const int rc = live ? r : rows - 1;                               // (idle tail lanes still take part in the shuffles)
+    float a[8], b[8], v[8];
+    unpack8(*reinterpret_cast<const uint4 *>(x + (size_t)rc * x_stride + hl * 8), a);
+    unpack8(*reinterpret_cast<const uint4 *>(y + (size_t)rc * D + hl * 8), b);
+    float s = 0.0f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = a[i] + b[i];
-    const float mean = warp_sum(v[0] + v[1] + v[2] + v[3]) * (1.0f / D);
+    for (int i = 0; i < 8; ++i) { v[i] = a[i] + b[i]; s += v[i]; }
+    const float mean = half_warp_sum(s) * (1.0f / D);
     float q = 0.0f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { v[i] -= mean; q = fmaf(v[i], v[i], q); }
-    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
-    float o[4];
+    for (int i = 0; i < 8; ++i) { v[i] -= mean; q = fmaf(v[i], v[i], q); }
+    const float rstd = rsqrtf(half_warp_sum(q) * (1.0f / D) + 1e-5f);
+    if (!live) return;
+    float o[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { v[i] *= rstd; o[i] = v[i] * g[lane * 4 + i] + beta[lane * 4 + i]; }
-    *reinterpret_cast<uint2 *>(xhat + (size_t)r * D + lane * 4) = pack4(v);
-    if (lane == 0) rstd_out[r] = rstd;
-    if (out16) *reinterpret_cast<uint2 *>(out16 + (size_t)r * D + lane * 4) = pack4(o);
-    if (out32) *reinterpret_cast<float4 *>(out32 + (size_t)r * out32_stride + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    for (int i = 0; i < 8; ++i) { v[i] *= rstd; o[i] = v[i] * g[hl * 8 + i] + beta[hl * 8 + i]; }
+    *reinterpret_cast<uint4 *>(xhat + (size_t)r * D + hl * 8) = pack8(v);
+    if (hl == 0) rstd_out[r] = rstd;
+    if (out16) *reinterpret_cast<uint4 *>(out16 + (size_t)r * D + hl * 8) = pack8(o);
+    if (out32) {
+        float4 *dst = reinterpret_cast<float4 *>(out32 + (size_t)r * out32_stride + hl * 8);
+        dst[0] = make_float4(o[0], o[1], o[2], o[3]); dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
 }
 
 // fp32 row-major [N,K] -> bf16 copy and / or bf16 transposed copy [K,N]; one launch converts every GEMM weight
@@ -621,7 +642,7 @@ void wgrad(TCtx &c, const bf16 *dY, int64_t ld_dy, const bf16 *X, int64_t ld_x, 
 void add_ln(TCtx &c, const bf16 *x, int64_t xs, const bf16 *y, const float *g, const float *b, int rows, bf16 *out16, float *out32,
             int64_t out32_stride, bf16 *xhat, float *rstd) {
     if (c.rc) return;
-    add_ln_train_kernel<<<(rows * 32 + 255) / 256, 256, 0, c.s>>>(x, xs, y, g, b, rows, out16, out32, out32_stride, xhat, rstd);
+    add_ln_train_kernel<<<(rows * 16 + 255) / 256, 256, 0, c.s>>>(x, xs, y, g, b, rows, out16, out32, out32_stride, xhat, rstd);
 }
 // launch geometry of the "a warp walks consecutive rows" kernels: about 8 CTAs of 8 warps per SM
 inline void row_grid(const uavtrain *p, int rows, int &grid, int &rpw) {
