@@ -4,15 +4,15 @@
 // Same formulation as the rollout forward (policy_forward.cu): the last encoder layer of a block computes K/V for all
 // five tokens but everything else for the newest token only.  Activations are bf16 and are KEPT for the backward;
 // LayerNorm statistics, softmax, all reductions and every parameter gradient are fp32.
-//   activation-gradient GEMMs  dX = dY W        -> uavp::gemm_bias_act on pre-transposed bf16 weights (tcgen05)
-//   weight-gradient GEMMs      dW += dY^T X     -> uavp::wgrad (policy_wgrad.cu: split-K, accumulator resident in TMEM)
-//   ReLU backward                           -> fused into the epilogue of the activation-gradient GEMM (uavp::gemm_drelu)
-//   everything else (LayerNorm / attention / embedding backward, bias + LayerNorm parameter gradients) is
-//   hand-written below; bias gradients are accumulated by the kernel that produces the corresponding dY, or by the
-//   weight-gradient kernel (as dY^T 1 on the tensor cores) where dY comes out of the attention backward.
-// Two boundaries: uavtrain_forward / _backward stop at the trunks' last-token features ([n,2,128] out, their gradient
+//   activation-gradient GEMMs  dX = dY W     -> uavp::gemm_bias_act on pre-transposed bf16 weights (tcgen05)
+//   weight-gradient GEMMs      dW += dY^T X  -> uavp::wgrad (policy_wgrad.cu: split-K, TMA ring, accumulator resident in TMEM)
+//   ReLU backward of the FFN                 -> fused into the epilogue of the activation-gradient GEMM (uavp::gemm_drelu)
+//   everything else (LayerNorm / attention / embedding backward, LayerNorm parameter gradients, heads, PPO loss) is
+//   hand-written below; bias gradients come from the LayerNorm backward where a bias feeds a LayerNorm, and from the
+//   weight-gradient kernel (as dY^T 1 on the tensor cores) everywhere else.
+// Three entry levels: uavtrain_forward / _backward stop at the trunks' last-token features ([n,2,128] out, their gradient
 // in); uavtrain_forward_heads / _backward_heads also run the two MLP heads (logits [n,2] + value [n] out, their
-// gradients in).  The PPO loss itself stays in PyTorch.
+// gradients in); uavtrain_ppo_loss turns the heads' outputs into the PPO loss statistics and those gradients.
 #include "uavpolicy_b200.h"
 
 #include <cstdarg>
