@@ -311,7 +311,7 @@ extern "C" int uavpolicy_get_action(uavpolicy_t *p, const float *d_obs, int32_t 
         P_TRY(p, cudaGetLastError());
         return 0;
     }
-    embed_kernel<<<(R + kEmbTok - 1) / kEmbTok, D, 0, c.s>>>(d_obs, R, p->actor, p->critic, p->Ea, p->Ec, p->pad);
+    embed_kernel<<<(R + kEmbTok - 1) / kEmbTok, kEmbThreads, 0, c.s>>>(d_obs, R, p->actor, p->critic, p->Ea, p->Ec, p->pad);
     last_layer(c, p->actor.layer[0], p->Ea, B, p->Za);              // actor: 1 layer
     full_layer(c, p->critic.layer[0], p->Ec, B, p->X1);             // critic: 2 layers
     last_layer(c, p->critic.layer[1], p->X1, B, p->Zc);

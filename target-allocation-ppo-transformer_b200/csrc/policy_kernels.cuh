@@ -37,63 +37,109 @@ __global__ void f32_to_bf16_kernel(const float *__restrict__ src, __nv_bfloat16 
 // embedding of both nets: E = relu(obs W^T + b) + pos (transformer_net.py:24-30,57-59) and the key-padding mask
 // (rows that are all zero, newest row never: :52-54).  One CTA = 64 tokens; thread = (net, feature pair), so a warp
 // stores 128 contiguous bytes per token.
-constexpr int kEmbTok = 64;
-__global__ void __launch_bounds__(D) embed_kernel(const float *__restrict__ obs, int R, BlockW a, BlockW c,
-                                                  __nv_bfloat16 *__restrict__ Ea, __nv_bfloat16 *__restrict__ Ec,
-                                                  uint8_t *__restrict__ pad, __nv_bfloat16 *__restrict__ obs16 = nullptr,
-                                                  uint32_t *__restrict__ relu_mask = nullptr) {
+constexpr int kEmbTok = 60;                                   // whole windows per CTA: token i sits at position i % 5
+// packed fp32x2 arithmetic (FFMA2): both features of a thread advance with one instruction per observation column
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+constexpr int kEmbThreads = 64;                               // warp 0: actor, warp 1: critic; lane = 4 features
+__global__ void __launch_bounds__(kEmbThreads) embed_kernel(const float *__restrict__ obs, int R, BlockW a, BlockW c,
+                                                            __nv_bfloat16 *__restrict__ Ea, __nv_bfloat16 *__restrict__ Ec,
+                                                            uint8_t *__restrict__ pad, __nv_bfloat16 *__restrict__ obs16 = nullptr,
+                                                            uint32_t *__restrict__ relu_mask = nullptr) {
     // obs16 / relu_mask (training only): a bf16 copy of the observation rows zero-padded to 64 columns (the B operand of
     // the embedding's weight-gradient product) and the ReLU activity bits of both networks, [R][net][4 words]:
-    // word 2h + parity, bit l  <->  feature 64 h + 2 l + parity
-    __shared__ float s_obs[kEmbTok][F];
+    // word k, bit l  <->  feature 4 l + k
+    __shared__ __align__(16) float2 s_obs[kEmbTok][F];            // every value twice: the (x, x) operand of the packed FMA
     const int t0 = blockIdx.x * kEmbTok;
-    for (int i = threadIdx.x; i < kEmbTok * F; i += D) {
-        const int t = t0 + i / F;
-        s_obs[i / F][i % F] = t < R ? obs[(size_t)t * F + i % F] : 0.0f;
+    {   // the CTA's 60 x 14 floats are contiguous and 16-byte aligned: all loads of a thread go out before any is used
+        constexpr int kVec = kEmbTok * F / 4, kPer = (kVec + kEmbThreads - 1) / kEmbThreads;
+        const float4 *src = reinterpret_cast<const float4 *>(obs + (size_t)t0 * F);
+        const int nvec = min(kVec, (int)(((size_t)(R - t0) * F) / 4));        // R % 5 == 0 and 5 * 14 % 4 != 0: see tail below
+        float4 v[kPer];
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int i = threadIdx.x + k * kEmbThreads;
+            v[k] = i < nvec ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int i = threadIdx.x + k * kEmbThreads;
+            if (i < kVec) {
+                float2 *dst = &s_obs[0][0] + i * 4;
+                dst[0] = make_float2(v[k].x, v[k].x); dst[1] = make_float2(v[k].y, v[k].y);
+                dst[2] = make_float2(v[k].z, v[k].z); dst[3] = make_float2(v[k].w, v[k].w);
+            }
+        }
+        const int done = nvec * 4, total = min(kEmbTok, R - t0) * F;          // at most 3 trailing floats of the last CTA
+        for (int i = done + threadIdx.x; i < total; i += kEmbThreads) { const float x = obs[(size_t)t0 * F + i]; (&s_obs[0][0])[i] = make_float2(x, x); }
     }
     __syncthreads();
     if (threadIdx.x < kEmbTok && t0 + threadIdx.x < R) {
         float sum = 0.0f;
-        for (int j = 0; j < F; ++j) sum += fabsf(s_obs[threadIdx.x][j]);
+        for (int j = 0; j < F; ++j) sum += fabsf(s_obs[threadIdx.x][j].x);
         pad[t0 + threadIdx.x] = (sum == 0.0f && (t0 + threadIdx.x) % S != S - 1) ? 1 : 0;
     }
     if (obs16) {
-        for (int i = threadIdx.x; i < kEmbTok * 32; i += D) {
+        for (int i = threadIdx.x; i < kEmbTok * 32; i += kEmbThreads) {
             const int tok = i >> 5, c2 = (i & 31) * 2;
             if (t0 + tok < R)
                 *reinterpret_cast<__nv_bfloat162 *>(obs16 + (size_t)(t0 + tok) * 64 + c2) =
-                    __floats2bfloat162_rn(c2 < F ? s_obs[tok][c2] : 0.0f, c2 + 1 < F ? s_obs[tok][c2 + 1] : 0.0f);
+                    __floats2bfloat162_rn(c2 < F ? s_obs[tok][c2].x : 0.0f, c2 + 1 < F ? s_obs[tok][c2 + 1].x : 0.0f);
         }
     }
-    const bool critic = threadIdx.x >= D / 2;
-    const int d = (threadIdx.x % (D / 2)) * 2;                    // features d, d+1
+    const bool critic = threadIdx.x >= 32;
+    const int d = (threadIdx.x & 31) * 4;                          // features d .. d+3
     const BlockW &w = critic ? c : a;
     __nv_bfloat16 *E = critic ? Ec : Ea;
-    float w0[F], w1[F];
+    uint64_t wa[F], wb[F];                                         // (w[d], w[d+1]) and (w[d+2], w[d+3]) per observation column
 #pragma unroll
-    for (int j = 0; j < F; ++j) { w0[j] = w.emb_w[d * F + j]; w1[j] = w.emb_w[(d + 1) * F + j]; }
-    const float b0 = w.emb_b[d], b1 = w.emb_b[d + 1];
-    float p0[S], p1[S];
+    for (int j = 0; j < F; ++j) {
+        wa[j] = pack_f32x2(w.emb_w[d * F + j], w.emb_w[(d + 1) * F + j]);
+        wb[j] = pack_f32x2(w.emb_w[(d + 2) * F + j], w.emb_w[(d + 3) * F + j]);
+    }
+    const uint64_t ba = pack_f32x2(w.emb_b[d], w.emb_b[d + 1]), bb = pack_f32x2(w.emb_b[d + 2], w.emb_b[d + 3]);
+    float pos[S][4];
 #pragma unroll
-    for (int p = 0; p < S; ++p) { p0[p] = w.pos[p * D + d]; p1[p] = w.pos[p * D + d + 1]; }
-    for (int i = 0; i < kEmbTok; ++i) {
-        const int t = t0 + i;
-        if (t >= R) break;
-        float x0 = b0, x1 = b1;
+    for (int p = 0; p < S; ++p)
 #pragma unroll
-        for (int j = 0; j < F; ++j) { x0 = fmaf(w0[j], s_obs[i][j], x0); x1 = fmaf(w1[j], s_obs[i][j], x1); }
-        if (relu_mask) {
-            const unsigned m0 = __ballot_sync(0xffffffffu, x0 > 0.0f), m1 = __ballot_sync(0xffffffffu, x1 > 0.0f);
-            if ((threadIdx.x & 31) == 0) {
-                uint32_t *dst = relu_mask + ((size_t)t * 2 + (critic ? 1 : 0)) * 4 + ((threadIdx.x >> 5) & 1) * 2;
-                dst[0] = m0; dst[1] = m1;
+        for (int k = 0; k < 4; ++k) pos[p][k] = w.pos[p * D + d + k];
+    uint32_t *const mask_dst = relu_mask ? relu_mask + (critic ? 4 : 0) : nullptr;
+    for (int win = 0; win < kEmbTok / S; ++win) {                 // R is a multiple of 5: windows are never split
+        if (t0 + win * S >= R) break;
+#pragma unroll
+        for (int p = 0; p < S; ++p) {                              // p = position of the token in its window (static)
+            const int i = win * S + p, t = t0 + i;
+            uint64_t xa = ba, xb = bb;
+#pragma unroll
+            for (int j = 0; j < F; ++j) {
+                const uint64_t oo = *reinterpret_cast<const uint64_t *>(&s_obs[i][j]);     // (o_j, o_j)
+                xa = fma_f32x2(wa[j], oo, xa);
+                xb = fma_f32x2(wb[j], oo, xb);
             }
-        }
-        const int p = t % S;
-        float q0 = p0[0], q1 = p1[0];
+            float x[4];
+            unpack_f32x2(xa, x[0], x[1]);
+            unpack_f32x2(xb, x[2], x[3]);
+            if (mask_dst) {
+                unsigned m[4];
 #pragma unroll
-        for (int k = 1; k < S; ++k) if (p == k) { q0 = p0[k]; q1 = p1[k]; }
-        *reinterpret_cast<__nv_bfloat162 *>(E + (size_t)t * D + d) = __floats2bfloat162_rn(fmaxf(x0, 0.0f) + q0, fmaxf(x1, 0.0f) + q1);
+                for (int k = 0; k < 4; ++k) m[k] = __ballot_sync(0xffffffffu, x[k] > 0.0f);
+                if ((threadIdx.x & 31) == 0) *reinterpret_cast<uint4 *>(mask_dst + (size_t)t * 8) = make_uint4(m[0], m[1], m[2], m[3]);
+            }
+            const __nv_bfloat162 e0 = __floats2bfloat162_rn(fmaxf(x[0], 0.0f) + pos[p][0], fmaxf(x[1], 0.0f) + pos[p][1]);
+            const __nv_bfloat162 e1 = __floats2bfloat162_rn(fmaxf(x[2], 0.0f) + pos[p][2], fmaxf(x[3], 0.0f) + pos[p][3]);
+            uint2 ev;
+            ev.x = *reinterpret_cast<const uint32_t *>(&e0); ev.y = *reinterpret_cast<const uint32_t *>(&e1);
+            *reinterpret_cast<uint2 *>(E + (size_t)t * D + d) = ev;
+        }
     }
 }
 

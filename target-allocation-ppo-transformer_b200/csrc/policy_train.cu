@@ -331,7 +331,6 @@ __global__ void __launch_bounds__(256) embed_mask_kernel(const bf16 *__restrict_
     __syncthreads();
     const int gw = blockIdx.x * 8 + warp;
     const int b0 = gw * samples_per_warp, b1 = min(n, b0 + samples_per_warp);
-    const int wsel = (lane >> 4) * 2, l0 = 2 * (lane & 15);      // word pair and bit of feature 4 * lane
     float dpos[S][4];
 #pragma unroll
     for (int s = 0; s < S; ++s)
@@ -349,12 +348,12 @@ __global__ void __launch_bounds__(256) embed_mask_kernel(const bf16 *__restrict_
 #pragma unroll
                 for (int f = 0; f < 4; ++f) g[f] += t[f];
             }
-            const uint2 m = *reinterpret_cast<const uint2 *>(mask + row * 8 + wsel);       // (even-feature word, odd-feature word)
+            const uint4 m = *reinterpret_cast<const uint4 *>(mask + row * 8);             // word f, bit lane <-> feature 4 lane + f
+            const unsigned mw[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
             for (int f = 0; f < 4; ++f) {
                 dpos[s][f] += g[f];
-                const unsigned bit = (((f & 1) ? m.y : m.x) >> (l0 + (f >> 1))) & 1u;
-                g[f] = bit ? g[f] : 0.0f;
+                g[f] = ((mw[f] >> lane) & 1u) ? g[f] : 0.0f;
             }
             *reinterpret_cast<uint2 *>(dpre + off) = pack4(g);
         }
@@ -838,7 +837,7 @@ int forward_impl(uavtrain *p, const float *w, const float *d_obs, int n, float *
     for (int j = 0; j < p->n_jobs; ++j) p->jobs.job[j].src = w + p->job_src_off[j];
     prep_weights_kernel<<<dim3(24, p->n_jobs), 256, 0, c.s>>>(p->jobs);
     const int R = n * S;
-    embed_kernel<<<(R + kEmbTok - 1) / kEmbTok, D, 0, c.s>>>(d_obs, R, p->actor, p->critic, p->Ea, p->Ec, p->pad, p->obs16, p->relu_mask);
+    embed_kernel<<<(R + kEmbTok - 1) / kEmbTok, kEmbThreads, 0, c.s>>>(d_obs, R, p->actor, p->critic, p->Ea, p->Ec, p->pad, p->obs16, p->relu_mask);
     last_layer_fwd(c, p->actor.layer[0], p->Ea, n, p->la, d_feat, 2 * D, heads ? p->ahead.Z : nullptr);
     full_layer_fwd(c, p->critic.layer[0], p->Ec, n, p->fc);
     last_layer_fwd(c, p->critic.layer[1], p->fc.Xout, n, p->lc, d_feat ? d_feat + D : nullptr, 2 * D, heads ? p->chead.Z : nullptr);
