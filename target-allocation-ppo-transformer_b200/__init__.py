@@ -25,8 +25,9 @@ def __getattr__(name):  # torch / CUDA are only touched when the env classes are
         from .networks.fused_train import FusedTrunks
         return FusedTrunks
     if name == "train":
-        from .train import train
-        return train
+        from .train import train as train_fn
+        globals()["train"] = train_fn        # (importing the submodule bound the MODULE to this name: rebind the function)
+        return train_fn
     if name == "load_library":
         from ._capi import load
         return load

@@ -105,3 +105,9 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "uavenv_oracle" not in src, f
                 assert "/root/reference" not in src, f
+
+
+def test_lazy_exports_resolve_to_the_same_objects_every_time():
+    for name in ("train", "PPOAgent", "FusedTrunks", "compute_gae", "TransformerActorCritic"):
+        first, second = getattr(ub, name), getattr(ub, name)
+        assert callable(first) and first is second, name
