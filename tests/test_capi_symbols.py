@@ -111,3 +111,11 @@ def test_lazy_exports_resolve_to_the_same_objects_every_time():
     for name in ("train", "PPOAgent", "FusedTrunks", "compute_gae", "TransformerActorCritic"):
         first, second = getattr(ub, name), getattr(ub, name)
         assert callable(first) and first is second, name
+
+
+def test_training_path_refuses_to_run_without_cuda():
+    """No CPU fallback anywhere on the product path: the update's library handle cannot be created on a CPU device."""
+    with pytest.raises(RuntimeError):
+        ub.FusedTrunks(8, "cpu")
+    with pytest.raises(RuntimeError):
+        ub.FusedPolicyForward(8, "cpu")
