@@ -28,6 +28,9 @@ def __getattr__(name):  # torch / CUDA are only touched when the env classes are
         from .train import train as train_fn
         globals()["train"] = train_fn        # (importing the submodule bound the MODULE to this name: rebind the function)
         return train_fn
+    if name in ("analyze_environment_difficulty", "record_decisions"):
+        from . import diagnostics
+        return getattr(diagnostics, name)
     if name == "load_library":
         from ._capi import load
         return load
