@@ -108,7 +108,8 @@ def test_product_never_imports_the_oracle():
 
 
 def test_lazy_exports_resolve_to_the_same_objects_every_time():
-    for name in ("train", "PPOAgent", "FusedTrunks", "compute_gae", "TransformerActorCritic"):
+    for name in ("train", "PPOAgent", "FusedTrunks", "compute_gae", "TransformerActorCritic", "analyze_environment_difficulty",
+                 "record_decisions"):
         first, second = getattr(ub, name), getattr(ub, name)
         assert callable(first) and first is second, name
 
