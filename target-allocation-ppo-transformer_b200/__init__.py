@@ -24,10 +24,9 @@ def __getattr__(name):  # torch / CUDA are only touched when the env classes are
     if name == "FusedTrunks":
         from .networks.fused_train import FusedTrunks
         return FusedTrunks
-    if name == "train":
-        from .train import train as train_fn
-        globals()["train"] = train_fn        # (importing the submodule bound the MODULE to this name: rebind the function)
-        return train_fn
+    if name == "train":                      # the submodule itself is callable: ub.train(...) == ub.train.train(...)
+        import importlib
+        return importlib.import_module(__name__ + ".train")
     if name in ("analyze_environment_difficulty", "record_decisions"):
         from . import diagnostics
         return getattr(diagnostics, name)
