@@ -99,81 +99,89 @@ def make_config(ub, w, reset_episodes=200):
     return ub.Config(NUM_UAVS=w["N"], NUM_TARGETS=w["M"], RESET_EPISODES=reset_episodes)
 
 
-def run_reference(args, w, rank, world):
-    """The reference's CPU algorithm (oracle port: the reference itself is Python and cannot travel to the GPU
-    box) on all host threads.  A step = one reference-algorithm step of a bounded sample of the workload's envs."""
-    if rank != 0:
-        return
+# The reference's own Python loop (envs/uav_env.py:295 under main_train.py:79's reset schedule, random actions), measured in
+# the BUILD container (8 vCPU Xeon, py3.12, numpy 2.3) by oracle/gen_golden.py while it recorded the golden trajectories.
+# The Python tree does not exist on the GPU box, so this is a recorded constant, not a live measurement.
+PY_REFERENCE_STEPS_PER_SEC_PER_CORE = {"c2": 86.0, "c3": 43.0, "c5": 9.8, "c4": 86.0}
+PY_REFERENCE_PROVENANCE = ("unmodified reference UAVEnv.step (envs/uav_env.py:295), 1 core, build container; recorded by "
+                           "oracle/gen_golden.py; SURVEY.md section 6 probe: 88-98 / 45 / 13.5")
+CPU_BURN_IN_STEPS = 300   # same burn-in as the GPU arm: the envs' decision pointers and episode phases are de-synchronised
+
+
+def timed_oracle(w, sample, min_seconds, min_steps=0):
+    """Steady-state throughput of the reference ALGORITHM (oracle/uavenv_oracle.c, the C port pinned to the Python
+    reference) on all host threads: CPU_BURN_IN_STEPS untimed steps, then whole steps until min_seconds AND min_steps
+    are reached.  Used by BOTH CPU arms (cpu_baseline and --impl reference) so that their numbers are comparable."""
     from oracle import oracle as orc
     ocfg = orc.make_cfg(NUM_UAVS=w["N"], NUM_TARGETS=w["M"])
     threads = orc.max_threads()
-    sample = max(threads * 8, min(w["envs_per_gpu"], 2048 if w["N"] <= 64 else 256))
+    sample = max(threads * 8, sample)
     batch = orc.OracleBatch(ocfg, sample, seed=SCENE_SEED, reset_episodes=200, threads=threads)
-    for s in range(args.warmup):
+    for s in range(CPU_BURN_IN_STEPS):
         batch.step_random(s, ACTION_SEED)
-    t0 = time.perf_counter()
-    for s in range(args.warmup, args.warmup + args.steps):
+    t0, s = time.perf_counter(), CPU_BURN_IN_STEPS
+    while True:
         batch.step_random(s, ACTION_SEED)
-    dt = time.perf_counter() - t0
-    value = sample * args.steps / dt
-    desc = "%d of the workload's envs, %d steps each, reference algorithm (C port, OpenMP)" % (sample, args.steps)
+        s += 1
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds and s - CPU_BURN_IN_STEPS >= min_steps:
+            break
+    n = s - CPU_BURN_IN_STEPS
+    batch.close()
+    return {"value": sample * n / dt, "unit": "env-steps/s", "cores": threads, "kind": "port",
+            "sample": "%d envs x %d steps of the same workload after %d burn-in steps, reference algorithm (C port of "
+                      "envs/uav_env.py pinned to the Python reference, OpenMP over envs), %.1f s" % (
+                          sample, n, CPU_BURN_IN_STEPS, dt),
+            "timed_steps": n, "seconds": dt, "sample_envs": sample}
+
+
+def cpu_sample_envs(w):
+    return 1024 if w["N"] <= 64 else 128
+
+
+def run_reference(args, w, rank, world):
+    """The reference's CPU algorithm (oracle port: the reference itself is Python and cannot travel to the GPU
+    box) on all host threads, in the SAME steady-state protocol as cpu_baseline (burn-in, then >= 3 s of whole steps of
+    a bounded sample of the workload's envs, however small --steps is)."""
+    if rank != 0:
+        return
+    r = timed_oracle(w, cpu_sample_envs(w), min_seconds=3.0, min_steps=args.steps)
+    value = r["value"]
     print(json.dumps({
         "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / r["timed_steps"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["name"], "num_uavs": w["N"], "num_targets": w["M"], "sample_envs": sample,
-                   "actions": "Bernoulli(0.5) counter RNG", "reset_schedule": "full reset every 200 episodes"},
-        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": desc},
+        "config": {"workload": w["name"], "num_uavs": w["N"], "num_targets": w["M"], "sample_envs": r["sample_envs"],
+                   "timed_steps_actual": r["timed_steps"], "burn_in_steps": CPU_BURN_IN_STEPS,
+                   "actions": "Bernoulli(0.5) counter RNG", "reset_schedule": "full reset every 200 episodes",
+                   "python_reference_steps_per_sec_per_core": PY_REFERENCE_STEPS_PER_SEC_PER_CORE.get(args.workload),
+                   "python_reference_provenance": PY_REFERENCE_PROVENANCE},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
 
 
 def cpu_baseline(w, seconds=12.0):
-    from oracle import oracle as orc
-    ocfg = orc.make_cfg(NUM_UAVS=w["N"], NUM_TARGETS=w["M"])
-    threads = orc.max_threads()
-    sample = max(threads * 8, 1024 if w["N"] <= 64 else 128)
-    batch = orc.OracleBatch(ocfg, sample, seed=SCENE_SEED, reset_episodes=200, threads=threads)
-    for s in range(3):
-        batch.step_random(s, ACTION_SEED)
-    t0, s = time.perf_counter(), 3
-    while time.perf_counter() - t0 < seconds:
-        batch.step_random(s, ACTION_SEED)
-        s += 1
-    dt = time.perf_counter() - t0
-    n = s - 3
-    return {"value": sample * n / dt, "unit": "env-steps/s", "cores": threads, "kind": "port",
-            "sample": "%d envs x %d steps of the same workload, reference algorithm (C port of envs/uav_env.py, "
-                      "OpenMP over envs), %.1f s" % (sample, n, dt)}
+    r = timed_oracle(w, cpu_sample_envs(w), min_seconds=seconds)
+    return {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
 
-def run_ppo(args):
+def measure_ppo(rank, local_rank, world, dev, B, T, K, W, with_clocks=True):
     """BASELINE.json configs[3]: end-to-end PPO samples/s = transitions collected AND trained on (K_EPOCHS = 5) per
-    second.  One "step" = one iteration: `horizon` rollout steps (tcgen05 policy forward + fused env step) followed
-    by the PPO update (GAE kernel; per minibatch the hand-written bf16 forward + backward of csrc/policy_train.cu,
-    the PPO loss in PyTorch, one flat NCCL gradient all-reduce at N > 1, clip, Adam - replayed as one CUDA graph).
-    Timed with CUDA events around whole iterations; max over ranks.  UAVENV_UPDATE_PRECISION=tf32|fp32|bf16 runs the
-    update through PyTorch autograd on the mirror network instead (A/B)."""
+    second.  One iteration = `T` rollout steps (tcgen05 policy forward + fused env step) followed by the PPO update (GAE
+    kernel; per minibatch the hand-written bf16 forward + loss + backward, one flat NCCL gradient all-reduce at N > 1,
+    fused clip + Adam - replayed as one CUDA graph).  K iterations are timed with ONE CUDA-event bracket, max over ranks.
+    The gradient all-reduce (the only collective) is also timed alone, eagerly, with events around 50 calls on the
+    same 1.68 MB flat buffer.  Returns the record (rank 0) or None."""
     import torch
     import uavenv_b200 as ub
     from target_allocation_ppo_transformer_b200 import parallel
-    if args.impl == "reference":
-        if int(os.environ.get("RANK", 0)) == 0:
-            print(json.dumps({"impl": "reference", "unavailable": "the reference's PPO loop is Python/PyTorch code that "
-                              "does not exist on the GPU box; in the build container it runs at ~59 samples/s (SURVEY.md 6)"}))
-        return
-    rank, local_rank, world = parallel.init("nccl")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    B, T = args.envs_per_gpu or PPO["envs_per_gpu"], PPO["horizon"]
-    K, W = args.steps if args.steps != 200 else 5, min(args.warmup, 3)
     env = ub.UAVEnvBatched(B, device=dev, seed=SCENE_SEED, env_id_base=rank * B)
     agent = ub.PPOAgent(B, T, dev, fused_rollout=True, env_id_base=rank * B, seed=SCENE_SEED,
                         update_precision=os.environ.get("UAVENV_UPDATE_PRECISION", "fused"),
                         graph_update=os.environ.get("UAVENV_GRAPH_UPDATE", "1") != "0")
     obs = env.reset()
-
     split = [torch.cuda.Event(enable_timing=True) for _ in range(3)]   # rollout | update boundaries of the last iteration
 
     def iteration():
@@ -191,7 +199,7 @@ def run_ppo(args):
     for _ in range(W):
         iteration()
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and with_clocks:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     parallel.barrier(); torch.cuda.synchronize(dev)
@@ -201,27 +209,57 @@ def run_ppo(args):
     e1.record()
     torch.cuda.synchronize(dev); parallel.barrier()
     ms = parallel.reduce_scalar(e0.elapsed_time(e1), "max", dev)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if (rank == 0 and with_clocks) else None
+    roll_ms = parallel.reduce_scalar(split[0].elapsed_time(split[1]), "max", dev)
+    upd_ms = parallel.reduce_scalar(split[1].elapsed_time(split[2]), "max", dev)
+    ar_us = parallel.reduce_scalar(agent.time_gradient_allreduce(50), "max", dev)
+    n_mb = 5 * (B * T // agent.minibatch_size)
+    launches_mb = agent.launches_per_minibatch()
+    rec = None
     if rank == 0:
         samples = B * T * world * K
-        print(json.dumps({
+        rec = {
             "metric": "ppo_samples_per_sec", "value": samples / (ms * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16 rollout forward (tcgen05) / %s update%s / f64 env" % (
                 "bf16 tcgen05 (fp32 accumulation, fp32 gradients)" if agent.update_precision == "fused" else agent.update_precision,
                 ", CUDA-graph replay" if agent.graph_update else ""), "data": "synthetic",
             "config": {"workload": PPO["name"], "envs_per_gpu": B, "horizon": T, "k_epochs": 5,
-                       "minibatch": agent.minibatch_size, "last_stats": stats,
-                       "last_iteration_ms": {"rollout": split[0].elapsed_time(split[1]), "update": split[1].elapsed_time(split[2])},
+                       "minibatch": agent.minibatch_size, "minibatch_steps_per_iteration": n_mb, "last_stats": stats,
+                       "last_iteration_ms": {"rollout": roll_ms, "update": upd_ms},
                        "parallelism": "env-sharded x%d, flat fp32 gradient all-reduce (NCCL) per minibatch" % world},
+            "comm": {"collective": "ncclAllReduce(sum) of the flat fp32 gradient, %d B, once per minibatch step" % (
+                         4 * agent.num_params),
+                     "nranks": world, "allreduce_us_per_minibatch": ar_us if world > 1 else 0.0,
+                     "allreduce_share_of_iteration": (ar_us * 1e-3 * n_mb) / (ms / K) if world > 1 else 0.0,
+                     "how": "CUDA events around 50 back-to-back all_reduce calls on the same buffer, max over ranks"},
             "e2e": {"value": samples / (ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 24,
                     "note": "the whole loop is device-resident; only the three mean losses leave the GPU per update"},
-            # own kernels per iteration: T x (fused policy blocks + heads + env step) + 2 GAE + per minibatch step 79
-            # (32 tcgen05 GEMMs, 16 weight-gradient, 29 LayerNorm / attention / ReLU / embedding / head kernels, 2 loss)
-            "gpu_launches": K * (T * 3 + 2 + (79 if agent.update_precision == "fused" else 4) * 5 * (B * T // agent.minibatch_size)),
-            "clocks": clocks}))
+            # own kernels per iteration: T x (fused policy blocks + heads + env step) + 2 GAE + the minibatch steps
+            "gpu_launches": K * (T * 3 + 2 + launches_mb * n_mb),
+            "clocks": clocks}
     agent.close()       # drop the captured graph before the communicator it references goes away
     env.close()
+    return rec
+
+
+def run_ppo(args):
+    """--workload c4: the PPO record as the main JSON line."""
+    import torch
+    from target_allocation_ppo_transformer_b200 import parallel
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", 0)) == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "the reference's PPO loop is Python/PyTorch code that "
+                              "does not exist on the GPU box; in the build container it runs at ~59 samples/s (SURVEY.md 6)"}))
+        return
+    rank, local_rank, world = parallel.init("nccl")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B, T = args.envs_per_gpu or PPO["envs_per_gpu"], PPO["horizon"]
+    K, W = args.steps if args.steps != 200 else 5, min(args.warmup, 3)
+    rec = measure_ppo(rank, local_rank, world, dev, B, T, K, W)
+    if rank == 0:
+        print(json.dumps(rec))
     if world > 1:
         torch.distributed.destroy_process_group()
 
@@ -236,6 +274,8 @@ def main():
                     help="c3 (default) / c2 / c5: env-steps/s of the fused step; c4: end-to-end PPO samples/s")
     ap.add_argument("--envs-per-gpu", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ppo", action="store_true", help="skip the configs[3] PPO sub-record of the default line")
+    ap.add_argument("--ppo-iterations", type=int, default=3, help="timed PPO iterations of the `ppo` sub-record")
     ap.add_argument("--no-flush", action="store_true", help="diagnostic only: keep L2 warm between steps")
     ap.add_argument("--reset-episodes", type=int, default=200, help="diagnostic only: cfg.RESET_EPISODES (200)")
     ap.add_argument("--flush-mode", default="write+read", choices=["write+read", "write", "read", "sleep"],
@@ -339,6 +379,9 @@ def main():
     # --- end to end through the host-buffer entry point ----------------------------------------------------
     ms_e2e = timed(lambda i: env.step_host(pool_host_i8[i % POOL]), W, K)
     ms_e2e_i64 = timed(lambda i: env.step_host(pool_host[i % POOL]), W, K)
+    # ... and with step()'s full 4-tuple crossing the boundary: the [B,5,14] window is copied to pinned host memory too
+    obs_host = torch.empty(B, 5, 14, dtype=torch.float32).pin_memory()
+    ms_e2e_obs = timed(lambda i: env.step_host(pool_host_i8[i % POOL], obs_out=obs_host), W, K)
     clocks = sampler.stop() if rank == 0 else None
     drift = env.recompute_objective()
     drift = parallel.reduce_scalar(drift, "max", dev)
@@ -389,13 +432,32 @@ def main():
                     "api": "UAVEnvBatched.step_host -> uavenv_step_host_i8 (pinned host int8 actions in; f32 reward + u8 "
                            "done out, in place over PCIe; observation window stays in HBM for the policy)",
                     "int64_actions": {"value": total_envs * K / (ms_e2e_i64 * 1e-3), "ms_per_step": ms_e2e_i64 / K,
-                                      "h2d_bytes_per_step": B * 8}},
+                                      "h2d_bytes_per_step": B * 8},
+                    # the reference's step() returns (obs, reward, done, info) (envs/uav_env.py:435): the same call with
+                    # the observation window ALSO copied to pinned host memory inside the bracket
+                    "with_obs": {"value": total_envs * K / (ms_e2e_obs * 1e-3), "ms_per_step": ms_e2e_obs / K,
+                                 "h2d_bytes_per_step": B * 1, "d2h_bytes_per_step": B * (5 + 280),
+                                 "pcie_d2h_gbs": B * 285 / (ms_e2e_obs / K * 1e-3) / 1e9,
+                                 "api": "UAVEnvBatched.step_host(actions, obs_out=pinned [B,5,14])"}},
             "gpu_launches": K, "clocks": clocks,
         }
+        out["config"]["python_reference_steps_per_sec_per_core"] = PY_REFERENCE_STEPS_PER_SEC_PER_CORE.get(args.workload)
+        out["config"]["python_reference_provenance"] = PY_REFERENCE_PROVENANCE
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(w)
-        print(json.dumps(out))
     env.close()
+    del env, pool, flush, sweep
+    torch.cuda.empty_cache()
+    if not args.no_ppo:
+        # second half of the BASELINE metric ("end-to-end PPO samples/sec", configs[3]) on the same N GPUs: rollout +
+        # update with the NCCL gradient all-reduce, so the driver's 1/2/4/8 runs carry its scaling curve too
+        ppo = measure_ppo(rank, local_rank, world, dev, PPO["envs_per_gpu"], PPO["horizon"], max(1, args.ppo_iterations), 2,
+                          with_clocks=False)
+        if rank == 0:
+            out["ppo"] = {k: ppo[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "dtype",
+                                              "config", "comm", "gpu_launches")}
+    if rank == 0:
+        print(json.dumps(out))
     if world > 1:
         torch.distributed.destroy_process_group()
 

@@ -192,6 +192,24 @@ int ppo_attn5_backward(const float *d_q, int64_t q_stride, const float *d_k, con
                        const uint8_t *d_pad, int64_t n, int32_t num_queries, const float *d_grad_out, float *d_grad_q,
                        float *d_grad_k, float *d_grad_v, int32_t device, void *stream);
 
+/* ---- PPO update: the post-backward chain of one minibatch step on FLAT fp32 buffers -------------------------------
+ * Replaces torch.nn.utils.clip_grad_norm_(policy.parameters(), GRAD_NORM_CLIP) + optimizer.step() of
+ * agents/ppo.py:160-162 (Adam with the four parameter groups of agents/ppo.py:17-22) - and the division by the
+ * world size that follows the NCCL gradient sum - with two launches:
+ *   g = d_grad * grad_scale;  g *= min(1, max_norm / (||g||_2 + 1e-6));  Adam(beta1, beta2, eps, lr of the segment).
+ * d_params / d_grad / d_exp_avg / d_exp_avg_sq: [n] fp32, same element order (d_grad is left holding the clipped g).
+ * seg_end / seg_lr (HOST arrays, num_segments <= PPO_OPTIM_MAX_GROUPS): exclusive end offsets (ascending, last == n)
+ * and learning rates of the contiguous parameter ranges.  d_step: device int64 Adam step counter (incremented by the
+ * call, so CUDA-graph replays advance it).  d_partials: device double[ppo_optim_partials()] scratch.  d_norm_out
+ * (optional): the pre-clip gradient norm.  The norm is reduced in a fixed order: bit-identical on every rank.
+ * max_norm <= 0 disables clipping. */
+#define PPO_OPTIM_MAX_GROUPS 8
+int ppo_clip_adam_step(float *d_params, float *d_grad, float *d_exp_avg, float *d_exp_avg_sq, int64_t n,
+                       const int64_t *seg_end, const float *seg_lr, int32_t num_segments, float grad_scale,
+                       float max_norm, float beta1, float beta2, float eps, int64_t *d_step, double *d_partials,
+                       float *d_norm_out, int32_t device, void *stream);
+int ppo_optim_partials(void);
+
 #ifdef __cplusplus
 }
 #endif

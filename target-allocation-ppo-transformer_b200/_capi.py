@@ -77,11 +77,10 @@ def load():
     path = _build.LIB_PATH
     if not _build.up_to_date():
         try:
-            _build.build()
-        except Exception as exc:  # no nvcc on this host, or a compile error
-            if not os.path.isfile(path):
-                raise ImportError("libuavenv_b200.so is missing and could not be built (%s); "
-                                  "the environment has no CPU fallback" % exc) from exc
+            _build.build(lib=path)
+        except Exception as exc:  # no nvcc on this host, or a compile error: never load a binary older than its sources
+            raise ImportError("libuavenv_b200.so is %s and could not be (re)built (%s); the environment has no CPU "
+                              "fallback" % ("stale" if os.path.isfile(path) else "missing", exc)) from exc
     L = C.CDLL(path)
     vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
     L.uavenv_default_cfg.argtypes = [C.POINTER(UavenvCfg)]
@@ -113,6 +112,10 @@ def load():
     L.ppo_normalize_advantages.argtypes = [vp, i64, vp, i32, vp]
     L.ppo_attn5_forward.argtypes = [vp, i64, vp, vp, i64, vp, i64, i32, vp, i32, vp]
     L.ppo_attn5_backward.argtypes = [vp, i64, vp, vp, i64, vp, i64, i32, vp, vp, vp, vp, i32, vp]
+    L.ppo_clip_adam_step.argtypes = [vp, vp, vp, vp, i64, C.POINTER(i64), C.POINTER(C.c_float), i32, C.c_float, C.c_float,
+                                     C.c_float, C.c_float, C.c_float, vp, vp, vp, i32, vp]
+    L.ppo_clip_adam_step.restype = C.c_int
+    L.ppo_optim_partials.restype = C.c_int
     L.ppo_attn5_forward.restype = C.c_int
     L.ppo_attn5_backward.restype = C.c_int
     for name in ("uavenv_create", "uavenv_destroy", "uavenv_reset", "uavenv_step", "uavenv_step_host",
@@ -146,8 +149,8 @@ def load_policy():
         try:
             _build.build(lib=path)
         except Exception as exc:
-            if not os.path.isfile(path):
-                raise ImportError("libuavpolicy_b200.so is missing and could not be built (%s)" % exc) from exc
+            raise ImportError("libuavpolicy_b200.so is %s and could not be (re)built (%s)" % (
+                "stale" if os.path.isfile(path) else "missing", exc)) from exc
     L = C.CDLL(path)
     vp, i32, u64 = C.c_void_p, C.c_int32, C.c_uint64
     L.uavpolicy_create.argtypes = [i32, i32, C.POINTER(vp)]

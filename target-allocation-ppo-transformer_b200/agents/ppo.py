@@ -80,7 +80,7 @@ class PPOAgent:
     """
 
     def __init__(self, num_envs, horizon, device, cfg=None, group=None, minibatch_size=None, seed=0,
-                 fused_rollout=False, env_id_base=0, update_precision="tf32", graph_update=False):
+                 fused_rollout=False, env_id_base=0, update_precision="tf32", graph_update=False, optimizer="fused"):
         from ..configs.config import cfg as global_cfg
         from ..networks.transformer_net import TransformerActorCritic
         self.cfg = cfg or global_cfg
@@ -89,26 +89,55 @@ class PPOAgent:
         self.group = group
         self.world = torch.distributed.get_world_size(group) if (
             torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
-        torch.manual_seed(seed)                       # identical initial weights on every rank
-        self.policy = TransformerActorCritic(self.cfg).to(self.device)
-        self.policy_old = TransformerActorCritic(self.cfg).to(self.device)
+        # identical initial weights on every rank, without touching the caller's global RNG stream
+        devs = [self.device] if self.device.type == "cuda" else []
+        with torch.random.fork_rng(devices=devs):
+            torch.manual_seed(seed)
+            self.policy = TransformerActorCritic(self.cfg).to(self.device)
+            self.policy_old = TransformerActorCritic(self.cfg).to(self.device)
         self.policy_old.load_state_dict(self.policy.state_dict())
         c = self.cfg
         # graph_update: after three eager minibatch steps the whole step is captured once and replayed as one CUDA
-        # graph launch (needs Adam's step counters on the device: capturable=True)
+        # graph launch (Adam's step counter lives on the device)
         self.graph_update = bool(graph_update) and self.device.type == "cuda"
-        self.optimizer = torch.optim.Adam([                                       # ppo.py:17-22
-            {"params": self.policy.actor_head.parameters(), "lr": c.LR_ACTOR},
-            {"params": self.policy.actor_net.parameters(), "lr": c.LR_ACTOR},
-            {"params": self.policy.critic_head.parameters(), "lr": c.LR_CRITIC},
-            {"params": self.policy.critic_net.parameters(), "lr": c.LR_CRITIC},
-        ], capturable=self.graph_update)
+        if optimizer not in ("fused", "torch"):
+            raise ValueError("optimizer must be 'fused' (csrc/ppo_optim.cu) or 'torch' (torch.optim.Adam, A/B reference)")
+        groups = [                                                                # ppo.py:17-22
+            {"params": list(self.policy.actor_head.parameters()), "lr": c.LR_ACTOR},
+            {"params": list(self.policy.actor_net.parameters()), "lr": c.LR_ACTOR},
+            {"params": list(self.policy.critic_head.parameters()), "lr": c.LR_CRITIC},
+            {"params": list(self.policy.critic_net.parameters()), "lr": c.LR_CRITIC},
+        ]
         params = list(self.policy.parameters())
-        self._flat_grad = torch.zeros(sum(p.numel() for p in params), device=self.device)
-        off = 0
-        for p in params:                               # .grad of every parameter is a view of one flat buffer
-            p.grad = self._flat_grad[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        self.num_params = sum(p.numel() for p in params)
+        # parameters and their .grad are views of ONE flat buffer each (state_dict order): the library reads the
+        # weights in place, the all-reduce is one call, and clip + Adam run over the flat buffers (csrc/ppo_optim.cu)
+        self._flat_params = torch.empty(self.num_params, device=self.device)
+        self._flat_grad = torch.zeros(self.num_params, device=self.device)
+        lr_of = {id(p): g["lr"] for g in groups for p in g["params"]}
+        off, seg_end, seg_lr = 0, [], []
+        for p in params:
+            n = p.numel()
+            self._flat_params[off:off + n].copy_(p.detach().reshape(-1))
+            p.data = self._flat_params[off:off + n].view_as(p)
+            p.grad = self._flat_grad[off:off + n].view_as(p)
+            off += n
+            if seg_lr and seg_lr[-1] == lr_of[id(p)]:
+                seg_end[-1] = off
+            else:
+                seg_end.append(off); seg_lr.append(lr_of[id(p)])
+        self.optimizer_kind = optimizer if self.device.type == "cuda" else "torch"
+        if self.optimizer_kind == "torch":
+            self.optimizer = torch.optim.Adam(groups, capturable=self.graph_update)
+        else:
+            self.optimizer = None
+            self._seg_end = (C.c_int64 * len(seg_end))(*seg_end)
+            self._seg_lr = (C.c_float * len(seg_lr))(*seg_lr)
+            self._exp_avg = torch.zeros(self.num_params, device=self.device)
+            self._exp_avg_sq = torch.zeros(self.num_params, device=self.device)
+            self._adam_step = torch.zeros(1, dtype=torch.int64, device=self.device)
+            self._norm_partials = torch.zeros(_capi.load().ppo_optim_partials(), dtype=torch.float64, device=self.device)
+            self.grad_norm = torch.zeros(1, device=self.device)      # pre-clip norm of the last step
         T, B, dev = self.T, self.B, self.device
         self.buf_obs = torch.zeros(T, B, c.SEQ_LEN, c.STATE_DIM, device=dev)
         self.buf_action = torch.zeros(T, B, dtype=torch.int64, device=dev)
@@ -203,10 +232,8 @@ class PPOAgent:
         obs = self.buf_obs.view(n, c.SEQ_LEN, c.STATE_DIM)
         act, old_logp, old_val = self.buf_action.view(n), self.buf_logp.view(n), self.buf_value.view(n)
         if self.trunks is not None:                                         # forward, loss and backward in the library
-            with torch.no_grad():
-                flat = torch.cat([p.reshape(-1) for p in self.policy.parameters()])
-            self.trunks.ppo_step(flat, obs[idx], act[idx], old_logp[idx], self._adv[idx], self._ret[idx], old_val[idx],
-                                 c.EPS_CLIP, 0.5, 0.01, self._flat_grad, self._mb_stats)
+            self.trunks.ppo_step(self._flat_params, obs[idx], act[idx], old_logp[idx], self._adv[idx], self._ret[idx],
+                                 old_val[idx], c.EPS_CLIP, 0.5, 0.01, self._flat_grad, self._mb_stats)
             self._apply_gradient()
             self._mb_sums += self._mb_stats
             return
@@ -228,14 +255,47 @@ class PPOAgent:
         self._mb_sums += torch.stack([loss_actor.detach(), loss_critic.detach(), ent.detach()])
 
     def _apply_gradient(self):
-        """all-reduce (the only collective of training), global-norm clip (ppo.py:160) on the flat view, Adam"""
+        """all-reduce (the only collective of training), then averaging over ranks + global-norm clip (ppo.py:160) + the
+        four-group Adam step (ppo.py:17-22,162) as two launches over the flat buffers (csrc/ppo_optim.cu)"""
         c = self.cfg
         if self.world > 1:
             torch.distributed.all_reduce(self._flat_grad, group=self.group)
-            self._flat_grad.div_(self.world)
-        norm = self._flat_grad.norm()
-        self._flat_grad.mul_(torch.clamp(c.GRAD_NORM_CLIP / (norm + 1e-6), max=1.0))
-        self.optimizer.step()
+        if self.optimizer_kind == "torch":                                  # A/B reference: eager tensor ops + torch Adam
+            if self.world > 1:
+                self._flat_grad.div_(self.world)
+            norm = self._flat_grad.norm()
+            self._flat_grad.mul_(torch.clamp(c.GRAD_NORM_CLIP / (norm + 1e-6), max=1.0))
+            self.optimizer.step()
+            return
+        rc = _capi.load().ppo_clip_adam_step(
+            _ptr(self._flat_params), _ptr(self._flat_grad), _ptr(self._exp_avg), _ptr(self._exp_avg_sq), self.num_params,
+            self._seg_end, self._seg_lr, len(self._seg_lr), 1.0 / self.world, float(c.GRAD_NORM_CLIP), 0.9, 0.999, 1e-8,
+            _ptr(self._adam_step), _ptr(self._norm_partials), _ptr(self.grad_norm), self.device.index,
+            C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        if rc != 0:
+            raise _capi.UavenvError(rc, "ppo_clip_adam_step failed")
+
+    def launches_per_minibatch(self):
+        """Own kernels launched by one minibatch step (bench.py's gpu_launches claim)."""
+        n = 79 if self.trunks is not None else 0      # 32 tcgen05 GEMMs, 16 weight-gradient, 29 LN / attention / embedding / head, 2 loss
+        return n + (2 if self.optimizer_kind == "fused" else 0)
+
+    def time_gradient_allreduce(self, iters=50):
+        """Microseconds per NCCL all-reduce of a buffer shaped like the flat gradient (CUDA events around `iters`
+        back-to-back calls on the current stream); 0.0 on one rank."""
+        if self.world == 1:
+            return 0.0
+        buf = torch.zeros_like(self._flat_grad)
+        for _ in range(5):
+            torch.distributed.all_reduce(buf, group=self.group)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(self.device)
+        e0.record()
+        for _ in range(iters):
+            torch.distributed.all_reduce(buf, group=self.group)
+        e1.record()
+        torch.cuda.synchronize(self.device)
+        return 1e3 * e0.elapsed_time(e1) / iters
 
     def _run_minibatch(self):
         """Eager for the first steps (they double as the warm-up torch wants before a capture), then ONE graph launch."""
@@ -259,8 +319,11 @@ class PPOAgent:
 
     def _update(self, last_obs):
         c = self.cfg
-        with torch.no_grad():
-            _, last_value = self.policy_old.logits_and_value(last_obs)
+        if self.fused is not None:          # V(s_T) from the same tcgen05 forward that produced the rollout's values
+            last_value = self.fused.get_action(last_obs, self._rollout_step)[2].clone()
+        else:
+            with torch.no_grad():
+                _, last_value = self.policy_old.logits_and_value(last_obs)
         returns, adv = compute_gae(self.buf_reward, self.buf_value, self.buf_done, last_value.squeeze(-1), c.GAMMA,
                                    c.GAE_LAMBDA, normalize=True, group=self.group if self.world > 1 else None)
         n = self.T * self.B

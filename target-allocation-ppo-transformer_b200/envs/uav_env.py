@@ -162,11 +162,13 @@ class UAVEnvBatched:
                                         C.byref(self._info_c) if self._info_c is not None else None, self._stream()))
         return self.obs, self.reward, self.done, self.info
 
-    def step_host(self, actions_cpu, reward_out=None, done_out=None):
+    def step_host(self, actions_cpu, reward_out=None, done_out=None, obs_out=None):
         """The same step driven from HOST buffers (the reference's caller lives on the host):
         actions (int64, or one byte each as int8/uint8) travel host->device, reward/done device->host, inside the
         call - in place over PCIe when the tensors are pinned, through staging copies otherwise.  The observation
-        window stays in self.obs on the device for the policy.  Returns (reward_cpu, done_cpu)."""
+        window stays in self.obs on the device for the policy; with obs_out (a pinned host [B,5,14] f32 tensor) it is
+        ALSO copied to the host inside the call, i.e. the reference's full (obs, reward, done) crosses the boundary
+        (envs/uav_env.py:435).  Returns (reward_cpu, done_cpu)."""
         if self._h_reward is None:
             self._h_reward = torch.zeros(self.num_envs, dtype=torch.float32).pin_memory()
             self._h_done = torch.zeros(self.num_envs, dtype=torch.uint8).pin_memory()
@@ -178,6 +180,12 @@ class UAVEnvBatched:
         fn = self._lib.uavenv_step_host if actions_cpu.dtype == torch.int64 else self._lib.uavenv_step_host_i8
         self._chk(fn(self._h, C.c_void_p(actions_cpu.data_ptr()), C.c_void_p(r.data_ptr()), C.c_void_p(d.data_ptr()),
                      C.c_void_p(self.obs.data_ptr()), self._stream()))
+        if obs_out is not None:
+            if obs_out.is_cuda or obs_out.dtype != torch.float32 or obs_out.numel() != self.obs.numel() \
+                    or not obs_out.is_contiguous():
+                raise ValueError("obs_out must be a contiguous host float32 tensor of [num_envs,5,14]")
+            obs_out.copy_(self.obs, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
         return r, d
 
     def random_actions(self, step, action_seed=1, out=None):

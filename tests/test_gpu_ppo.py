@@ -73,8 +73,9 @@ def test_train_loop_logs_reference_columns_and_saves_reference_loadable_checkpoi
     hist = tr.train(num_envs=256, horizon=40, iterations=2, log_dir=str(tmp_path), minibatch_size=4096, verbose=False)
     assert len(hist) == 2 and hist[-1]["samples_per_sec"] > 0 and hist[-1]["Episode"] > 0
     rows = list(csv.reader(open(tmp_path / "training_stats.csv")))
-    assert rows[0] == ["Episode", "Avg_Reward", "Avg_J_Val", "Max_Coverage", "Q0_Value", "Action1_Ratio",
+    assert rows[0] == ["Episode", "Avg_Reward", "Avg_Q0", "Avg_J_Value", "Max_Coverage", "Action1_Ratio",      # main_train.py:57-63
                        "Valid_Assign_Rate", "Avg_P_Dmg", "Avg_P_Final", "Loss_Critic", "Loss_Actor", "Entropy"]
+    assert np.isfinite(hist[-1]["Avg_Q0"]) and hist[-1]["Max_Coverage"] >= 1
     assert len(rows) == 3
     sd = torch.load(tmp_path / "final_model.pth", map_location="cpu")
     fx = np.load(os.path.join(GOLDEN, "policy_net.npz"))
@@ -143,3 +144,27 @@ def test_fused_attention_forward_and_gradients_match_tensor_ops(nq):
     else:
         assert torch.allclose(g1[..., 128:], g0[..., 128:], rtol=1e-4, atol=1e-6)
         assert torch.allclose(q1, q0, rtol=1e-4, atol=1e-6)
+
+
+def test_fused_clip_adam_matches_torch_clip_and_adam():
+    """csrc/ppo_optim.cu against clip_grad_norm_-style scaling + torch.optim.Adam with the reference's four groups
+    (agents/ppo.py:17-22,160-162): same parameters after 5 steps (1e-6), same clipped gradient, same pre-clip norm."""
+    import uavenv_b200 as ub
+    a = ub.PPOAgent(4, 4, "cuda", seed=5, optimizer="fused")
+    b = ub.PPOAgent(4, 4, "cuda", seed=5, optimizer="torch")
+    assert torch.equal(a._flat_params, b._flat_params)
+    assert a._flat_params.data_ptr() == next(a.policy.parameters()).data_ptr()      # parameters are views of the flat buffer
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for step in range(5):
+        grad = torch.randn(a.num_params, device="cuda", generator=g) * (0.01 if step % 2 else 0.0005)   # clipped and unclipped
+        a._flat_grad.copy_(grad); b._flat_grad.copy_(grad)
+        a._apply_gradient(); b._apply_gradient()
+        assert abs(float(a.grad_norm) - float(grad.norm())) <= 1e-5 * float(grad.norm())
+        assert torch.allclose(a._flat_grad, b._flat_grad, rtol=1e-5, atol=1e-9)
+        assert torch.allclose(a._flat_params, b._flat_params, rtol=1e-6, atol=2e-7), step
+    assert int(a._adam_step) == 5
+    # the two learning rates really differ by segment: actor params moved ~5x less than critic params
+    w0 = ub.PPOAgent(4, 4, "cuda", seed=5)._flat_params
+    moved = (a._flat_params - w0).abs()
+    n_actor = sum(p.numel() for p in a.policy.actor_net.parameters()) + sum(p.numel() for p in a.policy.actor_head.parameters())
+    assert float(moved[:n_actor].mean()) * 3 < float(moved[n_actor:].mean())
