@@ -59,11 +59,19 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.t_begin, self.t_end = None, None
+
+    def mark_begin(self):
+        """The timed region starts now: only samples taken from here on (until mark_end) are reported."""
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -71,7 +79,7 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -79,7 +87,12 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        lo = (self.t_begin or 0.0) - 0.05
+        hi = (self.t_end or time.time()) + 0.15
+        inside = [ln for ts, ln in self.lines if lo <= ts <= hi]
+        if not inside:                      # a region shorter than the sampling period: the sample nearest to it
+            inside = [min(self.lines, key=lambda x: abs(x[0] - lo))[1]] if self.lines else []
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -196,18 +209,20 @@ def measure_ppo(rank, local_rank, world, dev, B, T, K, W, with_clocks=True):
         split[2].record()
         return out
 
-    for _ in range(W):
-        iteration()
     sampler = ClockSampler(local_rank)
     if rank == 0 and with_clocks:
-        sampler.start()
+        sampler.start()                 # nvidia-smi takes a moment to come up: started before the warm-up
+    for _ in range(W):
+        iteration()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     parallel.barrier(); torch.cuda.synchronize(dev)
+    sampler.mark_begin()
     e0.record()
     for _ in range(K):
         stats = iteration()
     e1.record()
     torch.cuda.synchronize(dev); parallel.barrier()
+    sampler.mark_end()
     ms = parallel.reduce_scalar(e0.elapsed_time(e1), "max", dev)
     clocks = sampler.stop() if (rank == 0 and with_clocks) else None
     roll_ms = parallel.reduce_scalar(split[0].elapsed_time(split[1]), "max", dev)
@@ -305,6 +320,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     B = w["envs_per_gpu"]
     K, W = args.steps, args.warmup
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                 # nvidia-smi takes a moment to come up: started before the burn-in
     env = ub.UAVEnvBatched(B, device=dev, seed=SCENE_SEED, env_id_base=rank * B, config=make_config(ub, w, args.reset_episodes))
     env.reset(full_reset=True)
     # steady state of the main_train.py:79 schedule: after long training the envs sit at different phases of
@@ -369,10 +387,8 @@ def main():
         graph_us = 1e3 * e0.elapsed_time(e1) / (5 * POOL)
         print("graph replay: %.2f us/step" % graph_us, file=sys.stderr)
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     # --- device-resident inputs: the fused kernel alone --------------------------------------------------
+    sampler.mark_begin()
     ms_dev = timed(lambda i: env.step(pool[i % POOL]), W, K)
     # the same bracket around a ~2 us kernel (the action generator): what the protocol itself costs per step
     ms_floor = timed(lambda i: env.random_actions(i, ACTION_SEED), 3, min(K, 50)) / min(K, 50)
@@ -382,6 +398,7 @@ def main():
     # ... and with step()'s full 4-tuple crossing the boundary: the [B,5,14] window is copied to pinned host memory too
     obs_host = torch.empty(B, 5, 14, dtype=torch.float32).pin_memory()
     ms_e2e_obs = timed(lambda i: env.step_host(pool_host_i8[i % POOL], obs_out=obs_host), W, K)
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     drift = env.recompute_objective()
     drift = parallel.reduce_scalar(drift, "max", dev)

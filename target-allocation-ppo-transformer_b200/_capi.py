@@ -75,7 +75,10 @@ def load():
     if _lib is not None:
         return _lib
     path = _build.LIB_PATH
-    if not _build.up_to_date():
+    override = os.environ.get("UAVENV_LIB_OVERRIDE")     # timing experiments only: an ablation build of the same ABI
+    if override:
+        path = override
+    elif not _build.up_to_date():
         try:
             _build.build(lib=path)
         except Exception as exc:  # no nvcc on this host, or a compile error: never load a binary older than its sources

@@ -85,6 +85,8 @@ class PPOAgent:
         from ..networks.transformer_net import TransformerActorCritic
         self.cfg = cfg or global_cfg
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.B, self.T = int(num_envs), int(horizon)
         self.group = group
         self.world = torch.distributed.get_world_size(group) if (

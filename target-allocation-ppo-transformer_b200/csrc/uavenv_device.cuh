@@ -190,6 +190,9 @@ __device__ __forceinline__ double dist_score(double dist, double inv_zeta) {
 
 // envs/mechanics.py:93-114 calc_damage_prob (Eq.4)
 __device__ __forceinline__ double damage_prob(const Params &P, const UavRec &u, double tx, double ty, double tspeed) {
+#if defined(UAV_ABL) && (UAV_ABL & 1)
+    return clip01((tx - u.x) * 1e-3 * u.load + ty * 1e-4 * tspeed);
+#endif
     double dist;
     const double e_angle = angle_score(u.x, u.y, u.wx, u.wy, tx, ty, dist);
     const double e_dist = dist_score(dist, P.inv_zeta_d);

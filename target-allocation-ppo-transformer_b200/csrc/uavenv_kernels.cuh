@@ -14,6 +14,9 @@
 
 #include "uavenv_device.cuh"
 
+#ifndef UAV_ABL
+#define UAV_ABL 0   // ablation bitmask for timing experiments ONLY (breaks results): 1 cheap score, 2 no window traffic,
+#endif              // 4 no record gather, 8 no current-pair / ring stores
 namespace uavk {
 
 constexpr int kStepThreads = 128;          // envs per CTA in step_kernel (thread-per-env main phases)
@@ -355,6 +358,7 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
     const uint32_t head_new = (head_old + 1u) % (uint32_t)kSeqLen;       // ring slot of this step's row
     // older rows of the window: ring tile [slot][feature pair][32 lanes] -> tile rows 0..3 (time order)
     float2 *const ring = P.ring(bc);
+#if !(UAV_ABL & 2)
 #pragma unroll
     for (int a = kSeqLen - 1; a >= 1; --a) {
         const uint32_t slot = (head_new + (uint32_t)(kSeqLen - a)) % (uint32_t)kSeqLen;
@@ -363,6 +367,7 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
 #pragma unroll
         for (int f = 0; f < kStateDim / 2; ++f) cp_async_8(dst + 2 * f, src + f * 32);
     }
+#endif
     if (tid == 0) {
         // arrive; the last CTA to have READ the head publishes the new one (kept on the device so that
         // CUDA-graph replays stay correct).  The increment depends on head_old, so the read is ordered first.
@@ -453,8 +458,13 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
             warp_regen_inline(P, regen_mask, b0, slot, gen >> 1, s_keys);
         }
         if (live && (pass == 0 ? (!done || soft) : inline_regen)) {
+#if UAV_ABL & 4
+            UavRec u; u.x = c_pf; u.y = c_pd; u.wx = 1.0; u.wy = 0.0; u.load = 0.9; u.cost = c_ucost; u.p_pen = 0.5; u.inv_speed = 2.0;
+            TgtRec t; t.x = 170.0 + c_value; t.y = 80.0; t.speed = 0.01; t.value = c_value; t.nh = c_nh; t.nh_pure = c_nhp; t.lock_cost = c_lock_cost; t.lock_cnt = c_lock_cnt; t.id = c_tid;
+#else
             const UavRec u = P.uav[P.uoff(slot, b) + k];
             TgtRec t = P.tgt[P.toff(slot, b) + m];   // sees this thread's own accept store on target m
+#endif
             if (soft) { t.nh = 1.0; t.nh_pure = 1.0; t.lock_cost = 0.0; t.lock_cnt = 0; }  // cleared below by the warp
             cp_async_wait_all();                        // ring rows have landed in the tile (gathers still in flight)
             const int nprev = age < kSeqLen - 1 ? age : kSeqLen - 1;
@@ -469,6 +479,9 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
             double pf, pd;
             float row[kStateDim];
             eval_pointer_pair(P, u, t, cost_sum, covered_val, total_cost, total_val, pf, pd, row);
+#if UAV_ABL & 8
+            if (pf == 123.456) {
+#endif
             store_current_pair(H, u, t, pf, pd);
             float2 *dsth = ring + head_new * (kStateDim / 2) * 32;
 #pragma unroll
@@ -477,6 +490,9 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
                 dsth[f * 32] = v;
                 *reinterpret_cast<float2 *>(tile + (kSeqLen - 1) * kStateDim + 2 * f) = v;
             }
+#if UAV_ABL & 8
+            }
+#endif
             H.n(I_K) = k; H.n(I_M) = m; H.n(I_NASSIGNED) = nA; H.n(I_NCOVERED) = n0; H.n(I_AGE) = nprev + 1;
             H.f(F_REV) = rev; H.f(F_COST_SUM) = cost_sum; H.f(F_COVERED_VAL) = covered_val;
             H.f(F_SUM_PD) = sum_pd; H.f(F_SUM_PF) = sum_pf;
@@ -501,7 +517,8 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
             float *dst = io.obs + (size_t)b0 * kObsFloats;
             const float *src = s_tile[warp];
             const uint32_t bytes = (uint32_t)nenv * kObsFloats * sizeof(float);
-            if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0 && (bytes & 15u) == 0) {
+            if (UAV_ABL & 2) {
+            } else if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0 && (bytes & 15u) == 0) {
                 if (lane == 0) { bulk_store(dst, src, bytes); bulk_store_wait_read(); }
             } else {  // ragged tail / unaligned caller buffer
                 for (int i = lane; i < nenv * kObsFloats; i += 32) dst[i] = src[i];
