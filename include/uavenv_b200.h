@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define UAVENV_ABI_VERSION 1
+#define UAVENV_ABI_VERSION 2
 #define UAVENV_STATE_DIM 14 /* configs/config.py:61 STATE_DIM */
 #define UAVENV_SEQ_LEN 5    /* configs/config.py:62 SEQ_LEN   */
 

@@ -126,7 +126,7 @@ def load():
                  "uavenv_score_matrix_f64", "uavenv_recompute_objective", "uavenv_random_actions",
                  "ppo_gae_advantages", "ppo_normalize_advantages"):
         getattr(L, name).restype = C.c_int
-    if L.uavenv_abi_version() != 1:
+    if L.uavenv_abi_version() != 2:
         raise ImportError("libuavenv_b200.so ABI version mismatch")
     _lib = L
     return L

@@ -30,8 +30,6 @@ struct uavenv {
     size_t reset_smem = 0;
     int n_service = 0;
     bool ready = false;              // reset() or load_scene() happened
-    const void *zc_key[3] = {nullptr, nullptr, nullptr};  // last host buffers seen by step_host ...
-    void *zc_dev[3] = {nullptr, nullptr, nullptr};        // ... and their device aliases when pinned + mapped
     std::string err;
 };
 
@@ -114,11 +112,18 @@ static int create_impl(uavenv *h) {
     CU_TRY(h, dev_alloc(h, &P.tgt_vel, 2 * B * M));
     CU_TRY(h, dev_alloc(h, &P.nfz, 2 * B * K1));
     CU_TRY(h, dev_alloc(h, &P.intc, 2 * B * K2));
-    const size_t req_bytes = (B + kServiceEnvsPerWarp - 1) / kServiceEnvsPerWarp * kServiceEnvsPerWarp;
-    CU_TRY(h, dev_alloc(h, &P.pregen_req, req_bytes));
-    CU_TRY(h, dev_alloc(h, &P.pregen_ack, req_bytes));
-    CU_TRY(h, cudaMemset(P.pregen_req, 0, req_bytes));
-    CU_TRY(h, cudaMemset(P.pregen_ack, 0, req_bytes));
+    // pre-generation service: one CTA per 1024 envs (only when scenes are ever regenerated, and when a warp's
+    // shared-memory scratch holds the scene's obstacles)
+    const size_t n_svc = (B + kServiceEnvsPerCta - 1) / kServiceEnvsPerCta;
+    h->n_service = (c.auto_reset && c.reset_episodes > 0 &&
+                    K1 * sizeof(NfzRec) + K2 * sizeof(IntRec) <= (size_t)kServiceScratchPerWarp) ? (int)n_svc : 0;
+    CU_TRY(h, dev_alloc(h, &P.svc_ctr, n_svc));
+    CU_TRY(h, cudaMemset(P.svc_ctr, 0, n_svc * sizeof(uint32_t)));
+    CU_TRY(h, dev_alloc(h, &P.q_count, 2));
+    CU_TRY(h, cudaMemset(P.q_count, 0, 2 * sizeof(uint32_t)));
+    CU_TRY(h, dev_alloc(h, &P.q_env, 2 * B));
+    CU_TRY(h, dev_alloc(h, &P.q_gen, 2 * B));
+    CU_TRY(h, dev_alloc(h, &P.q_done, 2 * B));
     const size_t tiles = (B + 31) / 32;
     CU_TRY(h, dev_alloc(h, &P.step_ctr, 2));
     CU_TRY(h, dev_alloc(h, &P.hdr, tiles * kEnvTileBytes));
@@ -127,7 +132,6 @@ static int create_impl(uavenv *h) {
         for (size_t b = 0; b < tiles * 32; ++b) {
             const Hdr hv = header_at(init.data(), (int)b);
             hv.n(I_NEXT_TAG) = -1;
-            hv.n(I_JOB) = -256;
         }
         CU_TRY(h, cudaMemcpy(P.hdr, init.data(), init.size(), cudaMemcpyHostToDevice));
     }
@@ -140,13 +144,14 @@ static int create_impl(uavenv *h) {
     CU_TRY(h, dev_alloc(h, &h->d_scratch, 1));
     // per-warp scratch of the scene generator: max(N,M) sort keys, for the 4 warps of a CTA
     h->reset_smem = (size_t)kWarpsPerCta * std::max(N, M) * sizeof(uint32_t);
-    // CTAs appended to every step launch that prepare next scenes (only when scenes are ever regenerated)
-    h->n_service = (c.auto_reset && c.reset_episodes > 0)
-                       ? (int)((B + (size_t)kServiceEnvsPerWarp * kWarpsPerCta - 1) / ((size_t)kServiceEnvsPerWarp * kWarpsPerCta))
-                       : 0;
     if (h->reset_smem > 8 * 1024) {
-        CU_TRY(h, cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->reset_smem));
-        CU_TRY(h, cudaFuncSetAttribute(reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->reset_smem));
+        // process-wide function attributes: never lower what another handle (larger N, M) has already asked for
+        static size_t attr_smem = 0;
+        if (h->reset_smem > attr_smem) {
+            CU_TRY(h, cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->reset_smem));
+            CU_TRY(h, cudaFuncSetAttribute(reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->reset_smem));
+            attr_smem = h->reset_smem;
+        }
     }
     CU_TRY(h, cudaDeviceSynchronize());
     return UAVENV_OK;
@@ -228,7 +233,7 @@ static int launch_step(uavenv_t *h, const void *d_actions, int action_bytes, flo
     io.avg_p_final = info ? info->d_avg_p_final : nullptr;
     io.reward_f64 = info ? info->d_reward_f64 : nullptr;
     const int n_main = (h->B + kStepThreads - 1) / kStepThreads;
-    step_kernel<<<n_main + h->n_service, kStepThreads, h->reset_smem, (cudaStream_t)stream>>>(h->P, io, n_main);
+    step_kernel<<<h->n_service + n_main, kStepThreads, h->reset_smem, (cudaStream_t)stream>>>(h->P, io, h->n_service);
     return launch_check(h, "step_kernel");
 }
 
@@ -252,13 +257,11 @@ static int step_host_impl(uavenv_t *h, const void *h_actions, int action_bytes, 
     CU_TRY(h, cudaSetDevice(h->device));
     // Pinned, device-mapped host buffers are used in place: the fused kernel reads the actions and writes
     // reward / done straight over PCIe (no separate copy launches).  Pageable buffers go through staging copies.
-    if (h_actions != h->zc_key[0] || h_reward != h->zc_key[1] || h_done != h->zc_key[2]) {
-        h->zc_key[0] = h_actions; h->zc_key[1] = h_reward; h->zc_key[2] = h_done;
-        h->zc_dev[0] = mapped_alias(h_actions); h->zc_dev[1] = mapped_alias(h_reward); h->zc_dev[2] = mapped_alias(h_done);
-    }
-    if (h->zc_dev[0] && h->zc_dev[1] && h->zc_dev[2]) {
-        int rc = launch_step(h, h->zc_dev[0], action_bytes, d_obs ? d_obs : h->obs_buf, (float *)h->zc_dev[1],
-                             (uint8_t *)h->zc_dev[2], nullptr, stream);
+    // (the aliases are looked up on every call: a pointer VALUE can be re-used by a different allocation)
+    void *zc_a = mapped_alias(h_actions), *zc_r = mapped_alias(h_reward), *zc_d = mapped_alias(h_done);
+    if (zc_a && zc_r && zc_d) {
+        int rc = launch_step(h, zc_a, action_bytes, d_obs ? d_obs : h->obs_buf, (float *)zc_r, (uint8_t *)zc_d, nullptr,
+                             stream);
         if (rc != UAVENV_OK) return rc;
         CU_TRY(h, cudaStreamSynchronize(s));
         return UAVENV_OK;

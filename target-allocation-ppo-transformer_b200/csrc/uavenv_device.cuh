@@ -73,7 +73,7 @@ enum I32Field {
     I_CUR_TID,        // target_m.id
     I_FINISHED,       // auto_reset = 0 only
     I_NEXT_TAG,       // scene index held complete in the OTHER slot (-1: none).   Written by the service only.
-    I_JOB,            // (scene index << 8) | chunks done, of the service's job.   Written by the service only.
+    I_SPARE,
     NI32
 };
 constexpr size_t kHdrTileBytes = (size_t)NF64 * 32 * sizeof(double) + (size_t)NI32 * 32 * sizeof(int32_t);
@@ -115,8 +115,12 @@ struct Params {
     double2 *tgt_vel;   // [2][B][M]  cold
     NfzRec *nfz;        // [2][B][K1]
     IntRec *intc;       // [2][B][K2]
-    uint8_t *pregen_req;  // [B] request counter, written by the env's owner when it consumes / invalidates the next scene
-    uint8_t *pregen_ack;  // [B] value of pregen_req the service has satisfied
+    // pre-generation service (uavenv_kernels.cuh): per-CTA launch counters and two alternating job queues
+    uint32_t *svc_ctr;  // [service CTAs] launches seen by each service CTA (all equal: every CTA runs in every launch)
+    uint32_t *q_count;  // [2] entries of each queue
+    int32_t *q_env;     // [2][B] env of the entry
+    int32_t *q_gen;     // [2][B] its I_GEN word when it was queued
+    int32_t *q_done;    // [2][B] chunks finished
     uint32_t *step_ctr; // [0] = ring head (mod 5), [1] = CTA arrival counter of the running step
     unsigned char *hdr; // [B/32] env tiles (kEnvTileBytes each): header tile, then the observation ring tile
                         // [5 slots][7 feature pairs][32 lanes] float2
@@ -190,9 +194,6 @@ __device__ __forceinline__ double dist_score(double dist, double inv_zeta) {
 
 // envs/mechanics.py:93-114 calc_damage_prob (Eq.4)
 __device__ __forceinline__ double damage_prob(const Params &P, const UavRec &u, double tx, double ty, double tspeed) {
-#if defined(UAV_ABL) && (UAV_ABL & 1)
-    return clip01((tx - u.x) * 1e-3 * u.load + ty * 1e-4 * tspeed);
-#endif
     double dist;
     const double e_angle = angle_score(u.x, u.y, u.wx, u.wy, tx, ty, dist);
     const double e_dist = dist_score(dist, P.inv_zeta_d);
@@ -202,16 +203,14 @@ __device__ __forceinline__ double damage_prob(const Params &P, const UavRec &u, 
 }
 
 // envs/mechanics.py:118-163 calc_penetration_prob (Eq.5-6): depends on the UAV only
-__device__ __forceinline__ double penetration_prob(const Params &P, int slot, int b, const UavRec &u) {
+__device__ __forceinline__ double penetration_prob(const Params &P, const NfzRec *Z, const IntRec *I, const UavRec &u) {
     double p = 1.0;
-    const NfzRec *Z = P.nfz + ((size_t)slot * P.B + b) * P.K1;
     for (int i = 0; i < P.K1; ++i) {                               // :130-141
         double dist;
         const double ea = angle_score(u.x, u.y, u.wx, u.wy, Z[i].x, Z[i].y, dist);
         const double qd = dist / 10.0, ed = exp(-(qd * qd));       // zeta = 10 for obstacles (:78)
         p *= clip01((1.0 - ea) * (1.0 - ed));
     }
-    const IntRec *I = P.intc + ((size_t)slot * P.B + b) * P.K2;
     for (int i = 0; i < P.K2; ++i) {                               // :144-161
         double dist;
         const double ea = angle_score(u.x, u.y, u.wx, u.wy, I[i].x, I[i].y, dist);
@@ -224,12 +223,15 @@ __device__ __forceinline__ double penetration_prob(const Params &P, int slot, in
     return p;
 }
 
-// derived fields of a UAV record from its velocity (obstacles of env b must be visible for p_pen)
-__device__ __forceinline__ void finish_uav(const Params &P, int slot, int b, UavRec &u, double vx, double vy) {
+// derived fields of a UAV record from its velocity and the scene's obstacles Z[K1], I[K2] (any address space)
+__device__ __forceinline__ void finish_uav(const Params &P, const NfzRec *Z, const IntRec *I, UavRec &u, double vx, double vy) {
     const double speed = sqrt(vx * vx + vy * vy);
     if (speed < 1e-6) { u.wx = 1.0; u.wy = 0.0; u.inv_speed = -1.0; }
     else { u.wx = vx / speed; u.wy = vy / speed; u.inv_speed = 1.0 / speed; }
-    u.p_pen = penetration_prob(P, slot, b, u);
+    u.p_pen = penetration_prob(P, Z, I, u);
+}
+__device__ __forceinline__ void finish_uav(const Params &P, int slot, int b, UavRec &u, double vx, double vy) {
+    finish_uav(P, P.nfz + ((size_t)slot * P.B + b) * P.K1, P.intc + ((size_t)slot * P.B + b) * P.K2, u, vx, vy);
 }
 
 // envs/mechanics.py:185-241 get_state_vector (Eq.15): fp64 features, cast to f32, then the power-of-two

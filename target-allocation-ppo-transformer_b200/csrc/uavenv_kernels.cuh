@@ -14,14 +14,12 @@
 
 #include "uavenv_device.cuh"
 
-#ifndef UAV_ABL
-#define UAV_ABL 0   // ablation bitmask for timing experiments ONLY (breaks results): 1 cheap score, 2 no window traffic,
-#endif              // 4 no record gather, 8 no current-pair / ring stores
 namespace uavk {
 
 constexpr int kStepThreads = 128;          // envs per CTA in step_kernel (thread-per-env main phases)
 constexpr int kWarpsPerCta = kStepThreads / 32;
 constexpr int kResetThreads = 128;
+constexpr int kServiceScratchPerWarp = 32 * kObsFloats * 4;   // a service warp's obstacle scratch = its idle window tile (8960 B)
 
 struct StepIO {
     const void *actions;     // [B] int64 (action_bytes = 8) or int8 (action_bytes = 1)
@@ -91,31 +89,36 @@ __device__ __forceinline__ void scene_totals(const Params &P, int b, uint32_t sc
     total_cost = 1.0 * (P.N - P.N / 4) + 1.25 * (P.N / 4);
 }
 
-__device__ void warp_generate_chunk(const Params &P, int slot, int b, uint32_t scene, int chunk, uint32_t *s_keys) {
+// obstacles of a scene (uav_env.py:146-170) into Z[K1], I[K2] (global records, or a warp's shared-memory scratch)
+__device__ __forceinline__ void warp_generate_obstacles(const Params &P, int b, uint32_t scene, NfzRec *Z, IntRec *I) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t k0 = P.seed_lo, k1 = P.seed_hi, env = P.env_id_base + (uint32_t)b;
+    for (int i = lane; i < P.K1; i += 32) {
+        const uint4 a = philox4x32(k0, k1, i, S_NFZ_A, scene, env);
+        const uint4 c = philox4x32(k0, k1, i, S_NFZ_B, scene, env);
+        Z[i].radius = 5.0 + (10.0 - 5.0) * u53(a.x, a.y);
+        Z[i].x = 120.0 + (140.0 - 120.0) * u53(a.z, a.w);
+        Z[i].y = 0.0 + (P.map_h - 0.0) * u53(c.x, c.y);
+    }
+    for (int i = lane; i < P.K2; i += 32) {
+        const uint4 a = philox4x32(k0, k1, i, S_INT_A, scene, env);
+        const uint4 c = philox4x32(k0, k1, i, S_INT_B, scene, env);
+        I[i].x = 140.0 + (160.0 - 140.0) * u53(a.x, a.y);
+        I[i].y = 0.0 + (P.map_h - 0.0) * u53(a.z, a.w);
+        const double sp = 0.30 + (0.32 - 0.30) * u53(c.x, c.y);
+        const double ang = 0.0 + (2.0 * 3.141592653589793 - 0.0) * u53(c.z, c.w);
+        I[i].vx = cos(ang) * sp;
+        I[i].vy = sin(ang) * sp;
+    }
+}
+
+// entities [32*c, 32*c+32) of chunk c: target chunks first, then UAV chunks; Z / I: the scene's obstacles, already
+// visible to this warp (the UAV chunks need them for p_pen)
+__device__ void warp_generate_chunk(const Params &P, int slot, int b, uint32_t scene, int chunk, uint32_t *s_keys,
+                                    const NfzRec *Z, const IntRec *I) {
     const int lane = threadIdx.x & 31;
     const uint32_t k0 = P.seed_lo, k1 = P.seed_hi, env = P.env_id_base + (uint32_t)b;
     const int N = P.N, M = P.M, tchunks = (M + 31) / 32;
-    if (chunk == 0) {  // obstacles   (uav_env.py:146-170)
-        NfzRec *Z = P.nfz + ((size_t)slot * P.B + b) * P.K1;
-        for (int i = lane; i < P.K1; i += 32) {
-            const uint4 a = philox4x32(k0, k1, i, S_NFZ_A, scene, env);
-            const uint4 c = philox4x32(k0, k1, i, S_NFZ_B, scene, env);
-            Z[i].radius = 5.0 + (10.0 - 5.0) * u53(a.x, a.y);
-            Z[i].x = 120.0 + (140.0 - 120.0) * u53(a.z, a.w);
-            Z[i].y = 0.0 + (P.map_h - 0.0) * u53(c.x, c.y);
-        }
-        IntRec *I = P.intc + ((size_t)slot * P.B + b) * P.K2;
-        for (int i = lane; i < P.K2; i += 32) {
-            const uint4 a = philox4x32(k0, k1, i, S_INT_A, scene, env);
-            const uint4 c = philox4x32(k0, k1, i, S_INT_B, scene, env);
-            I[i].x = 140.0 + (160.0 - 140.0) * u53(a.x, a.y);
-            I[i].y = 0.0 + (P.map_h - 0.0) * u53(a.z, a.w);
-            const double sp = 0.30 + (0.32 - 0.30) * u53(c.x, c.y);
-            const double ang = 0.0 + (2.0 * 3.141592653589793 - 0.0) * u53(c.z, c.w);
-            I[i].vx = cos(ang) * sp;
-            I[i].vy = sin(ang) * sp;
-        }
-    }
     __syncwarp();
     if (chunk < tchunks) {
         // targets [32*chunk, 32*chunk+32): value by rank among the value keys (uav_env.py:121-129), list position
@@ -165,7 +168,7 @@ __device__ void warp_generate_chunk(const Params &P, int slot, int b, uint32_t s
             u.load = base_load * P.weather_load;                                      // :107
             const double ang = (-15.0 + (15.0 - (-15.0)) * u53(d.z, d.w)) * (3.141592653589793 / 180.0);  // :110
             const double vx = cos(ang) * real_speed, vy = sin(ang) * real_speed;      // :111
-            finish_uav(P, slot, b, u, vx, vy);
+            finish_uav(P, Z, I, u, vx, vy);
             P.uav[P.uoff(slot, b) + i] = u;
             P.uav_vel[P.uoff(slot, b) + i] = make_double2(vx, vy);
             P.uav_type[P.uoff(slot, b) + i] = type;
@@ -177,64 +180,114 @@ __device__ void warp_generate_chunk(const Params &P, int slot, int b, uint32_t s
 // whole scene in one go (reset(), and the fallback when the next scene was not pre-generated in time)
 __device__ __noinline__ void warp_generate_scene(const Params &P, int slot, int b, uint32_t scene, uint32_t *s_keys) {
     const int nchunks = scene_chunks(P);
-    for (int c = 0; c < nchunks; ++c) {
-        warp_generate_chunk(P, slot, b, scene, c, s_keys);
-        if (c == 0) __threadfence_block();  // obstacles visible to the UAV chunks of this warp
-    }
+    NfzRec *Z = P.nfz + ((size_t)slot * P.B + b) * P.K1;
+    IntRec *I = P.intc + ((size_t)slot * P.B + b) * P.K2;
+    warp_generate_obstacles(P, b, scene, Z, I);
+    __threadfence_block();  // obstacles visible to the UAV chunks of this warp
+    __syncwarp();
+    for (int c = 0; c < nchunks; ++c) warp_generate_chunk(P, slot, b, scene, c, s_keys, Z, I);
     warp_clear_allocation(P, slot, b, threadIdx.x & 31);
     __syncwarp();
 }
 
-// ---- pre-generation service: CTAs appended to the step grid (blockIdx >= main CTAs) ------------------
-// Every env always has its NEXT scene (index I_GEN >> 1) prepared in the slot it is not playing on.  The owner
-// bumps pregen_req[b] whenever that scene was consumed or invalidated; a service warp that finds
-// req != ack advances the env's job by ONE chunk per launch (a few microseconds, hidden behind the step),
-// and publishes I_NEXT_TAG = scene index + ack when the last chunk is in.  Single writer per word:
-// owner -> I_GEN, pregen_req; service -> I_JOB, I_NEXT_TAG, pregen_ack and the other slot's records.
-constexpr int kServiceEnvsPerWarp = 256;  // 32 lanes x 8 request bytes, scanned with one 8 B load per lane
+// ---- pre-generation service: the first CTAs of the step grid (blockIdx < service CTAs) -----------------------------
+// Every env always has its NEXT scene (index I_GEN >> 1) prepared in the slot it is not playing on, so that the
+// scheduled regeneration of main_train.py:79 is a slot flip for its owner: three header stores, NO fence and NO extra
+// load on the step's critical path.  That works because the service never acts on a request in the launch in which it
+// first sees it, and never publishes in a launch in which it still writes records - kernel boundaries do the ordering:
+//   a period = kServicePeriod launches, counted by every service CTA on its own (all counters are equal)
+//   launch 0            SCAN     each CTA reads I_GEN / I_NEXT_TAG of its 1024 envs; an env whose other slot does not hold
+//                                scene I_GEN >> 1 yet is appended to the period's queue (its I_GEN word is captured)
+//   launches 1..P-2     PROCESS  job j = (queue entry, chunk of 32 entities) -> warp j of the round; a warp re-generates the
+//                                few obstacles in its own shared-memory scratch, so jobs are independent and a whole batch
+//                                of scenes costs ONE chunk latency, hidden behind the step's main CTAs; jobs whose env has
+//                                moved on since the scan (I_GEN changed, or the scene was delivered by reset()) are dropped
+//   launch P-1          PUBLISH  entries with all chunks in: I_NEXT_TAG = scene index (I_GEN still unchanged)
+// Single writer per word: owner -> I_GEN; service -> I_NEXT_TAG, the queues and the other slot's records.  An owner that
+// sees the tag flips; its record reads are ordered after the service's writes by >= 1 kernel boundary.  Whatever is not
+// ready when an env needs it (RESET_EPISODES of a few steps) is generated in place by the owner's warp - same result.
+constexpr int kServicePeriod = 16;
+constexpr int kServiceEnvsPerCta = 1024;  // 128 threads x 8 envs
 
-__device__ __noinline__ void pregen_service(const Params &P, int service_cta, uint32_t *s_keys) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int base = (service_cta * kWarpsPerCta + warp) * kServiceEnvsPerWarp;
-    if (base >= P.B) return;
-    const int nchunks = scene_chunks(P);
-    // req/ack are padded to a multiple of kServiceEnvsPerWarp bytes, so the vector loads stay in bounds
-    const uint2 rq = *reinterpret_cast<const uint2 *>(P.pregen_req + base + lane * 8);
-    const uint2 ak = *reinterpret_cast<const uint2 *>(P.pregen_ack + base + lane * 8);
-    const uint64_t diff = ((uint64_t)(rq.y ^ ak.y) << 32) | (uint64_t)(rq.x ^ ak.x);
-    // ONE chunk of ONE env per warp and launch: bounded work, so the service never outlasts the step itself;
-    // whatever else is pending waits for the next launch (the scene is not needed for ~200 episodes)
-    int my_first = -1;
-#pragma unroll
-    for (int byte = 7; byte >= 0; --byte)
-        if (((diff >> (8 * byte)) & 0xffu) != 0u && base + lane * 8 + byte < P.B) my_first = byte;
-    const unsigned mask = __ballot_sync(kFullMask, my_first >= 0);
-    if (mask == 0u) return;
-    const int src = __ffs(mask) - 1;
-    const int byte = __shfl_sync(kFullMask, my_first, src);
-    const int eb = base + src * 8 + byte;
-    // the request value seen BEFORE I_GEN is read is the one acknowledged (a later bump stays pending)
-    const uint64_t rq64 = ((uint64_t)rq.y << 32) | (uint64_t)rq.x;
-    const uint8_t req = (uint8_t)__shfl_sync(kFullMask, (unsigned)((rq64 >> (8 * (byte & 7))) & 0xffu), src);
-    const Hdr h = P.header(eb);
-    __threadfence();                                        // acquire: I_GEN was written before the request became visible
-    const int gen = *(volatile int32_t *)&h.n(I_GEN);
-    const int job = *(volatile int32_t *)&h.n(I_JOB);
-    const int scene = gen >> 1, slot = (gen & 1) ^ 1;
-    const int done_chunks = (job >> 8) == scene ? (job & 0xff) : 0;       // a job for another scene is stale
-    __syncwarp();
-    if (done_chunks < nchunks) warp_generate_chunk(P, slot, eb, (uint32_t)scene, done_chunks, s_keys);
-    if (lane == 0) {
-        __threadfence();                                    // records before the job word / tag
-        if (done_chunks + 1 >= nchunks) {
-            h.n(I_JOB) = (scene << 8) | nchunks;
-            h.n(I_NEXT_TAG) = scene;
-            __threadfence();
-            P.pregen_ack[eb] = req;
-        } else {
-            h.n(I_JOB) = (scene << 8) | (done_chunks + 1);
-        }
+__device__ __noinline__ void pregen_service(const Params &P, int service_cta, int n_service, uint32_t *s_keys,
+                                            unsigned char *s_scratch) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ uint32_t s_tick;
+    __shared__ int s_n, s_base;
+    if (tid == 0) {
+        const uint32_t t = P.svc_ctr[service_cta];
+        P.svc_ctr[service_cta] = t + 1u;
+        s_tick = t;
+        s_n = 0;
     }
+    __syncthreads();
+    const uint32_t phase = s_tick % (uint32_t)kServicePeriod;
+    const int q = (int)((s_tick / (uint32_t)kServicePeriod) & 1u);
+    int32_t *const q_env = P.q_env + (size_t)q * P.B, *const q_gen = P.q_gen + (size_t)q * P.B;
+    int32_t *const q_done = P.q_done + (size_t)q * P.B;
+    const int nchunks = scene_chunks(P);
+    if (phase == 0u) {
+        // ---- SCAN: 8 consecutive envs per thread = one 32 B run of the I_GEN row and of the I_NEXT_TAG row of a tile
+        if (service_cta == 0 && tid == 0) P.q_count[q ^ 1] = 0u;   // the other queue is idle during this whole period
+        int *const s_list = reinterpret_cast<int *>(s_scratch);
+        const int e0 = service_cta * kServiceEnvsPerCta + tid * 8;
+        if (e0 < P.B) {
+            const Hdr h = P.header(e0);
+            const int4 g0 = *reinterpret_cast<const int4 *>(&h.n(I_GEN)), g1 = *reinterpret_cast<const int4 *>(&h.n(I_GEN) + 4);
+            const int4 t0 = *reinterpret_cast<const int4 *>(&h.n(I_NEXT_TAG)), t1 = *reinterpret_cast<const int4 *>(&h.n(I_NEXT_TAG) + 4);
+            const int gen[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const int tag[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (e0 + i < P.B && tag[i] != (gen[i] >> 1)) {
+                    const int at = atomicAdd(&s_n, 1);
+                    s_list[2 * at] = e0 + i;
+                    s_list[2 * at + 1] = gen[i];
+                }
+        }
+        __syncthreads();
+        const int n = s_n;
+        if (n == 0) return;
+        if (tid == 0) s_base = (int)atomicAdd(&P.q_count[q], (uint32_t)n);
+        __syncthreads();
+        for (int i = tid; i < n; i += blockDim.x) {
+            q_env[s_base + i] = s_list[2 * i];
+            q_gen[s_base + i] = s_list[2 * i + 1];
+            q_done[s_base + i] = 0;
+        }
+        return;
+    }
+    const int count = (int)P.q_count[q];
+    if (count == 0) return;
+    if (phase == (uint32_t)kServicePeriod - 1u) {
+        // ---- PUBLISH
+        for (int i = service_cta * blockDim.x + tid; i < count; i += n_service * blockDim.x) {
+            const int eb = q_env[i], gen = q_gen[i];
+            const Hdr h = P.header(eb);
+            if (q_done[i] == nchunks && h.n(I_GEN) == gen) h.n(I_NEXT_TAG) = gen >> 1;
+        }
+        return;
+    }
+    // ---- PROCESS, round phase-1: one (entry, chunk) job per warp
+    const long long job = (long long)(phase - 1u) * n_service * kWarpsPerCta + service_cta * kWarpsPerCta + warp;
+    if (job >= (long long)count * nchunks) return;
+    const int entry = (int)(job / nchunks), chunk = (int)(job % nchunks);
+    const int eb = q_env[entry], gen = q_gen[entry];
+    const Hdr h = P.header(eb);
+    if (*(volatile int32_t *)&h.n(I_GEN) != gen || *(volatile int32_t *)&h.n(I_NEXT_TAG) == (gen >> 1)) return;  // stale
+    const int scene = gen >> 1, slot = (gen & 1) ^ 1;
+    NfzRec *Z = reinterpret_cast<NfzRec *>(s_scratch + (size_t)warp * kServiceScratchPerWarp);
+    IntRec *I = reinterpret_cast<IntRec *>(Z + P.K1);
+    warp_generate_obstacles(P, eb, (uint32_t)scene, Z, I);
+    __syncwarp();
+    if (chunk == 0) {  // the records proper (scene readback)
+        NfzRec *Zg = P.nfz + ((size_t)slot * P.B + eb) * P.K1;
+        IntRec *Ig = P.intc + ((size_t)slot * P.B + eb) * P.K2;
+        for (int i = lane; i < P.K1; i += 32) Zg[i] = Z[i];
+        for (int i = lane; i < P.K2; i += 32) Ig[i] = I[i];
+    }
+    warp_generate_chunk(P, slot, eb, (uint32_t)scene, chunk, s_keys, Z, I);
+    if (lane == 0) atomicAdd(&q_done[entry], 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -322,17 +375,18 @@ __device__ __noinline__ void warp_regen_inline(const Params &P, unsigned mask, i
 }
 
 __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_constant__ Params P, const StepIO io,
-                                                               const int n_main) {
+                                                               const int n_service) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ __align__(128) float s_tile[kWarpsPerCta][32 * kObsFloats];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t *const s_keys = reinterpret_cast<uint32_t *>(s_dyn) + (size_t)warp * max(P.N, P.M);  // per-warp scratch
-    if ((int)blockIdx.x >= n_main) {  // service CTAs: prepare next scenes, off the step's critical path
-        pregen_service(P, (int)blockIdx.x - n_main, s_keys);
+    if ((int)blockIdx.x < n_service) {  // service CTAs: prepare next scenes, off the step's critical path
+        pregen_service(P, (int)blockIdx.x, n_service, s_keys, reinterpret_cast<unsigned char *>(&s_tile[0][0]));
         return;
     }
-    const int b0 = blockIdx.x * kStepThreads + warp * 32;   // first env of this warp
+    const int n_main = (int)gridDim.x - n_service;
+    const int b0 = ((int)blockIdx.x - n_service) * kStepThreads + warp * 32;   // first env of this warp
     const int b = b0 + lane;
     const bool live = b < P.B;
     const int bc = live ? b : P.B - 1;  // clamped index: idle tail lanes issue harmless loads
@@ -350,7 +404,7 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
     const double c_nhp = H.f(F_CUR_NHP), c_lock_cost = H.f(F_CUR_LOCK_COST), c_ucost = H.f(F_CUR_UCOST);
     const int c_lock_cnt = H.n(I_CUR_LOCK_CNT), c_tid = H.n(I_CUR_TID);
     const int episode_new = H.n(I_EPISODE) + 1;
-    const int gen = H.n(I_GEN);
+    const int gen = H.n(I_GEN), next_tag = H.n(I_NEXT_TAG);
     int slot = gen & 1;                                                  // storage slot of the current scene
     const bool was_finished = !P.auto_reset && H.n(I_FINISHED);
     const int64_t action = io.action_bytes == 8 ? static_cast<const int64_t *>(io.actions)[bc]
@@ -358,7 +412,6 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
     const uint32_t head_new = (head_old + 1u) % (uint32_t)kSeqLen;       // ring slot of this step's row
     // older rows of the window: ring tile [slot][feature pair][32 lanes] -> tile rows 0..3 (time order)
     float2 *const ring = P.ring(bc);
-#if !(UAV_ABL & 2)
 #pragma unroll
     for (int a = kSeqLen - 1; a >= 1; --a) {
         const uint32_t slot = (head_new + (uint32_t)(kSeqLen - a)) % (uint32_t)kSeqLen;
@@ -367,7 +420,6 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
 #pragma unroll
         for (int f = 0; f < kStateDim / 2; ++f) cp_async_8(dst + 2 * f, src + f * 32);
     }
-#endif
     if (tid == 0) {
         // arrive; the last CTA to have READ the head publishes the new one (kept on the device so that
         // CUDA-graph replays stay correct).  The increment depends on head_old, so the read is ordered first.
@@ -437,12 +489,11 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
             const int scene = gen >> 1;
             scene_totals(P, b, (uint32_t)scene, total_val, total_cost);
             H.f(F_TOTAL_VAL) = total_val; H.f(F_TOTAL_COST) = total_cost;
-            if (H.n(I_NEXT_TAG) == scene) slot ^= 1;        // the pre-generated scene: flip the storage slot
-            else inline_regen = true;                       // not there yet: generate in place (second pass)
-            __threadfence();                                // this step's accept store lands before the old slot is recycled
+            // the pre-generated scene: flip the storage slot (its records were written >= 1 launch ago) - or generate in
+            // place (second pass).  The service picks the new I_GEN up at its next scan: no fence, no request store.
+            if (next_tag == scene) slot ^= 1;
+            else inline_regen = true;
             H.n(I_GEN) = ((scene + 1) << 1) | slot;
-            __threadfence();
-            P.pregen_req[b] = (uint8_t)(P.pregen_req[b] + 1);  // ask the service for scene+1 in the other slot
         }
     }
     const bool soft = restarted && !inline_regen;
@@ -458,13 +509,8 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
             warp_regen_inline(P, regen_mask, b0, slot, gen >> 1, s_keys);
         }
         if (live && (pass == 0 ? (!done || soft) : inline_regen)) {
-#if UAV_ABL & 4
-            UavRec u; u.x = c_pf; u.y = c_pd; u.wx = 1.0; u.wy = 0.0; u.load = 0.9; u.cost = c_ucost; u.p_pen = 0.5; u.inv_speed = 2.0;
-            TgtRec t; t.x = 170.0 + c_value; t.y = 80.0; t.speed = 0.01; t.value = c_value; t.nh = c_nh; t.nh_pure = c_nhp; t.lock_cost = c_lock_cost; t.lock_cnt = c_lock_cnt; t.id = c_tid;
-#else
             const UavRec u = P.uav[P.uoff(slot, b) + k];
             TgtRec t = P.tgt[P.toff(slot, b) + m];   // sees this thread's own accept store on target m
-#endif
             if (soft) { t.nh = 1.0; t.nh_pure = 1.0; t.lock_cost = 0.0; t.lock_cnt = 0; }  // cleared below by the warp
             cp_async_wait_all();                        // ring rows have landed in the tile (gathers still in flight)
             const int nprev = age < kSeqLen - 1 ? age : kSeqLen - 1;
@@ -479,9 +525,6 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
             double pf, pd;
             float row[kStateDim];
             eval_pointer_pair(P, u, t, cost_sum, covered_val, total_cost, total_val, pf, pd, row);
-#if UAV_ABL & 8
-            if (pf == 123.456) {
-#endif
             store_current_pair(H, u, t, pf, pd);
             float2 *dsth = ring + head_new * (kStateDim / 2) * 32;
 #pragma unroll
@@ -490,9 +533,6 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
                 dsth[f * 32] = v;
                 *reinterpret_cast<float2 *>(tile + (kSeqLen - 1) * kStateDim + 2 * f) = v;
             }
-#if UAV_ABL & 8
-            }
-#endif
             H.n(I_K) = k; H.n(I_M) = m; H.n(I_NASSIGNED) = nA; H.n(I_NCOVERED) = n0; H.n(I_AGE) = nprev + 1;
             H.f(F_REV) = rev; H.f(F_COST_SUM) = cost_sum; H.f(F_COVERED_VAL) = covered_val;
             H.f(F_SUM_PD) = sum_pd; H.f(F_SUM_PF) = sum_pf;
@@ -517,8 +557,7 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
             float *dst = io.obs + (size_t)b0 * kObsFloats;
             const float *src = s_tile[warp];
             const uint32_t bytes = (uint32_t)nenv * kObsFloats * sizeof(float);
-            if (UAV_ABL & 2) {
-            } else if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0 && (bytes & 15u) == 0) {
+            if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0 && (bytes & 15u) == 0) {
                 if (lane == 0) { bulk_store(dst, src, bytes); bulk_store_wait_read(); }
             } else {  // ragged tail / unaligned caller buffer
                 for (int i = lane; i < nenv * kObsFloats; i += 32) dst[i] = src[i];
@@ -557,13 +596,13 @@ __global__ void __launch_bounds__(kResetThreads) reset_kernel(const __grid_const
                 scene_totals(P, b, (uint32_t)scene, tv, tc);
                 H.f(F_TOTAL_VAL) = tv; H.f(F_TOTAL_COST) = tc;
                 H.n(I_GEN) = ((scene + 1) << 1) | slot;
-                if (ahead) { H.n(I_NEXT_TAG) = scene + 1; H.n(I_JOB) = ((scene + 1) << 8) | scene_chunks(P); }
+                if (ahead) H.n(I_NEXT_TAG) = scene + 1;
             }
         } else if (mode == 2) {
             // injected scene (already packed into the current slot); prepare the generated scene that follows it
             if (ahead) {
                 warp_generate_scene(P, slot ^ 1, b, (uint32_t)(gen >> 1), s_keys);
-                if (lane == 0) { H.n(I_NEXT_TAG) = gen >> 1; H.n(I_JOB) = ((gen >> 1) << 8) | scene_chunks(P); }
+                if (lane == 0) H.n(I_NEXT_TAG) = gen >> 1;
             }
             warp_clear_allocation(P, slot, b, lane);
         } else {

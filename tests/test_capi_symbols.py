@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 20
     for name in names:
         assert hasattr(L, name), "libuavenv_b200.so does not export %s" % name
-    assert L.uavenv_abi_version() == 1
+    assert L.uavenv_abi_version() == 2
 
 
 def test_policy_library_exports_every_declared_symbol_and_is_tcgen05():

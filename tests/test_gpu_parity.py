@@ -433,3 +433,25 @@ def test_baseline_full_size_properties(name, B, N, M, steps):
     assert finished > 0
     assert env.recompute_objective() < 1e-9
     env.close(); shard.close()
+
+
+@pytest.mark.parametrize("B", [64, 301])
+def test_caller_obs_buffer_through_the_raw_c_abi(B):
+    """uavenv_step writes the windows into whatever device buffer the caller passes (include/uavenv_b200.h): through the
+    TMA bulk store (aligned tiles) or the plain-store tail (301 envs: the last tile is 13 x 280 B, not a multiple of 16)."""
+    ub = _ub()
+    import ctypes as C
+    cfg = ub.Config(COST_WEIGHT_OMEGA=0.5, RESET_EPISODES=3)
+    e1, e2 = ub.UAVEnvBatched(B, config=cfg, seed=11), ub.UAVEnvBatched(B, config=cfg, seed=11)
+    e1.reset(); e2.reset()
+    mine = torch.full((B, 5, 14), -7.0, device="cuda")
+    lib = ub.load_library()
+    for s in range(150):
+        a = e1.random_actions(s)
+        o1, r1, d1, _ = e1.step(a)
+        rc = lib.uavenv_step(e2._h, C.c_void_p(a.data_ptr()), C.c_void_p(mine.data_ptr()), C.c_void_p(e2.reward.data_ptr()),
+                             C.c_void_p(e2._done_u8.data_ptr()), None, None)
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert torch.equal(mine, o1) and torch.equal(e2.reward, r1)
+    e1.close(); e2.close()
