@@ -57,6 +57,10 @@ typedef struct uavenv_cfg {
     double uav_gen_x_lo, uav_gen_x_hi;             /* UAV_GEN_X_RANGE    :39 */
     double target_gen_x_lo, target_gen_x_hi;       /* TARGET_GEN_X_RANGE :40 */
     double intercept_rad;                          /* INTERCEPT_RAD      :50 */
+    double tie_band;          /* Eq.21 `new_r >= prev_r` (envs/uav_env.py:317) is decided from carried sums; when the two
+                                 rewards agree to within tie_band * max(|new_r|, |prev_r|) both are re-summed over the targets
+                                 in the reference's list order (uav_env.py:244-269) and THAT decides.  Default 1e-12 (the carried
+                                 sums are good to ~1e-14); a huge value takes the exact path always (tests) */
 } uavenv_cfg_t;
 
 /* Per-step diagnostics = the `info` dict of envs/uav_env.py:426-433, one value per env.

@@ -97,6 +97,8 @@ def lib():
         L.orc_batch_destroy.argtypes = [C.c_void_p]
         L.orc_batch_step_random.restype = C.c_double
         L.orc_batch_step_random.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32]
+        L.orc_batch_step_actions.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int32, dp, C.POINTER(C.c_uint8), ip, ip, ip, ip]
+        L.orc_batch_get_assigned.argtypes = [C.c_void_p, ip]
         L.orc_max_threads.restype = C.c_int32
         _lib = L
     return _lib
@@ -263,6 +265,22 @@ class OracleBatch:
 
     def step_random(self, step, action_seed=1):
         return lib().orc_batch_step_random(self._h, action_seed, step, self.threads)
+
+    def step_actions(self, actions):
+        """One reference-algorithm step of every env (auto-restart as main_train.py:79).  Returns per-env arrays
+        (reward f64, done, num_assigned, is_valid {-1,0,1}, uav_idx, target_idx) - pointers AFTER the restart."""
+        E = self.num_envs
+        a = np.ascontiguousarray(actions, np.int64)
+        out = (np.zeros(E), np.zeros(E, np.uint8), np.zeros(E, np.int32), np.zeros(E, np.int32), np.zeros(E, np.int32),
+               np.zeros(E, np.int32))
+        lib().orc_batch_step_actions(self._h, a.ctypes.data_as(C.POINTER(C.c_int64)), self.threads, _ptr(out[0]), _ptr(out[1]),
+                                     _ptr(out[2]), _ptr(out[3]), _ptr(out[4]), _ptr(out[5]))
+        return out
+
+    def assigned(self, num_uavs):
+        a = np.zeros((self.num_envs, num_uavs), np.int32)
+        lib().orc_batch_get_assigned(self._h, _ptr(a.reshape(-1)))
+        return a
 
     def close(self):
         if self._h:

@@ -594,6 +594,36 @@ double orc_batch_step_random(orc_batch *B, uint64_t action_seed, uint64_t step, 
     return sum;
 }
 
+/* differential testing at scale: one reference-algorithm step of every env with GIVEN actions; per-env outputs.
+ * The state reported (uav_idx, target_idx, and orc_batch_get_assigned) is the state AFTER the step and after the
+ * main_train.py:79 restart of finished envs - what the batched GPU env holds after its step. */
+void orc_batch_step_actions(orc_batch *B, const int64_t *actions, int32_t threads, double *reward, uint8_t *done,
+                            int32_t *num_assigned, int32_t *is_valid, int32_t *uav_idx, int32_t *target_idx) {
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#pragma omp parallel for schedule(dynamic, 16)
+#endif
+    for (int32_t b = 0; b < B->E; ++b) {
+        float obs[ORC_SEQ_LEN * ORC_STATE_DIM];
+        int32_t dn, rows; orc_info info;
+        orc_env *e = B->envs[b];
+        orc_step(e, actions[b], obs, &rows, &reward[b], &dn, &info);
+        done[b] = (uint8_t)dn; num_assigned[b] = info.num_assigned; is_valid[b] = info.is_valid_action;
+        if (dn) {                                     /* main_train.py:79 schedule */
+            ++B->episode[b];
+            if (B->reset_episodes > 0 && B->episode[b] % (uint32_t)B->reset_episodes == 0)
+                orc_generate_scene(e, B->seed, (uint32_t)b, ++B->scene[b]);
+            orc_reset(e, obs);
+        }
+        uav_idx[b] = e->uav_idx; target_idx[b] = e->target_idx;
+    }
+    (void)threads;
+}
+
+void orc_batch_get_assigned(const orc_batch *B, int32_t *assigned /* [E][N] */) {
+    for (int32_t b = 0; b < B->E; ++b) orc_get_assigned(B->envs[b], assigned + (size_t)b * B->envs[b]->N);
+}
+
 int32_t orc_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

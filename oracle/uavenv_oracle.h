@@ -119,6 +119,9 @@ typedef struct orc_batch orc_batch;
 orc_batch *orc_batch_create(const orc_cfg *c, int32_t num_envs, uint64_t seed, int32_t reset_episodes, int32_t threads);
 void orc_batch_destroy(orc_batch *b);
 double orc_batch_step_random(orc_batch *b, uint64_t action_seed, uint64_t step, int32_t threads);
+void orc_batch_step_actions(orc_batch *b, const int64_t *actions, int32_t threads, double *reward, uint8_t *done,
+                            int32_t *num_assigned, int32_t *is_valid, int32_t *uav_idx, int32_t *target_idx);
+void orc_batch_get_assigned(const orc_batch *b, int32_t *assigned);
 int32_t orc_max_threads(void);
 
 #ifdef __cplusplus

@@ -27,7 +27,7 @@ class UavenvCfg(C.Structure):
                 ("map_width", C.c_double), ("map_height", C.c_double),
                 ("uav_gen_x_lo", C.c_double), ("uav_gen_x_hi", C.c_double),
                 ("target_gen_x_lo", C.c_double), ("target_gen_x_hi", C.c_double),
-                ("intercept_rad", C.c_double)]
+                ("intercept_rad", C.c_double), ("tie_band", C.c_double)]
 
 
 class UavenvInfo(C.Structure):

@@ -51,7 +51,7 @@ class Config:
     def as_dict(self):
         return {name: getattr(self, name) for name in _DEFAULTS}
 
-    def to_c(self, auto_reset=True):
+    def to_c(self, auto_reset=True, tie_band=1e-12):
         """uavenv_cfg_t (include/uavenv_b200.h) holding the constants of the rollout path."""
         from .._capi import UavenvCfg
         if self.STATE_DIM != 14 or self.SEQ_LEN != 5:
@@ -69,6 +69,7 @@ class Config:
         c.uav_gen_x_lo, c.uav_gen_x_hi = float(self.UAV_GEN_X_RANGE[0]), float(self.UAV_GEN_X_RANGE[1])
         c.target_gen_x_lo, c.target_gen_x_hi = float(self.TARGET_GEN_X_RANGE[0]), float(self.TARGET_GEN_X_RANGE[1])
         c.intercept_rad = float(self.INTERCEPT_RAD)
+        c.tie_band = float(tie_band)
         return c
 
 

@@ -74,6 +74,7 @@ extern "C" void uavenv_default_cfg(uavenv_cfg_t *c) {
     c->uav_gen_x_lo = 60.0; c->uav_gen_x_hi = 90.0;
     c->target_gen_x_lo = 160.0; c->target_gen_x_hi = 180.0;
     c->intercept_rad = 2.0;
+    c->tie_band = 1e-12;
 }
 
 extern "C" int uavenv_abi_version(void) { return UAVENV_ABI_VERSION; }
@@ -96,7 +97,7 @@ static int create_impl(uavenv *h) {
     P.B = h->B; P.N = c.num_uavs; P.M = c.num_targets; P.K1 = c.num_nfz; P.K2 = c.num_interceptors;
     P.reset_episodes = c.reset_episodes; P.auto_reset = c.auto_reset ? 1 : 0;
     P.zeta_d = c.param_zeta_d; P.inv_zeta_d = 1.0 / c.param_zeta_d; P.k = c.param_k; P.c1 = c.param_c1; P.c2 = c.param_c2; P.c3 = c.param_c3;
-    P.c4 = c.param_c4; P.omega = c.cost_weight_omega;
+    P.c4 = c.param_c4; P.omega = c.cost_weight_omega; P.tie_band = c.tie_band;
     P.weather_speed = c.weather_speed_factor; P.weather_load = c.weather_load_factor;
     P.map_w = c.map_width; P.map_h = c.map_height;
     P.uav_x_lo = c.uav_gen_x_lo; P.uav_x_hi = c.uav_gen_x_hi;

@@ -99,7 +99,7 @@ __host__ __device__ __forceinline__ Hdr header_at(unsigned char *base, int b) {
 struct Params {
     int32_t B, N, M, K1, K2;
     int32_t reset_episodes, auto_reset;
-    double zeta_d, inv_zeta_d, k, c1, c2, c3, c4, omega;
+    double zeta_d, inv_zeta_d, k, c1, c2, c3, c4, omega, tie_band;
     double weather_speed, weather_load;
     double map_w, map_h, uav_x_lo, uav_x_hi, tgt_x_lo, tgt_x_hi, intercept_rad;
     uint32_t seed_lo, seed_hi;

@@ -348,6 +348,21 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 // (first episodes after a reset with a very short schedule) does the owner's warp generate it in place, in a
 // second pass of the evaluation loop (out of line, so nothing but a few scalars is live across the call).
 
+// Eq.21 near-tie (uav_env.py:317): r(X) and r(X') re-summed exactly as _calc_J_X does (uav_env.py:244-269): targets in
+// list order, one running fp64 sum; X' differs from X in target m's product (nh2) only.  One thread, rare, out of line.
+__device__ __noinline__ void exact_rewards(const Params &P, int slot, int b, int m, double nh2, double cost_sum, double cost2,
+                                           int n0, int n02, double &prev_r, double &new_r) {
+    const TgtRec *T = P.tgt + P.toff(slot, b);
+    double rev = 0.0, rev2 = 0.0;
+    for (int j = 0; j < P.M; ++j) {
+        const double nh = T[j].nh, value = T[j].value;
+        rev += (1.0 - nh) * value;                                    // :264-265
+        rev2 += (1.0 - (j == m ? nh2 : nh)) * value;
+    }
+    prev_r = paper_reward(rev - (P.omega * cost_sum), n0, P.M);       // :268, :287-291
+    new_r = paper_reward(rev2 - (P.omega * cost2), n02, P.M);
+}
+
 // restart bookkeeping of the finished envs in mask (their scene is in slot_of[lane]): stores only
 __device__ __noinline__ void warp_soft_reset(const Params &P, unsigned soft_mask, int b0, int my_slot) {
     const int lane = threadIdx.x & 31;
@@ -434,7 +449,7 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
     if (live) {
         double reward = 0.0;
         if (!was_finished) {
-            const double prev_r = paper_reward(rev - (P.omega * cost_sum), n0, M);      // :301
+            double prev_r = paper_reward(rev - (P.omega * cost_sum), n0, M);            // :301
             double cur_r = prev_r;
             bool advance_uav = false;
             if (action == 1) {                                                           // :306
@@ -443,7 +458,11 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
                 const double rev2 = rev + ((1.0 - nh2) - (1.0 - c_nh)) * c_value;
                 const double cost2 = cost_sum + c_ucost;
                 const int n02 = n0 + (c_lock_cnt == 0);
-                const double new_r = paper_reward(rev2 - (P.omega * cost2), n02, M);    // :313
+                double new_r = paper_reward(rev2 - (P.omega * cost2), n02, M);          // :313
+                // the carried sums differ from the reference's fresh sums by O(1e-14) relative: inside the tie band the
+                // decision (and the reward) come from the exact re-summation
+                if (fabs(new_r - prev_r) <= P.tie_band * fmax(fabs(new_r), fabs(prev_r)))
+                    exact_rewards(P, slot, b, m, nh2, cost_sum, cost2, n0, n02, prev_r, new_r);
                 if (new_r >= prev_r) {                                                   // :317 (Eq.21)
                     reward = new_r - prev_r;                                             // :321
                     cur_r = new_r;

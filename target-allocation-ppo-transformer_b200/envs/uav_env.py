@@ -52,7 +52,7 @@ class UAVEnvBatched:
     """
 
     def __init__(self, num_envs, device=None, seed=None, config=None, auto_reset=True, env_id_base=0,
-                 with_info=True):
+                 with_info=True, tie_band=1e-12):
         self._h = None
         if not torch.cuda.is_available():
             raise RuntimeError("UAVEnvBatched needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -71,7 +71,7 @@ class UAVEnvBatched:
         self.action_space = _Discrete(self.cfg.ACTION_DIM)
         self.observation_space = _Box((self.cfg.SEQ_LEN, self.cfg.STATE_DIM))
         self._lib = _capi.load()
-        ccfg = self.cfg.to_c(auto_reset=self.auto_reset)
+        ccfg = self.cfg.to_c(auto_reset=self.auto_reset, tie_band=tie_band)
         h = C.c_void_p()
         _capi.check(self._lib.uavenv_create(C.byref(ccfg), self.num_envs, self.device.index, self.seed,
                                             self.env_id_base, C.byref(h)))
