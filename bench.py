@@ -261,6 +261,7 @@ def measure_ppo(rank, local_rank, world, dev, B, T, K, W, with_clocks=True):
 def run_ppo(args):
     """--workload c4: the PPO record as the main JSON line."""
     import torch
+    import uavenv_b200  # noqa: F401  (registers the package under its importable name)
     from target_allocation_ppo_transformer_b200 import parallel
     if args.impl == "reference":
         if int(os.environ.get("RANK", 0)) == 0:

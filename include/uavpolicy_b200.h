@@ -5,9 +5,9 @@
  * step by PPOAgent.select_action (agents/ppo.py:52-62): for a batch of observation windows [B,5,14] it returns
  * the sampled action, its log-probability, the state value and the policy entropy.  All dense contractions run
  * on the 5th-generation tensor cores (tcgen05.mma, operands staged by TMA, fp32 accumulators in TMEM; bf16
- * operands) through CUTLASS/CuTe sm100 collectives instantiated in csrc/policy_gemm.cu; embedding, attention
- * over the 5-token window, residual + LayerNorm and the MLP heads + sampling are hand-written kernels
- * (csrc/policy_forward.cu).  Training (backward) stays on the fp32 PyTorch mirror of the network.
+ * operands) in hand-written kernels: the fused encoder blocks of csrc/policy_fused.cu (default) or one persistent
+ * TMA-fed GEMM launch per dense layer (csrc/policy_dense.cu) with separate embedding / attention / residual + LayerNorm
+ * kernels (csrc/policy_forward.cu).  No CUTLASS, cuBLAS or other library kernel is on the path.
  *
  * Conventions as in uavenv_b200.h: 0 on success, negative error code otherwise; d_ = device pointers; work is
  * enqueued on the caller's stream; a handle is not thread-safe; no CPU fallback.
@@ -94,6 +94,13 @@ int uavtrain_backward_heads(uavtrain_t *p, const float *d_dlogits, const float *
 int uavtrain_ppo_loss(uavtrain_t *p, const float *d_logits, const float *d_value, const int64_t *d_action, const float *d_old_logp,
                       const float *d_adv, const float *d_ret, const float *d_old_value, int32_t n, float eps_clip, float c_value,
                       float c_entropy, float *d_dlogits, float *d_dvalue, float *d_stats, void *stream);
+
+/* self-test of the hand-written dense-layer kernel (csrc/policy_dense.cu: persistent, TMA-fed tcgen05 GEMM with fused
+ * epilogues): d_out[M,N] (bf16, dense) = act(d_a[M,K] d_w[N,K]^T + d_bias[N]); bf16 row-major inputs, row stride lda of
+ * d_a (elements, multiple of 8); N in {64,128,256,384}, K a multiple of 64 <= 384, N*K*2 <= 96 KiB.  act: 0 identity,
+ * 1 ReLU, 2 ReLU backward (no bias; the product is zeroed where d_aux[M,N] (bf16, row stride ld_aux) is not > 0). */
+int uavpolicy_selftest_dense(const void *d_a, int64_t lda, const void *d_w, const float *d_bias, const void *d_aux,
+                             int64_t ld_aux, void *d_out, int32_t M, int32_t N, int32_t K, int32_t act, void *stream);
 
 /* self-test of the tcgen05 weight-gradient kernel (csrc/policy_wgrad.cu): d_dw[n_out,k_in] (f32) +=
  * dY[rows,n_out]^T X[rows,k_in]; bf16 row-major inputs with row strides ld_dy / ld_x (elements, multiples of 8);

@@ -21,18 +21,6 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
 
 
-def _cutlass_includes():
-    """CUTLASS / CuTe header trees vendored in site-packages (no /opt/cutlass in this image)."""
-    import site
-    for sp in site.getsitepackages():
-        for rel in ("flashinfer/data/cutlass", "tilelang/3rdparty/cutlass"):
-            base = os.path.join(sp, rel)
-            if os.path.isfile(os.path.join(base, "include", "cutlass", "gemm", "collective", "builders",
-                                           "sm100_umma_builder.inl")):
-                return ["-I", os.path.join(base, "include"), "-I", os.path.join(base, "tools", "util", "include")]
-    raise RuntimeError("no CUTLASS header tree with sm100 collectives found")
-
-
 # library -> [(source, extra flags, headers it depends on)].  The env kernels reproduce the reference's fp64
 # operation order: no FMA contraction there.
 LIBS = {
@@ -43,9 +31,7 @@ LIBS = {
         ("ppo_optim.cu", [], ["../../include/uavenv_b200.h"]),
     ],
     POLICY_LIB_PATH: [
-        ("policy_gemm.cu", "CUTLASS", ["policy_gemm.cuh", "policy_gemm_impl.cuh"]),
-        ("policy_gemm_wide.cu", "CUTLASS", ["policy_gemm.cuh", "policy_gemm_impl.cuh"]),
-        ("policy_gemm_drelu.cu", "CUTLASS", ["policy_gemm.cuh"]),
+        ("policy_dense.cu", [], ["policy_gemm.cuh", "tcgen05_util.cuh", "../../include/uavpolicy_b200.h"]),
         ("policy_forward.cu", [], ["policy_gemm.cuh", "policy_kernels.cuh", "policy_weights.cuh", "../../include/uavpolicy_b200.h"]),
         ("policy_train.cu", [], ["policy_gemm.cuh", "policy_kernels.cuh", "policy_weights.cuh", "../../include/uavpolicy_b200.h"]),
         ("policy_wgrad.cu", [], ["tcgen05_util.cuh", "policy_weights.cuh", "../../include/uavpolicy_b200.h"]),
@@ -92,15 +78,14 @@ def _unit_deps(src, headers):
 
 
 def _unit_flags(extra):
-    flags = (_cutlass_includes() + ["--expt-relaxed-constexpr"]) if extra == "CUTLASS" else list(extra)
-    return flags + os.environ.get("UAVENV_EXTRA_NVCC_FLAGS", "").split()
+    return list(extra) + os.environ.get("UAVENV_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _lib_digest(lib):
     deps, flags = [], []
     for src, extra, headers in LIBS[lib]:
         deps += _unit_deps(src, headers)
-        flags.append(extra if isinstance(extra, str) else " ".join(extra))
+        flags.append(" ".join(extra))
     return _digest(sorted(set(deps)), " ".join(ARCH + COMMON[:4] + flags) + os.environ.get("UAVENV_EXTRA_NVCC_FLAGS", ""))
 
 
@@ -153,7 +138,7 @@ def build(force=False, verbose=False, lib=None):
                 tmp_obj = "%s.%d.tmp" % (obj, os.getpid())
                 jobs.append((src, [nvcc] + ARCH + COMMON + flags + (["-Xptxas", "-v"] if verbose else []) + [
                     "-c", os.path.join(CSRC, src), "-o", tmp_obj], tmp_obj, obj, dg))
-            # the CUTLASS instantiations take minutes each: compile the translation units side by side
+            # compile the translation units side by side
             from concurrent.futures import ThreadPoolExecutor
             with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as pool:
                 results = list(pool.map(lambda j: (j, subprocess.run(j[1], capture_output=True, text=True)), jobs))

@@ -460,8 +460,10 @@ __global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_cons
                 const int n02 = n0 + (c_lock_cnt == 0);
                 double new_r = paper_reward(rev2 - (P.omega * cost2), n02, M);          // :313
                 // the carried sums differ from the reference's fresh sums by O(1e-14) relative: inside the tie band the
-                // decision (and the reward) come from the exact re-summation
-                if (fabs(new_r - prev_r) <= P.tie_band * fmax(fabs(new_r), fabs(prev_r)))
+                // decision (and the reward) come from the exact re-summation.  Only with a cost term: at omega = 0 an Assign
+                // can only grow one term of J and N0, so new_r >= prev_r holds under rounding in the reference's summation
+                // and in the carried one alike (and near-ties are the NORM there once a target's product has underflowed)
+                if (P.omega != 0.0 && fabs(new_r - prev_r) <= P.tie_band * fmax(fabs(new_r), fabs(prev_r)))
                     exact_rewards(P, slot, b, m, nh2, cost_sum, cost2, n0, n02, prev_r, new_r);
                 if (new_r >= prev_r) {                                                   // :317 (Eq.21)
                     reward = new_r - prev_r;                                             // :321
