@@ -42,9 +42,9 @@ POOL = 64                # pre-generated action vectors cycled through the timed
 L2_FLUSH_BYTES = 256 << 20
 
 # Algorithmic bytes per env-step of THIS design (DESIGN.md section 4.1 derives each term): io 38 (int64 action 8,
-# reward 4, done 1, info 25), header read 140 / write 124, window ring read 224 / write 56, window out 280,
+# reward 4, done 1, info 25), header read 144 / write 124, window ring read 224 / write 56, window out 280,
 # records of the new pointer pair 128, accept path (p = 1/2 under Bernoulli actions) 0.5 * (32 + 4).
-ALGO_BYTES_PER_ENV_STEP = 38 + 140 + 124 + 224 + 56 + 280 + 128 + 0.5 * (32 + 4)
+ALGO_BYTES_PER_ENV_STEP = 38 + 144 + 124 + 224 + 56 + 280 + 128 + 0.5 * (32 + 4)
 
 
 def survey_bytes(M):     # SURVEY.md §8d traffic model (re-sums J over all M targets every step)
@@ -362,8 +362,10 @@ def main():
             ev[i][1].record(stream)
         torch.cuda.synchronize(dev)
         parallel.barrier()
-        ms = sum(a.elapsed_time(b) for a, b in ev)
-        return parallel.reduce_scalar(ms, "max", dev)
+        per = sorted(a.elapsed_time(b) for a, b in ev)
+        timed.last_us = {"min": 1e3 * per[0], "median": 1e3 * per[len(per) // 2], "p90": 1e3 * per[(9 * len(per)) // 10],
+                         "max": 1e3 * per[-1]}                      # this rank's brackets (diagnostic)
+        return parallel.reduce_scalar(sum(per), "max", dev)
 
     graph_us = None
     if os.environ.get("UAVENV_BENCH_GRAPH"):
@@ -391,6 +393,7 @@ def main():
     # --- device-resident inputs: the fused kernel alone --------------------------------------------------
     sampler.mark_begin()
     ms_dev = timed(lambda i: env.step(pool[i % POOL]), W, K)
+    step_us = dict(timed.last_us)
     # the same bracket around a ~2 us kernel (the action generator): what the protocol itself costs per step
     ms_floor = timed(lambda i: env.random_actions(i, ACTION_SEED), 3, min(K, 50)) / min(K, 50)
     # --- end to end through the host-buffer entry point ----------------------------------------------------
@@ -434,7 +437,7 @@ def main():
                        if not args.no_flush else "NOT flushed (diagnostic)",
                        "timing": "CUDA events per step on the launching stream, summed; max over ranks",
                        "pair_evals_per_sec": value, "objective_drift_max_abs": drift,
-                       "bracket_floor_us": 1e3 * ms_floor,
+                       "bracket_floor_us": 1e3 * ms_floor, "step_bracket_us_rank0": step_us,
                        "parallelism": "env-sharded x%d, no rollout collective" % world},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "uavk::step_kernel",

@@ -478,8 +478,8 @@ static int score_matrix_impl(uavenv *h, OutT *pf, OutT *pd, void *stream) {
     if (!pf && !pd) return fail(h, UAVENV_EINVAL, "uavenv_score_matrix: both outputs NULL");
     if (!h->ready) return fail(h, UAVENV_ESTATE, "uavenv_score_matrix before reset()/load_scene()");
     CU_TRY(h, cudaSetDevice(h->device));
-    const size_t total = (size_t)h->B * h->P.N * h->P.M;
-    const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 32);
+    const size_t warps = (size_t)h->B * ((h->P.M + 31) / 32);          // one warp per (env, 32-target chunk)
+    const int grid = (int)std::min<size_t>((warps + 7) / 8, (size_t)148 * 32);
     score_matrix_kernel<OutT><<<grid, 256, 0, (cudaStream_t)stream>>>(h->P, pf, pd);
     return launch_check(h, "score_matrix_kernel");
 }

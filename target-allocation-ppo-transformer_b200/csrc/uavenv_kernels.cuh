@@ -718,22 +718,37 @@ __global__ void __launch_bounds__(kResetThreads) pack_scene_kernel(const __grid_
 }
 
 // ------------------------------------------------------------------------------------------------
-// Score matrix: one thread per (env, UAV, target) pair, target index fastest (coalesced stores).
+// Score matrix (main.py:38-45 over mechanics.py:167-181): p_final / p_damage [B,N,M].
+// A warp owns (env, chunk of 32 targets): lane = target (its x, y, speed stay in registers; stores are coalesced along
+// the target index), the loop runs over the env's UAVs, whose 64 B records arrive as warp-uniform loads.  Index
+// arithmetic and the header read happen once per warp, not once per pair: the first version (a thread per pair with
+// 64-bit div / mod and its own record loads) was ISSUE-bound - 81 % of the issue slots, fp64 pipe 47 % active
+// (profiles/r2_score_matrix_ncu.md).
 
 template <typename OutT>
 __global__ void __launch_bounds__(256) score_matrix_kernel(const __grid_constant__ Params P, OutT *p_final,
                                                             OutT *p_damage) {
-    const size_t total = (size_t)P.B * P.N * P.M;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const int m = (int)(idx % P.M);
-        const size_t bk = idx / P.M;  // b*N + k
-        const int b = (int)(bk / P.N), kk = (int)(bk % P.N);
+    const int lane = threadIdx.x & 31;
+    const int chunks = (P.M + 31) >> 5;
+    const long long items = (long long)P.B * chunks;
+    const long long wstride = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < items; w += wstride) {
+        const int b = (int)(w / chunks), m = (int)(w % chunks) * 32 + lane;
+        const bool ok = m < P.M;
         const int slot = P.header(b).n(I_GEN) & 1;
-        const UavRec u = P.uav[P.uoff(slot, b) + kk];
-        const TgtRec *t = P.tgt + P.toff(slot, b) + m;
-        const double pd = damage_prob(P, u, t->x, t->y, t->speed);
-        if (p_damage) p_damage[idx] = (OutT)pd;
-        if (p_final) p_final[idx] = (OutT)(pd * u.p_pen);
+        const TgtRec *t = P.tgt + P.toff(slot, b) + (ok ? m : P.M - 1);
+        const double tx = t->x, ty = t->y, ts = t->speed;
+        const UavRec *U = P.uav + P.uoff(slot, b);
+        const size_t out0 = (size_t)b * P.N * P.M + m;
+#pragma unroll 2
+        for (int k = 0; k < P.N; ++k) {
+            const UavRec u = U[k];                                    // warp-uniform address
+            const double pd = damage_prob(P, u, tx, ty, ts);
+            if (ok) {
+                if (p_damage) p_damage[out0 + (size_t)k * P.M] = (OutT)pd;
+                if (p_final) p_final[out0 + (size_t)k * P.M] = (OutT)(pd * u.p_pen);
+            }
+        }
     }
 }
 
