@@ -420,10 +420,10 @@ def main():
         per_launch_s = ms_dev * 1e-3 / K
         achieved = ALGO_BYTES_PER_ENV_STEP * B / per_launch_s / 1e9
         surv = survey_bytes(w["M"]) * B / per_launch_s / 1e9
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")))[args.workload][
-                "per_launch_total"]
+        traffic = traffic_src = None     # DRAM bytes per launch from the committed ncu capture of this command (ncu cannot run
+        try:                              # inside a timed run); null for workloads without a capture
+            rec = json.load(open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")))[args.workload]
+            traffic, traffic_src = rec["per_launch_total"], rec["source"]
         except Exception:
             pass
         out = {
@@ -440,7 +440,7 @@ def main():
                        "bracket_floor_us": 1e3 * ms_floor, "step_bracket_us_rank0": step_us,
                        "parallelism": "env-sharded x%d, no rollout collective" % world},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "uavk::step_kernel",
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": "uavk::step_kernel",
                          "bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650",
                          "survey_model": {"bytes_per_env_step": survey_bytes(w["M"]), "achieved": surv,

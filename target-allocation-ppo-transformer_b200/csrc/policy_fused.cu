@@ -381,8 +381,13 @@ int launch_fused_blocks(const float *d_obs, int B, const BlockW &actor, const He
                         const BlockW &critic, const HeadW &critic_head, __nv_bfloat16 *hh_critic, int *d_work_counter,
                         cudaStream_t stream) {
     const int items = 2 * ((B + kTileSamples - 1) / kTileSamples);
+    static int num_sms = 0;                       // one persistent CTA per SM of the device
+    if (num_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -2;
+    }
     if (cudaMemsetAsync(d_work_counter, 0, sizeof(int), stream) != cudaSuccess) return -2;
-    fused_block_kernel<<<items < 148 ? items : 148, kFusedThreads, kFusedSmem, stream>>>(
+    fused_block_kernel<<<items < num_sms ? items : num_sms, kFusedThreads, kFusedSmem, stream>>>(
         d_obs, B, actor, actor_head, hh_actor, critic, critic_head, hh_critic, d_work_counter);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
