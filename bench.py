@@ -342,29 +342,35 @@ def main():
     sink = torch.zeros(1, dtype=torch.int64, device=dev)
     stream = torch.cuda.current_stream(dev)
 
+    def flush_l2(i):
+        if args.no_flush:
+            return
+        if args.flush_mode in ("write+read", "write"):
+            flush.fill_(i & 0xff)      # L2 flush (256 MiB write), outside the bracket ...
+        if args.flush_mode in ("write+read", "read"):
+            sink.add_(sweep.sum())     # ... then a 256 MiB read sweep, so the timed kernel starts on a
+                                       # cold but CLEAN L2 and does not pay write-backs of the flush data
+        if args.flush_mode == "sleep":
+            torch.cuda._sleep(60000)   # diagnostic: GPU-side delay only (L2 stays warm, host runs ahead)
+
     def timed(step_fn, n_warm, n_timed):
-        for i in range(n_warm):
-            step_fn(i)
+        for i in range(n_warm):        # warm-up = the timed loop's exact sequence (flush, then step), untimed: the first
+            flush_l2(i)                # call of the flush ops allocates, which would otherwise stall the host inside the
+            step_fn(i)                 # first timed bracket and show up there as a ~100 us launch gap
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_timed)]
         parallel.barrier()
         torch.cuda.synchronize(dev)
         for i in range(n_timed):
-            if not args.no_flush:
-                if args.flush_mode in ("write+read", "write"):
-                    flush.fill_(i & 0xff)      # L2 flush (256 MiB write), outside the bracket ...
-                if args.flush_mode in ("write+read", "read"):
-                    sink.add_(sweep.sum())     # ... then a 256 MiB read sweep, so the timed kernel starts on a
-                                               # cold but CLEAN L2 and does not pay write-backs of the flush data
-                if args.flush_mode == "sleep":
-                    torch.cuda._sleep(60000)   # diagnostic: GPU-side delay only (L2 stays warm, host runs ahead)
+            flush_l2(i)
             ev[i][0].record(stream)
             step_fn(n_warm + i)
             ev[i][1].record(stream)
         torch.cuda.synchronize(dev)
         parallel.barrier()
-        per = sorted(a.elapsed_time(b) for a, b in ev)
+        raw = [a.elapsed_time(b) for a, b in ev]
+        per = sorted(raw)
         timed.last_us = {"min": 1e3 * per[0], "median": 1e3 * per[len(per) // 2], "p90": 1e3 * per[(9 * len(per)) // 10],
-                         "max": 1e3 * per[-1]}                      # this rank's brackets (diagnostic)
+                         "max": 1e3 * per[-1], "max_at_step": raw.index(per[-1])}   # this rank's brackets (diagnostic)
         return parallel.reduce_scalar(sum(per), "max", dev)
 
     graph_us = None

@@ -281,7 +281,7 @@ void full_layer(Ctx &c, const LayerW &L, const __nv_bfloat16 *X, int B, __nv_bfl
     uavpolicy *p = c.p;
     const int R = B * S;
     gemm(c, X, D, L.in_w, L.in_b, p->QKV, R, 3 * D, D, 0);
-    if (!c.rc) attn_full_kernel<<<(B * H * S + 255) / 256, 256, 0, c.s>>>(p->QKV, p->pad, B, p->ATT);
+    if (!c.rc) attn_full_kernel<<<(B + 7) / 8, 256, 0, c.s>>>(p->QKV, p->pad, B, p->ATT);
     gemm(c, p->ATT, D, L.out_w, L.out_b, p->T, R, D, D, 0);
     add_ln(c, X, D, p->T, L.n1_w, L.n1_b, R, p->Y);
     gemm(c, p->Y, D, L.l1_w, L.l1_b, p->Hf, R, FF, D, 1);

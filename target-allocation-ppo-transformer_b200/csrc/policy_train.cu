@@ -254,52 +254,63 @@ __global__ void __launch_bounds__(256) attn_bwd_last_kernel(const AttnBwdArgs a)
     store16(a.gq + b * a.q_stride + h * DH, dq);
 }
 
-// inner layer (five queries): a warp takes 6 (sample, head) pairs, lane = pair * 5 + token.  Pass 1: the lane is query
-// i = token (its softmax row, dS row and dQ).  The 5 x 5 p / dS blocks of a pair cross lanes through shared memory.
-// Pass 2: the lane is key j = token (dK_j, dV_j).
-constexpr int kPairsPerWarp = 6;
+// inner layer (five queries): warp = sample, lane = 4 feature dimensions of a head (policy_kernels.cuh: attn_full_kernel).
+// P is recomputed from Q, K; dP = dO V^T is a second folded 5 x 5 reduction; dS = P o (dP - rowsum(P o dP)) / 4; then
+// dQ = dS K, dK = dS^T Q, dV = P^T dO are plain 4-dimension FMAs per lane.  Every input row is loaded once (coalesced
+// 256 B per warp access) and every gradient row stored once.
 __global__ void __launch_bounds__(256, 2) attn_bwd_full_kernel(const AttnBwdArgs a) {
-    __shared__ float s_p[8][kPairsPerWarp][S][S], s_ds[8][kPairsPerWarp][S][S];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pr = lane / S, t = lane % S;
-    const int64_t pair = ((int64_t)blockIdx.x * 8 + warp) * kPairsPerWarp + pr;
-    const bool live = pr < kPairsPerWarp && pair < (int64_t)a.n * H;
-    const int64_t b = live ? pair / H : 0;
-    const int h = live ? (int)(pair % H) : 0;
-    if (live) {
-        float q[DH], go[DH], p[S], ds[S], dq[DH];
-        load16(a.q + (b * S + t) * a.q_stride + h * DH, q);
-        load16(a.gout + (b * S + t) * D + h * DH, go);
-        attn_row_grads(a, b, h, q, go, p, ds);
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int64_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < a.n; b += nwarps) {
+        Rows4 q, k, v, go;
 #pragma unroll
-        for (int e = 0; e < DH; ++e) dq[e] = 0.0f;
-#pragma unroll
-        for (int j = 0; j < S; ++j) {
-            float kk[DH];
-            load16(a.k + (b * S + j) * a.kv_stride + h * DH, kk);
-#pragma unroll
-            for (int e = 0; e < DH; ++e) dq[e] = fmaf(ds[j], kk[e], dq[e]);
-            s_p[warp][pr][t][j] = p[j];
-            s_ds[warp][pr][t][j] = ds[j];
+        for (int t = 0; t < S; ++t) {
+            q.t[t] = *reinterpret_cast<const uint2 *>(a.q + (b * S + t) * a.q_stride + lane * 4);
+            k.t[t] = *reinterpret_cast<const uint2 *>(a.k + (b * S + t) * a.kv_stride + lane * 4);
+            v.t[t] = *reinterpret_cast<const uint2 *>(a.v + (b * S + t) * a.kv_stride + lane * 4);
+            go.t[t] = *reinterpret_cast<const uint2 *>(a.gout + (b * S + t) * D + lane * 4);
         }
-        store16(a.gq + (b * S + t) * a.q_stride + h * DH, dq);
-    }
-    __syncwarp();
-    if (live) {
-        float dk[DH], dv[DH];
-#pragma unroll
-        for (int e = 0; e < DH; ++e) { dk[e] = 0.0f; dv[e] = 0.0f; }
+        float p[S][S], ds[S][S];
+        head_dots(q, k, p);
+        head_softmax(p, a.pad + b * S);
+        head_dots(go, v, ds);                                  // dP_ij = dO_i . v_j
 #pragma unroll
         for (int i = 0; i < S; ++i) {
-            float q[DH], go[DH];
-            load16(a.q + (b * S + i) * a.q_stride + h * DH, q);
-            load16(a.gout + (b * S + i) * D + h * DH, go);
-            const float dsi = s_ds[warp][pr][i][t], pi = s_p[warp][pr][i][t];
+            float dot = 0.0f;
 #pragma unroll
-            for (int e = 0; e < DH; ++e) { dk[e] = fmaf(dsi, q[e], dk[e]); dv[e] = fmaf(pi, go[e], dv[e]); }
+            for (int j = 0; j < S; ++j) dot = fmaf(p[i][j], ds[i][j], dot);
+#pragma unroll
+            for (int j = 0; j < S; ++j) ds[i][j] = p[i][j] * (ds[i][j] - dot) * 0.25f;
         }
-        store16(a.gk + (b * S + t) * a.kv_stride + h * DH, dk);
-        store16(a.gv + (b * S + t) * a.kv_stride + h * DH, dv);
+        {   // dQ_i = sum_j dS_ij k_j
+            float kf[S][4];
+#pragma unroll
+            for (int j = 0; j < S; ++j) unpack4f(k.t[j], kf[j]);
+#pragma unroll
+            for (int i = 0; i < S; ++i) {
+                float o[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+                for (int j = 0; j < S; ++j)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) o[e] = fmaf(ds[i][j], kf[j][e], o[e]);
+                *reinterpret_cast<uint2 *>(a.gq + (b * S + i) * a.q_stride + lane * 4) = pack4f(o);
+            }
+        }
+        {   // dK_j = sum_i dS_ij q_i ;  dV_j = sum_i p_ij dO_i
+            float qf[S][4], gf[S][4];
+#pragma unroll
+            for (int i = 0; i < S; ++i) { unpack4f(q.t[i], qf[i]); unpack4f(go.t[i], gf[i]); }
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                float dk[4] = {0.0f, 0.0f, 0.0f, 0.0f}, dv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+                for (int i = 0; i < S; ++i)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { dk[e] = fmaf(ds[i][j], qf[i][e], dk[e]); dv[e] = fmaf(p[i][j], gf[i][e], dv[e]); }
+                *reinterpret_cast<uint2 *>(a.gk + (b * S + j) * a.kv_stride + lane * 4) = pack4f(dk);
+                *reinterpret_cast<uint2 *>(a.gv + (b * S + j) * a.kv_stride + lane * 4) = pack4f(dv);
+            }
+        }
     }
 }
 
@@ -677,7 +688,7 @@ void full_layer_fwd(TCtx &c, const uavp::LayerW &L, const bf16 *X, int n, FullAc
     uavtrain *p = c.p;
     const int R = n * S;
     gemm(c, X, D, L.in_w, L.in_b, A.QKV, R, 3 * D, D, 0);
-    if (!c.rc) attn_full_kernel<<<(n * H * S + 255) / 256, 256, 0, c.s>>>(A.QKV, p->pad, n, A.ATT);
+    if (!c.rc) attn_full_kernel<<<std::min((n + 7) / 8, p->sms * 16), 256, 0, c.s>>>(A.QKV, p->pad, n, A.ATT);
     gemm(c, A.ATT, D, L.out_w, L.out_b, p->T, R, D, D, 0);
     add_ln(c, X, D, p->T, L.n1_w, L.n1_b, R, A.Y1, nullptr, 0, A.XH1, A.rstd1);
     gemm(c, A.Y1, D, L.l1_w, L.l1_b, A.Hf, R, FF, D, 1);
@@ -729,7 +740,7 @@ void full_layer_bwd(TCtx &c, const uavp::LayerW &L, const LayerT &T, const Layer
     gemm(c, p->dS1, D, T.out_t, nullptr, p->tmp, R, D, D, 0);                       // dATT
     if (!c.rc) {
         AttnBwdArgs a{A.QKV, A.QKV + D, A.QKV + 2 * D, p->tmp, p->dQKV, p->dQKV + D, p->dQKV + 2 * D, 3 * D, 3 * D, p->pad, n};
-        attn_bwd_full_kernel<<<(n * H + 8 * kPairsPerWarp - 1) / (8 * kPairsPerWarp), 256, 0, c.s>>>(a);
+        attn_bwd_full_kernel<<<std::min((n + 7) / 8, p->sms * 16), 256, 0, c.s>>>(a);
     }
     wgrad(c, p->dQKV, 3 * D, X, D, R, 3 * D, D, g + o.in_w, -1, g + o.in_b);                           // + bias gradient
     gemm(c, p->dQKV, 3 * D, T.in_t, nullptr, dXg, R, D, 3 * D, 0);

@@ -144,7 +144,7 @@ static int create_impl(uavenv *h) {
     CU_TRY(h, dev_alloc(h, &h->d_done, B));
     CU_TRY(h, dev_alloc(h, &h->d_scratch, 1));
     // per-warp scratch of the scene generator: max(N,M) sort keys, for the 4 warps of a CTA
-    h->reset_smem = (size_t)kWarpsPerCta * std::max(N, M) * sizeof(uint32_t);
+    h->reset_smem = (size_t)std::max(kWarpsPerCta, kResetThreads / 32) * std::max(N, M) * sizeof(uint32_t);
     if (h->reset_smem > 8 * 1024) {
         // process-wide function attributes: never lower what another handle (larger N, M) has already asked for
         static size_t attr_smem = 0;

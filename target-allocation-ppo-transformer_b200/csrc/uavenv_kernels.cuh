@@ -16,7 +16,10 @@
 
 namespace uavk {
 
-constexpr int kStepThreads = 128;          // envs per CTA in step_kernel (thread-per-env main phases)
+#ifndef UAV_STEP_THREADS
+#define UAV_STEP_THREADS 128
+#endif
+constexpr int kStepThreads = UAV_STEP_THREADS;   // envs per CTA in step_kernel (thread-per-env main phases)
 constexpr int kWarpsPerCta = kStepThreads / 32;
 constexpr int kResetThreads = 128;
 constexpr int kServiceScratchPerWarp = 32 * kObsFloats * 4;   // a service warp's obstacle scratch = its idle window tile (8960 B)
@@ -207,7 +210,7 @@ __device__ __noinline__ void warp_generate_scene(const Params &P, int slot, int 
 // sees the tag flips; its record reads are ordered after the service's writes by >= 1 kernel boundary.  Whatever is not
 // ready when an env needs it (RESET_EPISODES of a few steps) is generated in place by the owner's warp - same result.
 constexpr int kServicePeriod = 16;
-constexpr int kServiceEnvsPerCta = 1024;  // 128 threads x 8 envs
+constexpr int kServiceEnvsPerCta = kStepThreads * 8;  // every thread scans 8 envs
 
 __device__ __noinline__ void pregen_service(const Params &P, int service_cta, int n_service, uint32_t *s_keys,
                                             unsigned char *s_scratch) {
@@ -389,7 +392,7 @@ __device__ __noinline__ void warp_regen_inline(const Params &P, unsigned mask, i
     __threadfence_block();
 }
 
-__global__ void __launch_bounds__(kStepThreads, 4) step_kernel(const __grid_constant__ Params P, const StepIO io,
+__global__ void __launch_bounds__(kStepThreads, 512 / kStepThreads) step_kernel(const __grid_constant__ Params P, const StepIO io,
                                                                const int n_service) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ __align__(128) float s_tile[kWarpsPerCta][32 * kObsFloats];
