@@ -102,6 +102,13 @@ int uavtrain_ppo_loss(uavtrain_t *p, const float *d_logits, const float *d_value
 int uavpolicy_selftest_dense(const void *d_a, int64_t lda, const void *d_w, const float *d_bias, const void *d_aux,
                              int64_t ld_aux, void *d_out, int32_t M, int32_t N, int32_t K, int32_t act, void *stream);
 
+/* the same kernel with the residual + LayerNorm epilogue of a post-LN encoder layer (networks/transformer_net.py:34-43):
+ * d_out[M,128] = LayerNorm(d_x[M,128] + d_a[M,K] d_w[128,K]^T + d_bias) * d_gamma + d_beta (eps 1e-5), d_xhat[M,128] (bf16) =
+ * the normalised rows and d_rstd[M] (fp32) = 1/sigma, which the backward keeps.  d_x: bf16 with row stride ldx. */
+int uavpolicy_selftest_dense_ln(const void *d_a, int64_t lda, const void *d_w, const float *d_bias, const void *d_x, int64_t ldx,
+                                const float *d_gamma, const float *d_beta, void *d_out, void *d_xhat, float *d_rstd, int32_t M,
+                                int32_t K, void *stream);
+
 /* self-test of the tcgen05 weight-gradient kernel (csrc/policy_wgrad.cu): d_dw[n_out,k_in] (f32) +=
  * dY[rows,n_out]^T X[rows,k_in]; bf16 row-major inputs with row strides ld_dy / ld_x (elements, multiples of 8);
  * n_out % 128 == 0, k_in = 128 or 256.  d_dbias (optional, k_in = 128): d_dbias[n_out] += column sums of dY. */

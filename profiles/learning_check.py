@@ -14,6 +14,6 @@ for prec, graph in (("fused", True), ("tf32", False)):
     torch.manual_seed(0)
     hist = ub.train(num_envs=4096, horizon=32, iterations=40, verbose=False, seed=7, update_precision=prec, graph_update=graph)
     print(prec, "samples/s in the last iteration: %.3g" % hist[-1]["samples_per_sec"])
-    rows = [(h["iteration"], round(h["Avg_Reward"], 3), round(h["Avg_J_Val"], 3), round(h["Entropy"], 3), round(h["Loss_Critic"], 3)) for h in hist]
+    rows = [(h["iteration"], round(h["Avg_Reward"], 3), round(h["Avg_J_Value"], 3), round(h["Entropy"], 3), round(h["Loss_Critic"], 3)) for h in hist]
     for r in rows[::4] + [rows[-1]]:
         print("  ", r)

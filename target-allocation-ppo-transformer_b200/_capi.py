@@ -167,6 +167,7 @@ def load_policy():
     i64 = C.c_int64
     L.uavpolicy_selftest_wgrad.argtypes = [vp, i64, vp, i64, i32, i32, i32, vp, vp, vp]
     L.uavpolicy_selftest_dense.argtypes = [vp, i64, vp, vp, vp, i64, vp, i32, i32, i32, i32, vp]
+    L.uavpolicy_selftest_dense_ln.argtypes = [vp, i64, vp, vp, vp, i64, vp, vp, vp, vp, vp, i32, i32, vp]
     L.uavtrain_create.argtypes = [i32, i32, C.POINTER(vp)]
     L.uavtrain_destroy.argtypes = [vp]
     L.uavtrain_last_error.argtypes = [vp]
@@ -178,7 +179,7 @@ def load_policy():
     L.uavtrain_ppo_loss.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp]
     for name in ("uavpolicy_create", "uavpolicy_destroy", "uavpolicy_set_weights", "uavpolicy_get_action",
                  "uavpolicy_set_fused", "uavpolicy_selftest_gemm_tile", "uavpolicy_selftest_wgrad", "uavpolicy_selftest_dense",
-                 "uavtrain_create",
+                 "uavpolicy_selftest_dense_ln", "uavtrain_create",
                  "uavtrain_destroy", "uavtrain_forward", "uavtrain_backward", "uavtrain_forward_heads",
                  "uavtrain_backward_heads", "uavtrain_ppo_loss"):
         getattr(L, name).restype = C.c_int

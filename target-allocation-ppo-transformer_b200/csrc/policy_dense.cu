@@ -28,11 +28,13 @@ constexpr int kBoxBytes = 128 * 128;   // one [128 rows x 64 columns] bf16 box
 constexpr int kRing = 6;               // A boxes in flight
 constexpr int kMaxN = 384, kMaxK = 384;
 
-enum Act { kIdentity = 0, kRelu = 1, kDRelu = 2 };
+enum Act { kIdentity = 0, kRelu = 1, kDRelu = 2, kAddLN = 3 };
 
 struct DenseArgs {
     int M, N, K, act, ring;            // ring: A boxes in flight (<= kRing)
     const float *bias;                 // [N] or nullptr
+    const float *gamma, *beta;         // kAddLN: LayerNorm weight / bias [128]
+    float *rstd;                       // kAddLN: 1/sigma of every row [M]
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -51,12 +53,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *mbar) {
 }
 
 // shared memory: [W: K/64 boxes of N rows x 128 B][ring: g.ring boxes][staging: 2 boxes][aux: 2 boxes (kDRelu)][bias][barriers]
-// tm_aux (kDRelu only): the [M, N] bf16 tensor whose sign pattern masks the output (the forward's post-ReLU activations);
-// its [128 x 64] boxes are prefetched two output slabs ahead by the epilogue's elected thread.
+// tm_aux: kDRelu - the [M, N] bf16 tensor whose sign pattern masks the output (the forward's post-ReLU activations);
+// kAddLN (N = 128) - the residual x [M, 128]: the epilogue owns whole rows, so out = LayerNorm(x + A W^T + bias) * gamma + beta
+// (post-LN encoder layer, networks/transformer_net.py:34-43) is computed from the fp32 accumulator in three passes over
+// TMEM (mean, variance, outputs) and leaves through tm_d (out) and tm_d2 (the normalised row x^ the backward needs) + rstd.
+// The aux [128 x 64] boxes are prefetched two slabs ahead by the epilogue's elected thread.
 __global__ void __launch_bounds__(kThreads, 1) dense_kernel(const __grid_constant__ CUtensorMap tm_a,
                                                             const __grid_constant__ CUtensorMap tm_w,
                                                             const __grid_constant__ CUtensorMap tm_d,
-                                                            const __grid_constant__ CUtensorMap tm_aux, const DenseArgs g) {
+                                                            const __grid_constant__ CUtensorMap tm_aux,
+                                                            const __grid_constant__ CUtensorMap tm_d2, const DenseArgs g) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms are 1024 B aligned
     const int N = g.N, K = g.K, kboxes = K / 64;
@@ -66,7 +72,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(const __grid_constan
     const int ring = g.ring;
     unsigned char *s_stage = s_ring + ring * kBoxBytes;
     unsigned char *s_aux = s_stage + 2 * kBoxBytes;
-    float *s_bias = reinterpret_cast<float *>(s_aux + (g.act == kDRelu ? 2 * kBoxBytes : 0));
+    float *s_bias = reinterpret_cast<float *>(s_aux + (g.act >= kDRelu ? 2 * kBoxBytes : 0));
     uint64_t *full = reinterpret_cast<uint64_t *>(s_bias + kMaxN), *empty = full + kRing, *w_ready = empty + kRing;
     uint64_t *acc_full = w_ready + 1, *acc_empty = acc_full + 2, *aux_full = acc_empty + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(aux_full + 2);
@@ -79,6 +85,8 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(const __grid_constan
 
     if (warp == 1) tc::tmem_alloc(tmem_slot, tmem_cols);
     for (int i = tid; i < N; i += kThreads) s_bias[i] = g.bias ? g.bias[i] : 0.0f;
+    if (g.act == kAddLN)
+        for (int i = tid; i < 128; i += kThreads) { s_bias[128 + i] = g.gamma[i]; s_bias[256 + i] = g.beta[i]; }
     if (tid == 0) {
         for (int s = 0; s < kRing; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
         tc::mbar_init(w_ready, 1);
@@ -149,13 +157,81 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(const __grid_constan
             tc::mbar_expect_tx(&aux_full[seq & 1], kBoxBytes);
             tc::tma_load_2d(s_aux + (seq & 1) * kBoxBytes, &tm_aux, cc, ((int)blockIdx.x + tt * (int)gridDim.x) * 128, &aux_full[seq & 1]);
         };
-        if (g.act == kDRelu && et == 0) { prefetch_aux(0); prefetch_aux(1); }
+        if (g.act >= kDRelu && et == 0) { prefetch_aux(0); prefetch_aux(1); }
         for (int t = 0; t < my_tiles; ++t) {
             const int a = t % acc_stages, use = t / acc_stages;
             const int r0 = ((int)blockIdx.x + t * (int)gridDim.x) * 128;
             tc::mbar_wait(&acc_full[a], (uint32_t)(use & 1));
             tc::tc_fence_after();
             const uint32_t src = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * N);
+            if (g.act == kAddLN) {
+                // both residual slabs of this tile (aux buffer s holds slab 2 t + s)
+                tc::mbar_wait(&aux_full[0], (uint32_t)(t & 1));
+                tc::mbar_wait(&aux_full[1], (uint32_t)(t & 1));
+                // the whole row in registers: v = accumulator + bias + residual (ONE pass over TMEM and the residual boxes)
+                float v[128];
+#pragma unroll
+                for (int c32 = 0; c32 < 4; ++c32) {
+                    tc::tmem_ld32(src + (uint32_t)(c32 * 32), v + c32 * 32);
+                    const unsigned char *ab = s_aux + (c32 >> 1) * kBoxBytes + row * 128;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const uint4 rw = *reinterpret_cast<const uint4 *>(ab + ((((c32 & 1) * 4 + c) ^ (row & 7)) << 4));
+                        const uint32_t w4[4] = {rw.x, rw.y, rw.z, rw.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162 *>(&w4[e]);
+                            const int col = c32 * 32 + c * 8 + 2 * e;
+                            v[col] += s_bias[col] + __low2float(r2);
+                            v[col + 1] += s_bias[col + 1] + __high2float(r2);
+                        }
+                    }
+                }
+                float sum = 0.0f, sq = 0.0f;
+#pragma unroll
+                for (int i = 0; i < 128; ++i) sum += v[i];
+                const float mean = sum * (1.0f / 128.0f);
+#pragma unroll
+                for (int i = 0; i < 128; ++i) { v[i] -= mean; sq = fmaf(v[i], v[i], sq); }
+                const float rstd = rsqrtf(sq * (1.0f / 128.0f) + 1e-5f);
+                if (r0 + row < g.M) g.rstd[r0 + row] = rstd;
+#pragma unroll
+                for (int sl = 0; sl < 2; ++sl) {                 // one 64-column slab at a time: out -> staging box 0, x^ -> box 1
+                    if (stores > 0) {
+                        if (et == 0) bulk_wait_read<0>();
+                        named_bar_sync(1, 128);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        uint32_t py[4], px[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int col = sl * 64 + c * 8 + 2 * e;
+                            const float x0 = v[col] * rstd, x1 = v[col + 1] * rstd;
+                            const __nv_bfloat162 hx = __floats2bfloat162_rn(x0, x1);
+                            const __nv_bfloat162 hy = __floats2bfloat162_rn(fmaf(x0, s_bias[128 + col], s_bias[256 + col]),
+                                                                            fmaf(x1, s_bias[128 + col + 1], s_bias[256 + col + 1]));
+                            px[e] = *reinterpret_cast<const uint32_t *>(&hx);
+                            py[e] = *reinterpret_cast<const uint32_t *>(&hy);
+                        }
+                        const int off = row * 128 + ((c ^ (row & 7)) << 4);
+                        *reinterpret_cast<uint4 *>(s_stage + off) = make_uint4(py[0], py[1], py[2], py[3]);
+                        *reinterpret_cast<uint4 *>(s_stage + kBoxBytes + off) = make_uint4(px[0], px[1], px[2], px[3]);
+                    }
+                    tc::fence_async_smem();
+                    named_bar_sync(1, 128);
+                    if (et == 0) {
+                        tma_store_2d(&tm_d, s_stage, sl * 64, r0);
+                        tma_store_2d(&tm_d2, s_stage + kBoxBytes, sl * 64, r0);
+                    }
+                    ++stores;
+                }
+                if (et == 0) { prefetch_aux(2 * (t + 1)); prefetch_aux(2 * (t + 1) + 1); }   // (after the barrier: both boxes were read)
+                tc::tc_fence_before();
+                named_bar_sync(1, 128);
+                if (et == 0) mbar_arrive(&acc_empty[a]);
+                continue;
+            }
             for (int c0 = 0; c0 < N; c0 += 64, ++stores) {
                 unsigned char *stage = s_stage + (stores & 1) * kBoxBytes;
                 if (stores >= 2) {                               // the TMA store that last read this staging box is done with it
@@ -231,10 +307,10 @@ bool make_map(CUtensorMap *m, const void *base, int64_t ld, int64_t rows, int co
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-int ring_depth(int act) { return act == kDRelu ? 4 : kRing; }
+int ring_depth(int act) { return act >= kDRelu ? 4 : kRing; }
 
 size_t smem_bytes(int N, int K, int act) {
-    return (size_t)(K / 64) * N * 128 + (size_t)(ring_depth(act) + 2 + (act == kDRelu ? 2 : 0)) * kBoxBytes + kMaxN * sizeof(float) + 256 + 1024;
+    return (size_t)(K / 64) * N * 128 + (size_t)(ring_depth(act) + 2 + (act >= kDRelu ? 2 : 0)) * kBoxBytes + kMaxN * sizeof(float) + 256 + 1024;
 }
 
 int prepare() {
@@ -253,21 +329,26 @@ int prepare() {
 }
 
 int launch(const void *A, int64_t lda, const void *W, const float *bias, const void *aux, int64_t ld_aux, void *D, int M, int N, int K,
-           int act, cudaStream_t stream) {
+           int act, cudaStream_t stream, const float *gamma = nullptr, const float *beta = nullptr, void *xhat = nullptr,
+           float *rstd = nullptr) {
     if (M <= 0) return 0;
     // shapes of this network: N in {64, 128, 256, 384}, K a multiple of 64 up to 384, W <= 96 KB
     if (N % 64 || N > kMaxN || (N > 256 && N != 384) || K % 64 || K > kMaxK || (size_t)N * K * 2 > 96 * 1024 || lda % 8 || (aux && ld_aux % 8))
         return -1;
     if (prepare()) return -2;
-    if (act == kDRelu && (!aux || smem_bytes(N, K, act) > smem_bytes(kMaxN, 128, kIdentity))) return -1;
-    CUtensorMap tm_a, tm_w, tm_d, tm_aux;
+    if (act >= kDRelu && (!aux || smem_bytes(N, K, act) > smem_bytes(kMaxN, 128, kIdentity))) return -1;
+    if (act == kAddLN && (N != 128 || !gamma || !beta || !xhat || !rstd)) return -1;
+    CUtensorMap tm_a, tm_w, tm_d, tm_aux, tm_d2;
     if (!make_map(&tm_a, A, lda, M, K, 128) || !make_map(&tm_w, W, K, N, K, N > 256 ? 128 : N) || !make_map(&tm_d, D, N, M, N, 128)) return -3;
-    if (act == kDRelu) { if (!make_map(&tm_aux, aux, ld_aux, M, N, 128)) return -3; }
+    if (act >= kDRelu) { if (!make_map(&tm_aux, aux, ld_aux, M, N, 128)) return -3; }
     else tm_aux = tm_d;
+    if (act == kAddLN) { if (!make_map(&tm_d2, xhat, N, M, N, 128)) return -3; }
+    else tm_d2 = tm_d;
     DenseArgs g;
     g.M = M; g.N = N; g.K = K; g.act = act; g.ring = ring_depth(act); g.bias = bias;
+    g.gamma = gamma; g.beta = beta; g.rstd = rstd;
     const int tiles = (M + 127) / 128;
-    dense_kernel<<<tiles < g_sms ? tiles : g_sms, kThreads, smem_bytes(N, K, act), stream>>>(tm_a, tm_w, tm_d, tm_aux, g);
+    dense_kernel<<<tiles < g_sms ? tiles : g_sms, kThreads, smem_bytes(N, K, act), stream>>>(tm_a, tm_w, tm_d, tm_aux, tm_d2, g);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -285,11 +366,26 @@ int gemm_drelu(const void *A, int64_t lda, const void *W, const void *aux, int64
     return launch(A, lda, W, nullptr, aux, ld_aux, D, M, N, K, kDRelu, stream);
 }
 
+
+int gemm_add_ln(const void *A, int64_t lda, const void *W, const float *bias, const void *X, int64_t ldx, const float *gamma,
+                const float *beta, void *out, void *xhat, float *rstd, int M, int K, cudaStream_t stream) {
+    return launch(A, lda, W, bias, X, ldx, out, M, 128, K, kAddLN, stream, gamma, beta, xhat, rstd);
+}
+
 }  // namespace uavp
 
 // self-test hook: one dense product on caller-provided device buffers (act: 0 identity, 1 ReLU, 2 ReLU backward by d_aux)
 extern "C" int uavpolicy_selftest_dense(const void *d_a, int64_t lda, const void *d_w, const float *d_bias, const void *d_aux,
                                         int64_t ld_aux, void *d_out, int32_t M, int32_t N, int32_t K, int32_t act, void *stream) {
     if (act == 2) return uavp::gemm_drelu(d_a, lda, d_w, d_aux, ld_aux, d_out, M, N, K, nullptr, 0, (cudaStream_t)stream);
+    if (act == 3) return -1;   // residual + LayerNorm: uavpolicy_selftest_dense_ln
     return uavp::gemm_bias_act(d_a, lda, d_w, d_bias, d_out, M, N, K, act, nullptr, 0, (cudaStream_t)stream);
+}
+
+// self-test hook of the fused residual + LayerNorm epilogue: d_out = LayerNorm(d_x + d_a d_w^T + d_bias) * d_gamma + d_beta,
+// d_xhat = the normalised rows, d_rstd = 1/sigma (N = 128)
+extern "C" int uavpolicy_selftest_dense_ln(const void *d_a, int64_t lda, const void *d_w, const float *d_bias, const void *d_x,
+                                           int64_t ldx, const float *d_gamma, const float *d_beta, void *d_out, void *d_xhat,
+                                           float *d_rstd, int32_t M, int32_t K, void *stream) {
+    return uavp::gemm_add_ln(d_a, lda, d_w, d_bias, d_x, ldx, d_gamma, d_beta, d_out, d_xhat, d_rstd, M, K, (cudaStream_t)stream);
 }

@@ -15,5 +15,9 @@ int gemm_bias_act(const void *A, int64_t lda, const void *W, const float *bias, 
 // epilogue of the activation-gradient GEMM.
 int gemm_drelu(const void *A, int64_t lda, const void *W, const void *aux, int64_t ld_aux, void *D, int M, int N, int K, void *workspace,
                size_t workspace_bytes, cudaStream_t stream);
+// out[M,128] = LayerNorm(X[M,128] + A[M,K] W[128,K]^T + bias) * gamma + beta (eps 1e-5), plus what the backward keeps: the
+// normalised rows xhat (bf16 [M,128]) and rstd (fp32 [M]).  X: bf16 with row stride ldx (the residual stream).
+int gemm_add_ln(const void *A, int64_t lda, const void *W, const float *bias, const void *X, int64_t ldx, const float *gamma,
+                const float *beta, void *out, void *xhat, float *rstd, int M, int K, cudaStream_t stream);
 size_t gemm_workspace_bytes();
 }  // namespace uavp

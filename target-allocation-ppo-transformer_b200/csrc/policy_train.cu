@@ -642,6 +642,13 @@ void gemm(TCtx &c, const bf16 *A, int64_t lda, const bf16 *W, const float *bias,
     const int r = uavp::gemm_bias_act(A, lda, W, bias ? bias : c.p->zeros, Dst, M, N, K, relu, c.p->gemm_ws, uavp::gemm_workspace_bytes(), c.s);
     if (r) c.rc = tfail(c.p, -2, "tcgen05 GEMM (M=%d N=%d K=%d) failed with %d", M, N, K, r);
 }
+// out = LayerNorm(x + A W^T + bias) fused into the dense kernel's epilogue (policy_dense.cu), keeping x^ and 1/sigma
+void gemm_ln(TCtx &c, const bf16 *A, int64_t lda, const bf16 *W, const float *bias, const bf16 *x, int64_t xs, const float *g,
+             const float *b, int rows, int K, bf16 *out16, bf16 *xhat, float *rstd) {
+    if (c.rc) return;
+    const int r = uavp::gemm_add_ln(A, lda, W, bias, x, xs, g, b, out16, xhat, rstd, rows, K, c.s);
+    if (r) c.rc = tfail(c.p, -2, "tcgen05 GEMM + LayerNorm (M=%d K=%d) failed with %d", rows, K, r);
+}
 void wgrad(TCtx &c, const bf16 *dY, int64_t ld_dy, const bf16 *X, int64_t ld_x, int rows, int Nout, int Kin, float *dW,
            int nout_valid = -1, float *dbias = nullptr, int out_ld = 0, int kin_valid = 0) {
     if (c.rc) return;
@@ -678,8 +685,7 @@ void last_layer_fwd(TCtx &c, const uavp::LayerW &L, const bf16 *X, int n, LastAc
     gemm(c, X, D, L.in_w + D * D, L.in_b + D, A.KV, R, 2 * D, D, 0);
     gemm(c, Xl, (int64_t)S * D, L.in_w, L.in_b, A.Q, n, D, D, 0);
     if (!c.rc) attn_last_kernel<<<(n * H + 255) / 256, 256, 0, c.s>>>(A.Q, A.KV, p->pad, n, A.AL);
-    gemm(c, A.AL, D, L.out_w, L.out_b, p->T, n, D, D, 0);
-    add_ln(c, Xl, (int64_t)S * D, p->T, L.n1_w, L.n1_b, n, A.Y1, nullptr, 0, A.XH1, A.rstd1);
+    gemm_ln(c, A.AL, D, L.out_w, L.out_b, Xl, (int64_t)S * D, L.n1_w, L.n1_b, n, D, A.Y1, A.XH1, A.rstd1);
     gemm(c, A.Y1, D, L.l1_w, L.l1_b, A.Hs, n, FF, D, 1);
     gemm(c, A.Hs, FF, L.l2_w, L.l2_b, p->T2, n, D, FF, 0);
     add_ln(c, A.Y1, D, p->T2, L.n2_w, L.n2_b, n, feat16, feat, feat_stride, A.XH2, A.rstd2);
@@ -689,11 +695,9 @@ void full_layer_fwd(TCtx &c, const uavp::LayerW &L, const bf16 *X, int n, FullAc
     const int R = n * S;
     gemm(c, X, D, L.in_w, L.in_b, A.QKV, R, 3 * D, D, 0);
     if (!c.rc) attn_full_kernel<<<std::min((n + 7) / 8, p->sms * 16), 256, 0, c.s>>>(A.QKV, p->pad, n, A.ATT);
-    gemm(c, A.ATT, D, L.out_w, L.out_b, p->T, R, D, D, 0);
-    add_ln(c, X, D, p->T, L.n1_w, L.n1_b, R, A.Y1, nullptr, 0, A.XH1, A.rstd1);
+    gemm_ln(c, A.ATT, D, L.out_w, L.out_b, X, D, L.n1_w, L.n1_b, R, D, A.Y1, A.XH1, A.rstd1);
     gemm(c, A.Y1, D, L.l1_w, L.l1_b, A.Hf, R, FF, D, 1);
-    gemm(c, A.Hf, FF, L.l2_w, L.l2_b, p->T, R, D, FF, 0);
-    add_ln(c, A.Y1, D, p->T, L.n2_w, L.n2_b, R, A.Xout, nullptr, 0, A.XH2, A.rstd2);
+    gemm_ln(c, A.Hf, FF, L.l2_w, L.l2_b, A.Y1, D, L.n2_w, L.n2_b, R, FF, A.Xout, A.XH2, A.rstd2);
 }
 
 // ---- backward ----------------------------------------------------------------------------------------------

@@ -32,7 +32,7 @@ def test_policy_library_exports_every_declared_symbol_and_is_tcgen05():
     from target_allocation_ppo_transformer_b200 import _build, _capi
     L = _capi.load_policy()
     names = _declared("uavpolicy_b200.h", "uavpolicy|uavtrain")
-    assert len(names) == 17
+    assert len(names) == 18
     for name in names:
         assert hasattr(L, name), "libuavpolicy_b200.so does not export %s" % name
     sass = subprocess.run(["cuobjdump", "-sass", _build.POLICY_LIB_PATH], capture_output=True, text=True).stdout

@@ -47,3 +47,35 @@ def test_dense_kernel_matches_fp32_reference(M, N, K, act):
     assert bool((err <= tol).all()), (float(err.max()), int((err > tol).sum()))
     if act == 2:
         assert bool((out[aux.float() <= 0] == 0).all())
+
+
+@pytest.mark.parametrize("M,K,ldx", [(1000, 128, 128), (128 * 9 + 5, 256, 128), (70001, 128, 640), (1, 128, 128)])
+def test_dense_kernel_with_residual_layernorm_epilogue(M, K, ldx):
+    """out = LayerNorm(x + a W^T + b) * gamma + beta fused into the GEMM epilogue (post-LN encoder layer,
+    networks/transformer_net.py:34-43), with the normalised rows and 1/sigma the backward keeps."""
+    import uavenv_b200  # noqa: F401
+    from target_allocation_ppo_transformer_b200 import _capi
+    L = _capi.load_policy()
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.7).to(torch.bfloat16)
+    w = (torch.randn(128, K, device="cuda", generator=g) * 0.15).to(torch.bfloat16)
+    bias = torch.randn(128, device="cuda", generator=g) * 0.3
+    x_full = torch.randn(M, ldx, device="cuda", generator=g).to(torch.bfloat16)       # the residual is a strided view
+    gamma = 1.0 + 0.2 * torch.randn(128, device="cuda", generator=g)
+    beta = 0.3 * torch.randn(128, device="cuda", generator=g)
+    out = torch.full((M, 128), 7.0, device="cuda", dtype=torch.bfloat16)
+    xhat = torch.full((M, 128), 7.0, device="cuda", dtype=torch.bfloat16)
+    rstd = torch.full((M,), 7.0, device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr())
+    rc = L.uavpolicy_selftest_dense_ln(p(a), K, p(w), p(bias), p(x_full), ldx, p(gamma), p(beta), p(out), p(xhat), p(rstd), M, K, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    v = a.float() @ w.float().t() + bias + x_full[:, :128].float()
+    mean = v.mean(-1, keepdim=True)
+    var = ((v - mean) ** 2).mean(-1, keepdim=True)
+    r = torch.rsqrt(var + 1e-5)
+    xh = (v - mean) * r
+    ref = xh * gamma + beta
+    assert torch.allclose(rstd, r.squeeze(-1), rtol=2e-4, atol=1e-6)
+    assert bool(((xhat.float() - xh).abs() <= 1e-2 * xh.abs() + 1e-2).all())
+    assert bool(((out.float() - ref).abs() <= 1e-2 * ref.abs() + 2e-2).all())
