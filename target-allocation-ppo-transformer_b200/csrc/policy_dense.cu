@@ -8,9 +8,9 @@
 //     every A row is read exactly once and W (<= 96 KB) is loaded once per CTA and stays in shared memory;
 //   * warp-specialised: one thread streams [128 x 64] bf16 boxes of A into a 6-box ring with TMA tensor loads
 //     (128-byte swizzle; rows past M arrive as zeros), one thread issues tcgen05.mma.kind::f16 (M = 128, N <= 256 per
-//     instruction, K = 16; both operands K-major, 128B-swizzled shared-memory descriptors) into TMEM, four warps run the
-//     epilogue (tcgen05.ld -> bias / ReLU / mask -> bf16 -> swizzled staging tile -> TMA tensor store, which also clips the
-//     ragged last tile);
+//     instruction, K = 16; both operands K-major, 128B-swizzled shared-memory descriptors) into TMEM, eight warps run the
+//     epilogue - two per TMEM lane quadrant, each taking half of the columns (tcgen05.ld -> bias / ReLU / mask / residual +
+//     LayerNorm -> bf16 -> swizzled staging tile -> TMA tensor store, which also clips the ragged last tile);
 //   * the TMEM accumulator is double-buffered whenever 2 N <= 512 columns, so the MMAs of tile i+1 run under the
 //     epilogue of tile i; the staging tile is double-buffered against the TMA store.
 #include <cstdlib>
@@ -23,7 +23,8 @@
 namespace uavp {
 namespace {
 
-constexpr int kThreads = 192;          // warp 0: TMA producer, warp 1: MMA issuer (+ TMEM owner), warps 2-5: epilogue
+constexpr int kThreads = 320;          // warp 0: TMA producer, warp 1: MMA issuer (+ TMEM owner), warps 2-9: epilogue
+constexpr int kEpi = 256;              // epilogue threads: two warps per TMEM lane quadrant, each taking half of the columns
 constexpr int kBoxBytes = 128 * 128;   // one [128 rows x 64 columns] bf16 box
 constexpr int kRing = 6;               // A boxes in flight
 constexpr int kMaxN = 384, kMaxK = 384;
@@ -55,8 +56,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *mbar) {
 // shared memory: [W: K/64 boxes of N rows x 128 B][ring: g.ring boxes][staging: 2 boxes][aux: 2 boxes (kDRelu)][bias][barriers]
 // tm_aux: kDRelu - the [M, N] bf16 tensor whose sign pattern masks the output (the forward's post-ReLU activations);
 // kAddLN (N = 128) - the residual x [M, 128]: the epilogue owns whole rows, so out = LayerNorm(x + A W^T + bias) * gamma + beta
-// (post-LN encoder layer, networks/transformer_net.py:34-43) is computed from the fp32 accumulator in three passes over
-// TMEM (mean, variance, outputs) and leaves through tm_d (out) and tm_d2 (the normalised row x^ the backward needs) + rstd.
+// (post-LN encoder layer, networks/transformer_net.py:34-43) is computed from the fp32 accumulator held in registers (a
+// thread owns 64 columns of its row; the two halves exchange their partial sums through shared memory) and leaves through
+// tm_d (out) and tm_d2 (the normalised row x^ the backward needs) + rstd.
 // The aux [128 x 64] boxes are prefetched two slabs ahead by the epilogue's elected thread.
 __global__ void __launch_bounds__(kThreads, 1) dense_kernel(const __grid_constant__ CUtensorMap tm_a,
                                                             const __grid_constant__ CUtensorMap tm_w,
@@ -71,9 +73,10 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(const __grid_constan
     unsigned char *s_ring = s_w + kboxes * w_box;
     const int ring = g.ring;
     unsigned char *s_stage = s_ring + ring * kBoxBytes;
-    unsigned char *s_aux = s_stage + 2 * kBoxBytes;
+    unsigned char *s_aux = s_stage + (g.act == kAddLN ? 4 : 2) * kBoxBytes;
     float *s_bias = reinterpret_cast<float *>(s_aux + (g.act >= kDRelu ? 2 * kBoxBytes : 0));
-    uint64_t *full = reinterpret_cast<uint64_t *>(s_bias + kMaxN), *empty = full + kRing, *w_ready = empty + kRing;
+    float *s_part = s_bias + kMaxN;                              // kAddLN: [2 halves][128 rows] partial sums
+    uint64_t *full = reinterpret_cast<uint64_t *>(s_part + (g.act == kAddLN ? 256 : 0)), *empty = full + kRing, *w_ready = empty + kRing;
     uint64_t *acc_full = w_ready + 1, *acc_empty = acc_full + 2, *aux_full = acc_empty + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(aux_full + 2);
 
@@ -147,7 +150,8 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(const __grid_constan
             }
         }
     } else {                                                     // ---- epilogue: warp w owns TMEM lanes 32 * (w % 4) ..
-        const int q = warp & 3, et = tid - 64;                   // et: 0..127 among the epilogue threads
+        const int q = warp & 3, et = tid - 64;                   // et: 0..255 among the epilogue threads
+        const int half = (warp - 2) >> 2;                        // which 32 of a slab's 64 columns (kAddLN: which slab) it takes
         const int row = q * 32 + lane;                           // row of the tile = TMEM lane
         int stores = 0;
         const int spt = N / 64, total_slabs = my_tiles * spt;    // output slabs per tile / of this CTA
@@ -165,124 +169,120 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(const __grid_constan
             tc::tc_fence_after();
             const uint32_t src = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * N);
             if (g.act == kAddLN) {
-                // both residual slabs of this tile (aux buffer s holds slab 2 t + s)
-                tc::mbar_wait(&aux_full[0], (uint32_t)(t & 1));
-                tc::mbar_wait(&aux_full[1], (uint32_t)(t & 1));
-                // the whole row in registers: v = accumulator + bias + residual (ONE pass over TMEM and the residual boxes)
-                float v[128];
+                // this thread's half of the row (= residual slab `half`, aux buffer `half` holds slab 2 t + half) in registers:
+                // v = accumulator + bias + residual
+                tc::mbar_wait(&aux_full[half], (uint32_t)(t & 1));
+                float v[64];
 #pragma unroll
-                for (int c32 = 0; c32 < 4; ++c32) {
-                    tc::tmem_ld32(src + (uint32_t)(c32 * 32), v + c32 * 32);
-                    const unsigned char *ab = s_aux + (c32 >> 1) * kBoxBytes + row * 128;
+                for (int h = 0; h < 2; ++h) {
+                    tc::tmem_ld32(src + (uint32_t)(half * 64 + h * 32), v + h * 32);
+                    const unsigned char *ab = s_aux + half * kBoxBytes + row * 128;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        const uint4 rw = *reinterpret_cast<const uint4 *>(ab + ((((c32 & 1) * 4 + c) ^ (row & 7)) << 4));
+                        const uint4 rw = *reinterpret_cast<const uint4 *>(ab + (((h * 4 + c) ^ (row & 7)) << 4));
                         const uint32_t w4[4] = {rw.x, rw.y, rw.z, rw.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162 *>(&w4[e]);
-                            const int col = c32 * 32 + c * 8 + 2 * e;
-                            v[col] += s_bias[col] + __low2float(r2);
-                            v[col + 1] += s_bias[col + 1] + __high2float(r2);
+                            const int i = h * 32 + c * 8 + 2 * e;
+                            v[i] += s_bias[half * 64 + i] + __low2float(r2);
+                            v[i + 1] += s_bias[half * 64 + i + 1] + __high2float(r2);
                         }
                     }
                 }
                 float sum = 0.0f, sq = 0.0f;
 #pragma unroll
-                for (int i = 0; i < 128; ++i) sum += v[i];
-                const float mean = sum * (1.0f / 128.0f);
-#pragma unroll
-                for (int i = 0; i < 128; ++i) { v[i] -= mean; sq = fmaf(v[i], v[i], sq); }
-                const float rstd = rsqrtf(sq * (1.0f / 128.0f) + 1e-5f);
-                if (r0 + row < g.M) g.rstd[r0 + row] = rstd;
-#pragma unroll
-                for (int sl = 0; sl < 2; ++sl) {                 // one 64-column slab at a time: out -> staging box 0, x^ -> box 1
-                    if (stores > 0) {
-                        if (et == 0) bulk_wait_read<0>();
-                        named_bar_sync(1, 128);
-                    }
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        uint32_t py[4], px[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int col = sl * 64 + c * 8 + 2 * e;
-                            const float x0 = v[col] * rstd, x1 = v[col + 1] * rstd;
-                            const __nv_bfloat162 hx = __floats2bfloat162_rn(x0, x1);
-                            const __nv_bfloat162 hy = __floats2bfloat162_rn(fmaf(x0, s_bias[128 + col], s_bias[256 + col]),
-                                                                            fmaf(x1, s_bias[128 + col + 1], s_bias[256 + col + 1]));
-                            px[e] = *reinterpret_cast<const uint32_t *>(&hx);
-                            py[e] = *reinterpret_cast<const uint32_t *>(&hy);
-                        }
-                        const int off = row * 128 + ((c ^ (row & 7)) << 4);
-                        *reinterpret_cast<uint4 *>(s_stage + off) = make_uint4(py[0], py[1], py[2], py[3]);
-                        *reinterpret_cast<uint4 *>(s_stage + kBoxBytes + off) = make_uint4(px[0], px[1], px[2], px[3]);
-                    }
-                    tc::fence_async_smem();
-                    named_bar_sync(1, 128);
-                    if (et == 0) {
-                        tma_store_2d(&tm_d, s_stage, sl * 64, r0);
-                        tma_store_2d(&tm_d2, s_stage + kBoxBytes, sl * 64, r0);
-                    }
-                    ++stores;
-                }
-                if (et == 0) { prefetch_aux(2 * (t + 1)); prefetch_aux(2 * (t + 1) + 1); }   // (after the barrier: both boxes were read)
+                for (int i = 0; i < 64; ++i) sum += v[i];
+                s_part[half * 128 + row] = sum;
                 tc::tc_fence_before();
-                named_bar_sync(1, 128);
+                named_bar_sync(1, kEpi);                         // partial sums visible; every thread has read the accumulator
                 if (et == 0) mbar_arrive(&acc_empty[a]);
+                const float mean = (s_part[row] + s_part[128 + row]) * (1.0f / 128.0f);
+#pragma unroll
+                for (int i = 0; i < 64; ++i) { v[i] -= mean; sq = fmaf(v[i], v[i], sq); }
+                named_bar_sync(1, kEpi);                         // (the sums were read before they are overwritten)
+                s_part[half * 128 + row] = sq;
+                if (t > 0 && et == 0) bulk_wait_read<0>();       // the previous tile's stores have read the staging boxes
+                named_bar_sync(1, kEpi);
+                const float rstd = rsqrtf((s_part[row] + s_part[128 + row]) * (1.0f / 128.0f) + 1e-5f);
+                if (half == 0 && r0 + row < g.M) g.rstd[r0 + row] = rstd;
+                unsigned char *sy = s_stage + (2 * half) * kBoxBytes, *sx = sy + kBoxBytes;   // out / x^ boxes of this slab
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    uint32_t py[4], px[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int i = c * 8 + 2 * e, col = half * 64 + i;
+                        const float x0 = v[i] * rstd, x1 = v[i + 1] * rstd;
+                        const __nv_bfloat162 hx = __floats2bfloat162_rn(x0, x1);
+                        const __nv_bfloat162 hy = __floats2bfloat162_rn(fmaf(x0, s_bias[128 + col], s_bias[256 + col]),
+                                                                        fmaf(x1, s_bias[128 + col + 1], s_bias[256 + col + 1]));
+                        px[e] = *reinterpret_cast<const uint32_t *>(&hx);
+                        py[e] = *reinterpret_cast<const uint32_t *>(&hy);
+                    }
+                    const int off = row * 128 + ((c ^ (row & 7)) << 4);
+                    *reinterpret_cast<uint4 *>(sy + off) = make_uint4(py[0], py[1], py[2], py[3]);
+                    *reinterpret_cast<uint4 *>(sx + off) = make_uint4(px[0], px[1], px[2], px[3]);
+                }
+                tc::fence_async_smem();
+                named_bar_sync(1, kEpi);                         // staging boxes complete; both residual boxes have been read
+                if (et == 0) {
+                    tma_store_2d(&tm_d, s_stage, 0, r0);
+                    tma_store_2d(&tm_d2, s_stage + kBoxBytes, 0, r0);
+                    tma_store_2d(&tm_d, s_stage + 2 * kBoxBytes, 64, r0);
+                    tma_store_2d(&tm_d2, s_stage + 3 * kBoxBytes, 64, r0);
+                    prefetch_aux(2 * (t + 1)); prefetch_aux(2 * (t + 1) + 1);
+                }
                 continue;
             }
             for (int c0 = 0; c0 < N; c0 += 64, ++stores) {
                 unsigned char *stage = s_stage + (stores & 1) * kBoxBytes;
                 if (stores >= 2) {                               // the TMA store that last read this staging box is done with it
                     if (et == 0) bulk_wait_read<1>();
-                    named_bar_sync(1, 128);
+                    named_bar_sync(1, kEpi);
                 }
-                uint4 mask[8];
+                uint4 mask[4];
                 if (g.act == kDRelu) {                           // this slab's aux box (rows past M arrive as zeros: masked)
                     tc::mbar_wait(&aux_full[stores & 1], (uint32_t)((stores >> 1) & 1));
                     const unsigned char *ab = s_aux + (stores & 1) * kBoxBytes + row * 128;
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) mask[c] = *reinterpret_cast<const uint4 *>(ab + ((c ^ (row & 7)) << 4));
+                    for (int c = 0; c < 4; ++c) mask[c] = *reinterpret_cast<const uint4 *>(ab + (((half * 4 + c) ^ (row & 7)) << 4));
                 }
+                float v[32];
+                tc::tmem_ld32(src + (uint32_t)(c0 + half * 32), v);
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float v[32];
-                    tc::tmem_ld32(src + (uint32_t)(c0 + h * 32), v);
+                for (int c = 0; c < 4; ++c) {                    // 8 columns = one 16-byte chunk of the output row
+                    uint32_t pk[4];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {                // 8 columns = one 16-byte chunk of the output row
-                        uint32_t pk[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            float x0 = v[c * 8 + 2 * e] + s_bias[c0 + h * 32 + c * 8 + 2 * e];
-                            float x1 = v[c * 8 + 2 * e + 1] + s_bias[c0 + h * 32 + c * 8 + 2 * e + 1];
-                            if (g.act == kRelu) { x0 = fmaxf(x0, 0.0f); x1 = fmaxf(x1, 0.0f); }
-                            __nv_bfloat162 p2 = __floats2bfloat162_rn(x0, x1);
-                            pk[e] = *reinterpret_cast<uint32_t *>(&p2);
-                        }
-                        if (g.act == kDRelu) {
-                            const uint32_t *mw = reinterpret_cast<const uint32_t *>(&mask[h * 4 + c]);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {        // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-                                const uint32_t z = mw[e];
-                                const uint32_t lo_ok = ((z & 0x8000u) == 0u && (z & 0x7fffu) != 0u) ? 0xffffu : 0u;
-                                const uint32_t hi_ok = ((z & 0x80000000u) == 0u && (z & 0x7fff0000u) != 0u) ? 0xffff0000u : 0u;
-                                pk[e] &= (lo_ok | hi_ok);
-                            }
-                        }
-                        const int chunk = h * 4 + c;             // 128-byte swizzle: chunk index XOR (row mod 8)
-                        *reinterpret_cast<uint4 *>(stage + row * 128 + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    for (int e = 0; e < 4; ++e) {
+                        float x0 = v[c * 8 + 2 * e] + s_bias[c0 + half * 32 + c * 8 + 2 * e];
+                        float x1 = v[c * 8 + 2 * e + 1] + s_bias[c0 + half * 32 + c * 8 + 2 * e + 1];
+                        if (g.act == kRelu) { x0 = fmaxf(x0, 0.0f); x1 = fmaxf(x1, 0.0f); }
+                        __nv_bfloat162 p2 = __floats2bfloat162_rn(x0, x1);
+                        pk[e] = *reinterpret_cast<uint32_t *>(&p2);
                     }
+                    if (g.act == kDRelu) {
+                        const uint32_t *mw = reinterpret_cast<const uint32_t *>(&mask[c]);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {            // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+                            const uint32_t z = mw[e];
+                            const uint32_t lo_ok = ((z & 0x8000u) == 0u && (z & 0x7fffu) != 0u) ? 0xffffu : 0u;
+                            const uint32_t hi_ok = ((z & 0x80000000u) == 0u && (z & 0x7fff0000u) != 0u) ? 0xffff0000u : 0u;
+                            pk[e] &= (lo_ok | hi_ok);
+                        }
+                    }
+                    const int chunk = half * 4 + c;              // 128-byte swizzle: chunk index XOR (row mod 8)
+                    *reinterpret_cast<uint4 *>(stage + row * 128 + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
                 tc::fence_async_smem();
-                named_bar_sync(1, 128);                          // staging box complete; everyone has read this slab's aux box
+                named_bar_sync(1, kEpi);                         // staging box complete; everyone has read this slab's aux box
                 if (et == 0) {
                     tma_store_2d(&tm_d, stage, c0, r0);
                     if (g.act == kDRelu) prefetch_aux(stores + 2);
                 }
             }
             tc::tc_fence_before();
-            named_bar_sync(1, 128);                              // every epilogue thread has read this accumulator
+            named_bar_sync(1, kEpi);                             // every epilogue thread has read this accumulator
             if (et == 0) mbar_arrive(&acc_empty[a]);
         }
         if (et == 0) bulk_wait_all();
@@ -307,10 +307,11 @@ bool make_map(CUtensorMap *m, const void *base, int64_t ld, int64_t rows, int co
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-int ring_depth(int act) { return act >= kDRelu ? 4 : kRing; }
+int ring_depth(int act, int K) { return act == kAddLN ? (K > 128 ? 3 : 4) : (act == kDRelu ? 4 : kRing); }
 
 size_t smem_bytes(int N, int K, int act) {
-    return (size_t)(K / 64) * N * 128 + (size_t)(ring_depth(act) + 2 + (act >= kDRelu ? 2 : 0)) * kBoxBytes + kMaxN * sizeof(float) + 256 + 1024;
+    return (size_t)(K / 64) * N * 128 + (size_t)(ring_depth(act, K) + (act == kAddLN ? 4 : 2) + (act >= kDRelu ? 2 : 0)) * kBoxBytes +
+           (kMaxN + (act == kAddLN ? 256 : 0)) * sizeof(float) + 256 + 1024;
 }
 
 int prepare() {
@@ -345,7 +346,7 @@ int launch(const void *A, int64_t lda, const void *W, const float *bias, const v
     if (act == kAddLN) { if (!make_map(&tm_d2, xhat, N, M, N, 128)) return -3; }
     else tm_d2 = tm_d;
     DenseArgs g;
-    g.M = M; g.N = N; g.K = K; g.act = act; g.ring = ring_depth(act); g.bias = bias;
+    g.M = M; g.N = N; g.K = K; g.act = act; g.ring = ring_depth(act, K); g.bias = bias;
     g.gamma = gamma; g.beta = beta; g.rstd = rstd;
     const int tiles = (M + 127) / 128;
     dense_kernel<<<tiles < g_sms ? tiles : g_sms, kThreads, smem_bytes(N, K, act), stream>>>(tm_a, tm_w, tm_d, tm_aux, tm_d2, g);
