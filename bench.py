@@ -368,6 +368,8 @@ def main():
         torch.cuda.synchronize(dev)
         parallel.barrier()
         raw = [a.elapsed_time(b) for a, b in ev]
+        if os.environ.get("UAVENV_BENCH_DUMP") and rank == 0:       # diagnostic: every bracket of this rank, in order
+            print("brackets_us " + " ".join("%.1f" % (1e3 * x) for x in raw), file=sys.stderr)
         per = sorted(raw)
         timed.last_us = {"min": 1e3 * per[0], "median": 1e3 * per[len(per) // 2], "p90": 1e3 * per[(9 * len(per)) // 10],
                          "max": 1e3 * per[-1], "max_at_step": raw.index(per[-1])}   # this rank's brackets (diagnostic)
