@@ -53,7 +53,7 @@ def _digest(paths, extra=""):
     import hashlib
     h = hashlib.sha256(extra.encode())
     for p in paths:
-        h.update(p.encode())
+        h.update(os.path.relpath(p, ROOT).encode())      # relative: the tree is checked out at different places
         with open(p, "rb") as f:
             h.update(f.read())
     return h.hexdigest()
@@ -132,7 +132,7 @@ def build(force=False, verbose=False, lib=None):
                 obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
                 objs.append(obj)
                 flags = _unit_flags(extra)
-                dg = _digest(_unit_deps(src, headers), " ".join(ARCH + COMMON + flags))
+                dg = _digest(_unit_deps(src, headers), " ".join(ARCH + COMMON[:4] + flags))
                 if not force and _stamp_ok(obj, dg):
                     continue
                 tmp_obj = "%s.%d.tmp" % (obj, os.getpid())
