@@ -12,7 +12,8 @@
 //     epilogue - two per TMEM lane quadrant, each taking half of the columns (tcgen05.ld -> bias / ReLU / mask / residual +
 //     LayerNorm -> bf16 -> swizzled staging tile -> TMA tensor store, which also clips the ragged last tile);
 //   * the TMEM accumulator is double-buffered whenever 2 N <= 512 columns, so the MMAs of tile i+1 run under the
-//     epilogue of tile i; the staging tile is double-buffered against the TMA store.
+//     epilogue of tile i (N = 384: two single-buffered units of 256 + 128 columns, so that the next tile's first unit is
+//     computed while the second one is still being drained); the staging tile is double-buffered against the TMA store.
 #include <cstdlib>
 
 #include <cuda.h>
@@ -126,6 +127,38 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(const __grid_constan
             tc::mbar_wait(w_ready, 0);
             int it = 0;
             for (int t = 0; t < my_tiles; ++t) {
+                if (N > 256) {
+                    // N = 384 does not fit twice into the 512 TMEM columns: two single-buffered units instead, A = columns
+                    // 0..255 (one 256-wide instruction per k-step) and B = 256..383 (128-wide), each with its own full / empty
+                    // barrier pair - unit A of tile t+1 is computed while the epilogue still drains unit B of tile t
+                    const int it0 = it;
+                    if (t > 0) tc::mbar_wait(&acc_empty[0], (uint32_t)((t - 1) & 1));
+                    tc::tc_fence_after();
+                    for (int kb = 0; kb < kboxes; ++kb, ++it) {
+                        const int s = it % ring;
+                        tc::mbar_wait(&full[s], (uint32_t)((it / ring) & 1));
+                        tc::tc_fence_after();
+                        const uint32_t sa = tc::smem_u32(s_ring + s * kBoxBytes), sw = tc::smem_u32(s_w + kb * w_box);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            tc::mma_bf16(tmem, tc::smem_desc_sw128(sa + j * 32, 16, 1024), tc::smem_desc_sw128(sw + j * 32, 16, 1024),
+                                         idesc_lo, (kb > 0 || j > 0) ? 1u : 0u);
+                    }
+                    tc::mma_commit(&acc_full[0]);
+                    if (t > 0) tc::mbar_wait(&acc_empty[1], (uint32_t)((t - 1) & 1));
+                    tc::tc_fence_after();
+                    for (int kb = 0; kb < kboxes; ++kb) {
+                        const int s = (it0 + kb) % ring;
+                        const uint32_t sa = tc::smem_u32(s_ring + s * kBoxBytes), sw = tc::smem_u32(s_w + kb * w_box + 256 * 128);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            tc::mma_bf16(tmem + 256, tc::smem_desc_sw128(sa + j * 32, 16, 1024), tc::smem_desc_sw128(sw + j * 32, 16, 1024),
+                                         idesc_hi, (kb > 0 || j > 0) ? 1u : 0u);
+                        tc::mma_commit(&empty[s]);               // both passes have read the box
+                    }
+                    tc::mma_commit(&acc_full[1]);
+                    continue;
+                }
                 const int a = t % acc_stages;
                 const int use = t / acc_stages;                  // how often this accumulator has been used before
                 if (use > 0) tc::mbar_wait(&acc_empty[a], (uint32_t)((use - 1) & 1));
@@ -137,13 +170,9 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(const __grid_constan
                     tc::tc_fence_after();
                     const uint32_t sa = tc::smem_u32(s_ring + s * kBoxBytes), sw = tc::smem_u32(s_w + kb * w_box);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {                // K = 16 per instruction: 32 B further into the 128 B rows
-                        const uint64_t ad = tc::smem_desc_sw128(sa + j * 32, 16, 1024);
-                        tc::mma_bf16(d, ad, tc::smem_desc_sw128(sw + j * 32, 16, 1024), idesc_lo, (kb > 0 || j > 0) ? 1u : 0u);
-                        if (n_hi)
-                            tc::mma_bf16(d + 256, ad, tc::smem_desc_sw128(sw + 256 * 128 + j * 32, 16, 1024), idesc_hi,
-                                         (kb > 0 || j > 0) ? 1u : 0u);
-                    }
+                    for (int j = 0; j < 4; ++j)                  // K = 16 per instruction: 32 B further into the 128 B rows
+                        tc::mma_bf16(d, tc::smem_desc_sw128(sa + j * 32, 16, 1024), tc::smem_desc_sw128(sw + j * 32, 16, 1024), idesc_lo,
+                                     (kb > 0 || j > 0) ? 1u : 0u);
                     tc::mma_commit(&empty[s]);                   // frees the ring slot when these MMAs have read it
                 }
                 tc::mma_commit(&acc_full[a]);
@@ -163,10 +192,13 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(const __grid_constan
         };
         if (g.act >= kDRelu && et == 0) { prefetch_aux(0); prefetch_aux(1); }
         for (int t = 0; t < my_tiles; ++t) {
-            const int a = t % acc_stages, use = t / acc_stages;
+            const bool split = N > 256;                          // N = 384: units A (columns 0..255) and B (256..383), see the MMA issuer
+            const int a = split ? 0 : t % acc_stages, use = split ? t : t / acc_stages;
             const int r0 = ((int)blockIdx.x + t * (int)gridDim.x) * 128;
-            tc::mbar_wait(&acc_full[a], (uint32_t)(use & 1));
-            tc::tc_fence_after();
+            if (!split) {
+                tc::mbar_wait(&acc_full[a], (uint32_t)(use & 1));
+                tc::tc_fence_after();
+            }
             const uint32_t src = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * N);
             if (g.act == kAddLN) {
                 // this thread's half of the row (= residual slab `half`, aux buffer `half` holds slab 2 t + half) in registers:
@@ -236,6 +268,10 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(const __grid_constan
                 continue;
             }
             for (int c0 = 0; c0 < N; c0 += 64, ++stores) {
+                if (split && (c0 == 0 || c0 == 256)) {
+                    tc::mbar_wait(&acc_full[c0 >> 8], (uint32_t)(t & 1));
+                    tc::tc_fence_after();
+                }
                 unsigned char *stage = s_stage + (stores & 1) * kBoxBytes;
                 if (stores >= 2) {                               // the TMA store that last read this staging box is done with it
                     if (et == 0) bulk_wait_read<1>();
@@ -275,12 +311,15 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(const __grid_constan
                     *reinterpret_cast<uint4 *>(stage + row * 128 + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
                 tc::fence_async_smem();
+                tc::tc_fence_before();
                 named_bar_sync(1, kEpi);                         // staging box complete; everyone has read this slab's aux box
                 if (et == 0) {
                     tma_store_2d(&tm_d, stage, c0, r0);
                     if (g.act == kDRelu) prefetch_aux(stores + 2);
+                    if (split && (c0 == 192 || c0 == 320)) mbar_arrive(&acc_empty[c0 == 192 ? 0 : 1]);   // the unit is drained
                 }
             }
+            if (split) continue;
             tc::tc_fence_before();
             named_bar_sync(1, kEpi);                             // every epilogue thread has read this accumulator
             if (et == 0) mbar_arrive(&acc_empty[a]);
