@@ -435,17 +435,23 @@ extern "C" int uavenv_get_state(uavenv_t *h, uavenv_state_t *st, int32_t first_e
         if (st->scene_index) st->scene_index[i] = hv.n(I_GEN) >> 1;
         if (st->finished) st->finished[i] = (uint8_t)(hv.n(I_FINISHED) != 0);
         if (st->J_val) st->J_val[i] = hv.f(F_REV) - (P.omega * hv.f(F_COST_SUM));
+        // UAV slots at / past the decision pointer have not decided in this episode (a restart does not clear them)
+        if (st->assigned_target_id)
+            for (int32_t k = std::max(hv.n(I_K), 0); k < P.N; ++k) st->assigned_target_id[i * P.N + k] = -1;
     }
     if (st->lock_count || st->not_hit || st->not_hit_pure) {
         std::vector<TgtRec> T;
         for (int slot = 0; slot < 2; ++slot) {
             CU_TRY(h, fetch(T, P.tgt + ((size_t)slot * h->B + f) * P.M, c * P.M));
             for (size_t e = 0; e < c; ++e) {
-                if ((header_at(tiles.data(), (int)(f + e - t0 * 32)).n(I_GEN) & 1) != slot) continue;
+                const Hdr hv = header_at(tiles.data(), (int)(f + e - t0 * 32));
+                if ((hv.n(I_GEN) & 1) != slot) continue;
                 for (size_t j = e * P.M; j < (e + 1) * P.M; ++j) {
-                    if (st->lock_count) st->lock_count[j] = T[j].lock_cnt;
-                    if (st->not_hit) st->not_hit[j] = T[j].nh;
-                    if (st->not_hit_pure) st->not_hit_pure[j] = T[j].nh_pure;
+                    TgtRec t = T[j];                       // as the env sees it in its current episode
+                    const int cnt = target_view(t, hv.n(I_EPISODE));
+                    if (st->lock_count) st->lock_count[j] = cnt;
+                    if (st->not_hit) st->not_hit[j] = t.nh;
+                    if (st->not_hit_pure) st->not_hit_pure[j] = t.nh_pure;
                 }
             }
         }
@@ -462,11 +468,15 @@ extern "C" int uavenv_set_episode_counters(uavenv_t *h, const int32_t *h_episode
     const Params &P = h->P;
     CU_TRY(h, cudaSetDevice(h->device));
     CU_TRY(h, cudaDeviceSynchronize());
-    const size_t f = (size_t)first_env, c = (size_t)count, t0 = f / 32, t1 = (f + c + 31) / 32;
-    std::vector<unsigned char> tiles;
-    CU_TRY(h, fetch(tiles, P.hdr + t0 * kEnvTileBytes, (t1 - t0) * kEnvTileBytes));
-    for (size_t i = 0; i < c; ++i) header_at(tiles.data(), (int)(f + i - t0 * 32)).n(I_EPISODE) = h_episode[i];
-    CU_TRY(h, cudaMemcpy(P.hdr + t0 * kEnvTileBytes, tiles.data(), tiles.size(), cudaMemcpyHostToDevice));
+    int32_t *d_ep = nullptr;
+    CU_TRY(h, cudaMalloc(&d_ep, (size_t)count * sizeof(int32_t)));
+    cudaError_t e = cudaMemcpy(d_ep, h_episode, (size_t)count * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        set_episode_kernel<<<std::min((count + 7) / 8, 148 * 8), 256>>>(P, d_ep, first_env, count);
+        e = cudaDeviceSynchronize();
+    }
+    cudaFree(d_ep);
+    if (e != cudaSuccess) return fail(h, UAVENV_ECUDA, "uavenv_set_episode_counters: %s", cudaGetErrorString(e));
     return UAVENV_OK;
 }
 

@@ -34,10 +34,31 @@ struct __align__(64) TgtRec {  // envs/entities.py:39-49 + velocity norm (uav_en
     double nh;                 // sector 1: prod(1 - p_final) over the lock list  ("target health")
     double nh_pure;            //           prod(1 - p_damage)
     double lock_cost;          //           sum of costs of the UAVs locked on it (chi_mc numerator)
-    int32_t lock_cnt;          //           len(locked_by_uavs); covered ("kill flag") <=> lock_cnt > 0
+    int32_t lock_tag;          //           len(locked_by_uavs) (bits 0..13; covered ("kill flag") <=> count > 0) | episode tag
+                               //           (bits 14..31): the four dynamic fields are those of the env's CURRENT episode only
+                               //           if the tag matches it - otherwise they read as cleared (see target_view)
     int32_t id;                //           Target.id (list position != id after the shuffle, uav_env.py:173)
 };
 static_assert(sizeof(UavRec) == 64 && sizeof(TgtRec) == 64, "records must be one 64 B line half");
+
+// A restarted env (uav_env.py:175-182) does not touch its M target records: they carry the episode they were last
+// written in, and a record of another episode is read as cleared.  (Aliasing needs a record left untouched for 2^18
+// episodes; the step kernel wipes the arrays every 2^16 episodes, so it cannot happen.)
+constexpr int kTagShift = 14;
+constexpr uint32_t kEpochMask = 0x3ffffu;
+__host__ __device__ __forceinline__ int32_t make_tag(int count, int episode) {
+    return (int32_t)((uint32_t)count | (((uint32_t)episode & kEpochMask) << kTagShift));
+}
+__host__ __device__ __forceinline__ int tag_count(int32_t tag) { return (int)((uint32_t)tag & ((1u << kTagShift) - 1u)); }
+__host__ __device__ __forceinline__ bool tag_current(int32_t tag, int episode) {
+    return ((uint32_t)tag >> kTagShift) == ((uint32_t)episode & kEpochMask);
+}
+// the record as the env sees it in `episode`: returns the lock count, clears nh / nh_pure / lock_cost of a stale record
+__host__ __device__ __forceinline__ int target_view(TgtRec &t, int episode) {
+    if (tag_current(t.lock_tag, episode)) return tag_count(t.lock_tag);
+    t.nh = 1.0; t.nh_pure = 1.0; t.lock_cost = 0.0;
+    return 0;
+}
 
 struct NfzRec { double x, y, radius; };            // envs/entities.py:52-55
 struct IntRec { double x, y, vx, vy; };            // envs/entities.py:58-61 + velocity (uav_env.py:168)

@@ -66,7 +66,7 @@ __device__ __forceinline__ void warp_clear_allocation(const Params &P, int slot,
     for (int i = lane; i < P.N; i += 32) asg[i] = -1;
     TgtRec *T = P.tgt + P.toff(slot, b);
     for (int j = lane; j < P.M; j += 32) {
-        T[j].nh = 1.0; T[j].nh_pure = 1.0; T[j].lock_cost = 0.0; T[j].lock_cnt = 0;
+        T[j].nh = 1.0; T[j].nh_pure = 1.0; T[j].lock_cost = 0.0; T[j].lock_tag = 0;
     }
 }
 
@@ -148,7 +148,7 @@ __device__ void warp_generate_chunk(const Params &P, int slot, int b, uint32_t s
             const double vx = (u53(v.x, v.y) - 0.5) * 0.03, vy = (u53(v.z, v.w) - 0.5) * 0.03;  // :139
             t.speed = sqrt(vx * vx + vy * vy);
             t.value = value;
-            t.nh = 1.0; t.nh_pure = 1.0; t.lock_cost = 0.0; t.lock_cnt = 0; t.id = i;
+            t.nh = 1.0; t.nh_pure = 1.0; t.lock_cost = 0.0; t.lock_tag = 0; t.id = i;
             P.tgt[P.toff(slot, b) + pos] = t;
             P.tgt_vel[P.toff(slot, b) + pos] = make_double2(vx, vy);
         }
@@ -312,9 +312,10 @@ __device__ __forceinline__ void eval_pointer_pair(const Params &P, const UavRec 
 }
 
 // capture the new current pair in the header (the next step's accept rule reads only these)
-__device__ __forceinline__ void store_current_pair(const Hdr &h, const UavRec &u, const TgtRec &t, double pf, double pd) {
+// (t: the record as seen in the current episode, lock_cnt = target_view(t, episode))
+__device__ __forceinline__ void store_current_pair(const Hdr &h, const UavRec &u, const TgtRec &t, int lock_cnt, double pf, double pd) {
     h.f(F_CUR_PF) = pf; h.f(F_CUR_PD) = pd; h.f(F_CUR_VALUE) = t.value; h.f(F_CUR_NH) = t.nh; h.f(F_CUR_NHP) = t.nh_pure;
-    h.f(F_CUR_LOCK_COST) = t.lock_cost; h.f(F_CUR_UCOST) = u.cost; h.n(I_CUR_LOCK_CNT) = t.lock_cnt; h.n(I_CUR_TID) = t.id;
+    h.f(F_CUR_LOCK_COST) = t.lock_cost; h.f(F_CUR_UCOST) = u.cost; h.n(I_CUR_LOCK_CNT) = lock_cnt; h.n(I_CUR_TID) = t.id;
 }
 
 // ---- async copy / TMA helpers (sm_100a) --------------------------------------------------------------
@@ -353,12 +354,12 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 
 // Eq.21 near-tie (uav_env.py:317): r(X) and r(X') re-summed exactly as _calc_J_X does (uav_env.py:244-269): targets in
 // list order, one running fp64 sum; X' differs from X in target m's product (nh2) only.  One thread, rare, out of line.
-__device__ __noinline__ void exact_rewards(const Params &P, int slot, int b, int m, double nh2, double cost_sum, double cost2,
-                                           int n0, int n02, double &prev_r, double &new_r) {
+__device__ __noinline__ void exact_rewards(const Params &P, int slot, int b, int episode, int m, double nh2, double cost_sum,
+                                           double cost2, int n0, int n02, double &prev_r, double &new_r) {
     const TgtRec *T = P.tgt + P.toff(slot, b);
     double rev = 0.0, rev2 = 0.0;
     for (int j = 0; j < P.M; ++j) {
-        const double nh = T[j].nh, value = T[j].value;
+        const double nh = tag_current(T[j].lock_tag, episode) ? T[j].nh : 1.0, value = T[j].value;
         rev += (1.0 - nh) * value;                                    // :264-265
         rev2 += (1.0 - (j == m ? nh2 : nh)) * value;
     }
@@ -467,13 +468,13 @@ __global__ void __launch_bounds__(kStepThreads, 512 / kStepThreads) step_kernel(
                 // can only grow one term of J and N0, so new_r >= prev_r holds under rounding in the reference's summation
                 // and in the carried one alike (and near-ties are the NORM there once a target's product has underflowed)
                 if (P.omega != 0.0 && fabs(new_r - prev_r) <= P.tie_band * fmax(fabs(new_r), fabs(prev_r)))
-                    exact_rewards(P, slot, b, m, nh2, cost_sum, cost2, n0, n02, prev_r, new_r);
+                    exact_rewards(P, slot, b, episode_new - 1, m, nh2, cost_sum, cost2, n0, n02, prev_r, new_r);
                 if (new_r >= prev_r) {                                                   // :317 (Eq.21)
                     reward = new_r - prev_r;                                             // :321
                     cur_r = new_r;
                     TgtRec *tp = P.tgt + P.toff(slot, b) + m;
                     tp->nh = nh2; tp->nh_pure = c_nhp * (1.0 - c_pd);
-                    tp->lock_cost = c_lock_cost + c_ucost; tp->lock_cnt = c_lock_cnt + 1;
+                    tp->lock_cost = c_lock_cost + c_ucost; tp->lock_tag = make_tag(c_lock_cnt + 1, episode_new - 1);
                     P.assigned[(size_t)b * N + k] = c_tid;                               // :308
                     rev = rev2; cost_sum = cost2;
                     if (c_lock_cnt == 0) { covered_val += c_value; n0 = n02; }
@@ -482,7 +483,11 @@ __global__ void __launch_bounds__(kStepThreads, 512 / kStepThreads) step_kernel(
                 }
             }
             if (advance_uav) { k += 1; m = 0; }
-            else { m += 1; if (m >= M) { k += 1; m = 0; } }                              // :336-342, :347-352
+            else {                                                                       // :336-342, :347-352
+                m += 1;
+                // a UAV that passes every target stays unassigned: its slot may hold the previous episode's value
+                if (m >= M) { P.assigned[(size_t)b * N + k] = -1; k += 1; m = 0; }
+            }
             done = k >= N;                                                               // :355
             if (done) reward += cur_r;                                                   // :361-363
             if (io.is_valid) io.is_valid[b] = (action == 1) ? (reward != 0.0 ? 1 : 0) : -1;  // :429
@@ -521,12 +526,17 @@ __global__ void __launch_bounds__(kStepThreads, 512 / kStepThreads) step_kernel(
         }
     }
     const bool soft = restarted && !inline_regen;
+    // a restart leaves the allocation arrays alone: target records carry their episode (target_view) and UAV slots at or
+    // past the pointer are read as unassigned.  Every 2^16-th episode of an env the arrays are wiped, so that a record's
+    // 18-bit episode tag can never alias
+    const bool wipe = soft && (episode_new & 0xffff) == 0;
+    const int episode_eval = restarted ? episode_new : episode_new - 1;   // the episode the new pointer pair belongs to
 
     // ---- trip 2 + evaluation.  pass 0: every env but the (rare) inline-regenerated ones; pass 1: those ----
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
         if (pass == 1) {
-            const unsigned soft_mask = __ballot_sync(kFullMask, soft);
+            const unsigned soft_mask = __ballot_sync(kFullMask, wipe);
             if (soft_mask) warp_soft_reset(P, soft_mask, b0, slot);
             const unsigned regen_mask = __ballot_sync(kFullMask, inline_regen);
             if (regen_mask == 0u) break;
@@ -535,7 +545,7 @@ __global__ void __launch_bounds__(kStepThreads, 512 / kStepThreads) step_kernel(
         if (live && (pass == 0 ? (!done || soft) : inline_regen)) {
             const UavRec u = P.uav[P.uoff(slot, b) + k];
             TgtRec t = P.tgt[P.toff(slot, b) + m];   // sees this thread's own accept store on target m
-            if (soft) { t.nh = 1.0; t.nh_pure = 1.0; t.lock_cost = 0.0; t.lock_cnt = 0; }  // cleared below by the warp
+            const int t_cnt = target_view(t, episode_eval);   // (a restarted env sees every record as cleared)
             cp_async_wait_all();                        // ring rows have landed in the tile (gathers still in flight)
             const int nprev = age < kSeqLen - 1 ? age : kSeqLen - 1;
 #pragma unroll
@@ -549,7 +559,7 @@ __global__ void __launch_bounds__(kStepThreads, 512 / kStepThreads) step_kernel(
             double pf, pd;
             float row[kStateDim];
             eval_pointer_pair(P, u, t, cost_sum, covered_val, total_cost, total_val, pf, pd, row);
-            store_current_pair(H, u, t, pf, pd);
+            store_current_pair(H, u, t, t_cnt, pf, pd);
             float2 *dsth = ring + head_new * (kStateDim / 2) * 32;
 #pragma unroll
             for (int f = 0; f < kStateDim / 2; ++f) {
@@ -638,9 +648,9 @@ __global__ void __launch_bounds__(kResetThreads) reset_kernel(const __grid_const
             double pf, pd;
             float row[kStateDim];
             const UavRec u = P.uav[P.uoff(slot, b)];
-            const TgtRec t = P.tgt[P.toff(slot, b)];
+            const TgtRec t = P.tgt[P.toff(slot, b)];       // (just cleared)
             eval_pointer_pair(P, u, t, 0.0, 0.0, total_cost, total_val, pf, pd, row);
-            store_current_pair(H, u, t, pf, pd);
+            store_current_pair(H, u, t, 0, pf, pd);
             H.n(I_K) = 0; H.n(I_M) = 0; H.n(I_NASSIGNED) = 0; H.n(I_NCOVERED) = 0; H.n(I_AGE) = 1;
             H.f(F_REV) = 0.0; H.f(F_COST_SUM) = 0.0; H.f(F_COVERED_VAL) = 0.0;
             H.f(F_SUM_PD) = 0.0; H.f(F_SUM_PF) = 0.0;
@@ -708,7 +718,7 @@ __global__ void __launch_bounds__(kResetThreads) pack_scene_kernel(const __grid_
             const double vx = s.tgt_vx[g], vy = s.tgt_vy[g];
             t.speed = sqrt(vx * vx + vy * vy);
             t.value = s.tgt_value[g];
-            t.nh = 1.0; t.nh_pure = 1.0; t.lock_cost = 0.0; t.lock_cnt = 0; t.id = s.tgt_id[g];
+            t.nh = 1.0; t.nh_pure = 1.0; t.lock_cost = 0.0; t.lock_tag = 0; t.id = s.tgt_id[g];
             P.tgt[P.toff(slot, b) + j] = t;
             P.tgt_vel[P.toff(slot, b) + j] = make_double2(vx, vy);
             val_part += t.value;
@@ -771,13 +781,16 @@ __global__ void __launch_bounds__(256) recompute_kernel(const __grid_constant__ 
         int n0 = 0;
         const int slot = P.header(b).n(I_GEN) & 1;
         const TgtRec *T = P.tgt + P.toff(slot, b);
+        const int episode = P.header(b).n(I_EPISODE), kptr = P.header(b).n(I_K);
         for (int j = lane; j < P.M; j += 32) {
-            rev += (1.0 - T[j].nh) * T[j].value;
-            if (T[j].lock_cnt > 0) { cval += T[j].value; n0 += 1; }
+            TgtRec t = T[j];
+            const int cnt = target_view(t, episode);
+            rev += (1.0 - t.nh) * t.value;
+            if (cnt > 0) { cval += t.value; n0 += 1; }
         }
         const UavRec *U = P.uav + P.uoff(slot, b);
         const int32_t *asg = P.assigned + (size_t)b * P.N;
-        for (int i = lane; i < P.N; i += 32) if (asg[i] >= 0) cost += U[i].cost;
+        for (int i = lane; i < min(P.N, kptr); i += 32) if (asg[i] >= 0) cost += U[i].cost;   // slots at / past the pointer are stale
         for (int o = 16; o > 0; o >>= 1) {
             rev += __shfl_xor_sync(0xffffffffu, rev, o);
             cval += __shfl_xor_sync(0xffffffffu, cval, o);
@@ -795,6 +808,24 @@ __global__ void __launch_bounds__(256) recompute_kernel(const __grid_constant__ 
     if (lane == 0 && max_abs_diff && worst > 0.0) {
         // doubles >= 0 order like their bit patterns
         atomicMax(reinterpret_cast<unsigned long long *>(max_abs_diff), (unsigned long long)__double_as_longlong(worst));
+    }
+}
+
+// uavenv_set_episode_counters: the new counters, and the records written in an env's current episode follow it (their
+// episode tag is what makes them current).  One warp per env.
+__global__ void __launch_bounds__(256) set_episode_kernel(const __grid_constant__ Params P, const int32_t *episodes, int first_env,
+                                                           int count) {
+    const int lane = threadIdx.x & 31;
+    const int wglobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int e = wglobal; e < count; e += nwarps) {
+        const int b = first_env + e;
+        const Hdr h = P.header(b);
+        const int old_ep = h.n(I_EPISODE), new_ep = episodes[e];
+        TgtRec *T = P.tgt + P.toff(h.n(I_GEN) & 1, b);
+        for (int j = lane; j < P.M; j += 32)
+            if (tag_current(T[j].lock_tag, old_ep)) T[j].lock_tag = make_tag(tag_count(T[j].lock_tag), new_ep);
+        __syncwarp();
+        if (lane == 0) h.n(I_EPISODE) = new_ep;
     }
 }
 

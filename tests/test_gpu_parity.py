@@ -511,3 +511,42 @@ def test_decisions_match_the_oracle_at_scale_with_rollbacks(N, M, omega, steps):
             assert np.array_equal(st["assigned_target_id"], ob.assigned(N)), s
     assert n_rejected > B and n_done >= (B if M == 10 else 0)      # rollbacks really happened; episodes really ended
     ob.close(); env.close()
+
+
+def test_episode_tags_across_wipe_and_wrap_boundaries():
+    """A restart leaves the allocation arrays alone: target records carry an 18-bit episode tag and are wiped every 2^16-th
+    episode.  Envs whose counters start just below 65536 and 262144 (set right after the reset) must stay identical to the
+    oracle while they cross both boundaries - pointers, assignments, covered flags, rewards, windows."""
+    ub = _ub()
+    from oracle import oracle as orc
+    B, seed = 96, 9
+    cfg = ub.Config(NUM_UAVS=5, NUM_TARGETS=3, COST_WEIGHT_OMEGA=0.3, RESET_EPISODES=0)   # the scene stays: no schedule to align
+    env = ub.UAVEnvBatched(B, config=cfg, seed=seed)
+    obs = env.reset()
+    start = np.where(np.arange(B) % 3 == 0, 65530, np.where(np.arange(B) % 3 == 1, 262138, 1)).astype(np.int32)
+    env.set_episode_counters(start)
+    oenvs = _oracle_envs(cfg, B, seed)
+    for oe in oenvs:
+        oe.reset()
+    n_done = np.zeros(B, np.int64)
+    for s in range(400):
+        a = env.random_actions(s, action_seed=3)
+        a_h = a.cpu().numpy()
+        obs, reward, done, info = env.step(a)
+        o_h, r_h, d_h = obs.cpu().numpy(), info["reward_f64"].cpu().numpy(), done.cpu().numpy()
+        st = env.get_state()
+        for b, oe in enumerate(oenvs):
+            o_obs, o_r, o_done, o_info = oe.step(int(a_h[b]))
+            assert bool(d_h[b]) == o_done, (s, b)
+            rel_close(r_h[b], o_r, 1e-9, 1e-11)
+            if o_done:
+                n_done[b] += 1
+                o_obs = oe.reset()
+            assert st["uav_idx"][b] == oe.uav_idx and st["target_idx"][b] == oe.target_idx, (s, b)
+            assert np.array_equal(st["assigned_target_id"][b], oe.assigned()), (s, b)
+            assert np.array_equal(st["lock_count"][b] > 0, oe.covered().astype(bool)), (s, b)
+            rel_close(o_h[b], o_obs, RTOL32, ATOL32)
+        assert np.array_equal(st["episode"], start + n_done)
+    assert n_done.min() >= 20                                   # every env crossed its boundary (6 and 10 episodes away)
+    assert env.recompute_objective() < 1e-9
+    env.close()
