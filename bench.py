@@ -360,6 +360,10 @@ def main():
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_timed)]
         parallel.barrier()
         torch.cuda.synchronize(dev)
+        # lead-in: ~0.25 ms of untimed flush work queued ahead of the first bracket, so that the host (which comes out of
+        # the barrier late under torchrun) is enqueueing ahead of the GPU when bracket 0 opens - a bracket only measures
+        # the kernel if its launch is already waiting in the stream (without this, bracket 0 read 40-120 us at N > 1)
+        flush_l2(0); flush_l2(1)
         for i in range(n_timed):
             flush_l2(i)
             ev[i][0].record(stream)
