@@ -148,7 +148,10 @@ def load_policy():
     if _policy_lib is not None:
         return _policy_lib
     path = _build.POLICY_LIB_PATH
-    if not _build.up_to_date(path):
+    override = os.environ.get("UAVPOLICY_LIB_OVERRIDE")   # timing experiments only: a diagnostic build of the same ABI
+    if override:
+        path = override
+    elif not _build.up_to_date(path):
         try:
             _build.build(lib=path)
         except Exception as exc:

@@ -2,6 +2,7 @@
 #include "uavpolicy_b200.h"
 
 #include <cstdint>
+#include <cstdio>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -13,19 +14,36 @@ using namespace tc;
 using namespace uavp;
 
 // ------------------------------------------------------------------------------------------------------------
-// Fused encoder block.  One CTA (8 warps) owns a tile of 25 samples = 125 token rows (3 rows of padding make the
+// Fused encoder block.  One CTA (16 warps) owns a tile of 25 samples = 125 token rows (3 rows of padding make the
 // M = 128 of tcgen05.mma).  Activations never leave the SM: the layer input X lives in shared memory as a UMMA
-// A-operand (canonical K-major tile), each GEMM accumulates in TMEM, the epilogue threads (one per row: TMEM lane =
-// row) apply bias / ReLU / residual + LayerNorm entirely thread-locally and write the next A-operand back to shared
-// memory.  Weights stream L2 -> shared memory by warps 4-7 while warps 0-3 run the previous epilogue.
+// A-operand (canonical K-major tile), each GEMM accumulates in TMEM, the epilogue threads (FOUR per row: TMEM lane =
+// row, each thread a quarter of the columns - a warp can only read the 32 TMEM lanes of its quadrant, so the way to
+// put more threads on an epilogue is more warps per quadrant) apply bias / ReLU / residual + LayerNorm and write the
+// next A-operand back to shared memory.  Weights stream L2 -> shared memory by bulk TMA behind the running epilogue.
+// In the LAST layer of a network only the newest token of a sample is consumed (transformer_net.py:106): its attention
+// is evaluated for that query alone (a fifth of the CUDA-core work of the layer).
 //
-//   shared memory (224 KB):  sX 32 KB | sQ sK sV 3 x 32 KB (attention output overwrites Q; the FFN hidden tile
-//                            [128 x 256] later aliases sQ+sK) | sW 96 KB (one weight matrix at a time)
-//   TMEM: 512 columns; QKV uses [0,384), the other GEMMs [0,256) / [0,128) / [0,64)
-constexpr int kTileSamples = 25, kTileRows = kTileSamples * S;     // 125 valid rows of the 128
-constexpr int kFusedThreads = 256;
+//   shared memory (215 KB):  sX 32 KB | sQ sK sV 3 x 32 KB (attention output overwrites Q; the FFN hidden tile
+//                            [128 x 256] later aliases sQ+sK) | sW 64 KB (one weight matrix at a time; the QKV projection
+//                            arrives as Wq|Wk, then Wv) | 23 KB: every bias / LayerNorm / position vector of both networks,
+//                            staged once per CTA (they are warp-uniform operands of every epilogue: as global loads they
+//                            kept missing the 28 KB of L1 that is left and cost an L2 round trip per phase)
+//   TMEM: 512 columns; Q|K uses [0,256), V [256,384), the other GEMMs [0,256) / [0,128) / [0,64).  TMEM reads are
+//   64 B per cycle per SM, so reading a [128 x N] fp32 accumulator costs 8 N cycles - more than its MMAs (4.2 N): wherever
+//   a GEMM has independent column blocks (Q|K vs V, the two halves of the FFN hidden layer) the second block's MMAs run
+//   under the first block's epilogue.
+constexpr int kTileSamples = 25;                                   // 125 valid token rows of the 128
+constexpr int kFusedThreads = 512, kColParts = kFusedThreads / 128;   // column parts per row
 constexpr uint32_t kTileBytes = 128 * D * 2;                       // a [128 x 128] bf16 canonical tile
-constexpr size_t kFusedSmem = 4 * (size_t)kTileBytes + 96 * 1024;  // sX + sQ/sK/sV + sW
+// parameter vectors in shared memory (float offsets).  per network: emb_b | pos | layers | head b1
+constexpr int kPEmbB = 0, kPPos = D, kPLayer = D + S * D, kPLayerSize = 9 * D + FF;
+constexpr int kPInB = 0, kPOutB = 3 * D, kPN1W = 4 * D, kPN1B = 5 * D, kPL1B = 6 * D, kPL2B = 6 * D + FF, kPN2W = 7 * D + FF,
+              kPN2B = 8 * D + FF;
+constexpr int kPActor = 0, kPActorSize = kPLayer + 1 * kPLayerSize + HID, kPCritic = kPActorSize,
+              kPCriticSize = kPLayer + 2 * kPLayerSize + HID;
+static_assert(kPActorSize % 4 == 0 && kPLayer % 4 == 0 && kPLayerSize % 4 == 0, "16-byte loads of the staged vectors");
+constexpr uint32_t kWBytes = 64 * 1024;                            // sW: the largest block staged at once (Wq|Wk, W1, W2)
+constexpr size_t kFusedSmem = 4 * (size_t)kTileBytes + kWBytes + (size_t)(kPActorSize + kPCriticSize) * 4;
 
 struct Phase { uint32_t parity = 0; };
 
@@ -44,12 +62,11 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem, const unsigned char *s
     mma_commit(mbar);
 }
 
-__device__ __forceinline__ void unpack8(const uint4 &q, float *o) {
+__device__ __forceinline__ void unpack8(const uint4 &q, float *o) {   // bf16 -> fp32 is a 16-bit shift
     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162 *>(&w[i]);
-        o[2 * i] = __low2float(v); o[2 * i + 1] = __high2float(v);
+        o[2 * i] = __uint_as_float(w[i] << 16); o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
     }
 }
 __device__ __forceinline__ uint4 pack8(const float *v) {
@@ -62,99 +79,190 @@ __device__ __forceinline__ uint4 pack8(const float *v) {
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// Epilogues run on all 8 warps: warp w reads TMEM lanes 32*(w%4).. (its rows) and the column half w/4.
+// Epilogues run on all 16 warps: warp w reads TMEM lanes 32*(w%4).. (its rows) and the column quarter w/4.
+
+// phase timing of CTA 0 (diagnostic build -DUAVP_FUSED_TIMING only): cycles between the waits / barriers of a work item
+#ifdef UAVP_FUSED_TIMING
+struct TpLog { long long t[128]; const char *n[128]; int k; };
+#define TP_ARG , TpLog &tp
+#define TP_PASS , tp
+#define TP(name) do { if (threadIdx.x == 0 && blockIdx.x == 0 && tp.k < 128) { tp.t[tp.k] = clock64(); tp.n[tp.k] = name; ++tp.k; } } while (0)
+#else
+#define TP_ARG
+#define TP_PASS
+#define TP(name) do { } while (0)
+#endif
+
+// Column parameters (bias, gamma, beta) are the same for every row: warp-uniform (broadcast) loads from the staged copy in
+// shared memory, issued BEFORE the TMEM load (or the barrier) an epilogue has to wait for anyway; packed fp32x2 arithmetic.
+__device__ __forceinline__ void load_cols32(const float *p, float2 *o) {   // p: shared memory, 16 B aligned
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 q = reinterpret_cast<const float4 *>(p)[i];
+        o[2 * i] = make_float2(q.x, q.y); o[2 * i + 1] = make_float2(q.z, q.w);
+    }
+}
 
 // plain layer: out = act(acc + bias) -> bf16; column c goes to tile (c / tile_cols) of dst, canonical row length Kout
-__device__ __forceinline__ void epilogue_bias_act(uint32_t tmem_lane, int row, const float *__restrict__ bias, int c_begin,
-                                                  int c_end, bool relu, unsigned char *dst, int Kout, int tile_cols) {
+__device__ __forceinline__ void epilogue_bias_act(uint32_t tmem_lane, int row, const float *bias, int c_begin,
+                                                  int c_end, bool relu, unsigned char *dst, int Kout, int tile_cols TP_ARG) {
     for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+        float2 b[16];
+        load_cols32(bias + c0, b);
         float v[32];
         tmem_ld32(tmem_lane + c0, v);
+        TP("e.ld");
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {                       // (the flat parameter buffer is 8 B aligned at best)
-            const float2 b2 = __ldg(reinterpret_cast<const float2 *>(bias + c0 + i));
-            v[i] += b2.x; v[i + 1] += b2.y;
-            if (relu) { v[i] = fmaxf(v[i], 0.0f); v[i + 1] = fmaxf(v[i + 1], 0.0f); }
+        for (int i = 0; i < 16; ++i) {
+            float2 u = __fadd2_rn(make_float2(v[2 * i], v[2 * i + 1]), b[i]);
+            if (relu) { u.x = fmaxf(u.x, 0.0f); u.y = fmaxf(u.y, 0.0f); }
+            v[2 * i] = u.x; v[2 * i + 1] = u.y;
         }
+        TP("e.ma");
         unsigned char *tile = dst + (c0 / tile_cols) * kTileBytes;
 #pragma unroll
         for (int g = 0; g < 4; ++g)
             *reinterpret_cast<uint4 *>(tile + canon_off(row, (c0 % tile_cols) + g * 8, Kout)) = pack8(v + g * 8);
+        TP("e.st");
     }
 }
 
-// residual layer: X[row] <- LayerNorm(X[row] + acc + bias) * g + beta (post-LN, eps 1e-5), in place.  The two column
-// halves of a row exchange their partial sums through shared memory (all 256 threads call: contains a CTA barrier).
-__device__ __forceinline__ void epilogue_residual_ln(uint32_t tmem_lane, int row, int half, const float *__restrict__ bias,
-                                                     const float *__restrict__ g, const float *__restrict__ beta,
-                                                     unsigned char *sX, float (*s_part)[2][128]) {
-    float t[64];
-    float sum = 0.0f, sq = 0.0f;
+// residual layer: X[row] <- LayerNorm(X[row] + acc + bias) * g + beta (post-LN, eps 1e-5), in place.  The four column
+// quarters of a row exchange their partial sums through shared memory (all threads call: contains a CTA barrier).
+__device__ __forceinline__ void epilogue_residual_ln(uint32_t tmem_lane, int row, int part, const float *bias,
+                                                     const float *g, const float *beta,
+                                                     unsigned char *sX, float2 (*s_part)[128] TP_ARG) {
+    constexpr int W = D / kColParts;              // 32 columns per thread
+    static_assert(W == 32, "one tcgen05.ld of 32 columns per thread");
+    const int c0 = part * W;
+    float2 p[16];
+    load_cols32(bias + c0, p);
+    uint4 xr[4];
 #pragma unroll
-    for (int cc = 0; cc < 2; ++cc) {
-        const int c0 = half * 64 + cc * 32;
-        float v[32];
-        tmem_ld32(tmem_lane + c0, v);
+    for (int gch = 0; gch < 4; ++gch) xr[gch] = *reinterpret_cast<const uint4 *>(sX + canon_off(row, c0 + gch * 8, D));
+    float t[W];
+    tmem_ld32(tmem_lane + c0, t);
+    TP("l.ld");
+    float2 s2 = make_float2(0.0f, 0.0f), q2 = make_float2(0.0f, 0.0f);
 #pragma unroll
-        for (int gch = 0; gch < 4; ++gch) {
-            float x[8];
-            unpack8(*reinterpret_cast<const uint4 *>(sX + canon_off(row, c0 + gch * 8, D)), x);
+    for (int gch = 0; gch < 4; ++gch) {
+        float x[8];
+        unpack8(xr[gch], x);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float u = v[gch * 8 + i] + __ldg(bias + c0 + gch * 8 + i) + x[i];
-                t[cc * 32 + gch * 8 + i] = u;
-                sum += u; sq = fmaf(u, u, sq);
-            }
+        for (int i = 0; i < 4; ++i) {
+            const int c = gch * 8 + 2 * i;
+            const float2 u = __fadd2_rn(__fadd2_rn(make_float2(t[c], t[c + 1]), p[c / 2]), make_float2(x[2 * i], x[2 * i + 1]));
+            t[c] = u.x; t[c + 1] = u.y;
+            s2 = __fadd2_rn(s2, u); q2 = __ffma2_rn(u, u, q2);
         }
     }
-    s_part[half][0][row] = sum; s_part[half][1][row] = sq;
+    s_part[part][row] = make_float2(s2.x + s2.y, q2.x + q2.y);
+    TP("l.ma");
+    load_cols32(g + c0, p);                        // gamma arrives while the CTA meets at the barrier
     __syncthreads();
-    sum += s_part[half ^ 1][0][row]; sq += s_part[half ^ 1][1][row];
+    TP("l.ba");
+    float sum = 0.0f, sq = 0.0f;
+#pragma unroll
+    for (int q = 0; q < kColParts; ++q) { const float2 p2 = s_part[q][row]; sum += p2.x; sq += p2.y; }
     const float mean = sum * (1.0f / D);
     const float rstd = rsqrtf(fmaxf(sq * (1.0f / D) - mean * mean, 0.0f) + 1e-5f);
+    const float2 a2 = make_float2(rstd, rstd), m2 = make_float2(-mean * rstd, -mean * rstd);
 #pragma unroll
-    for (int gch = 0; gch < 8; ++gch) {
-        const int c = half * 64 + gch * 8;
+    for (int i = 0; i < 16; ++i) p[i] = __fmul2_rn(__ffma2_rn(make_float2(t[2 * i], t[2 * i + 1]), a2, m2), p[i]);   // x^ * gamma
+    float2 be[16];
+    load_cols32(beta + c0, be);
+#pragma unroll
+    for (int gch = 0; gch < 4; ++gch) {
         float o[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = (t[gch * 8 + i] - mean) * rstd * __ldg(g + c + i) + __ldg(beta + c + i);
-        *reinterpret_cast<uint4 *>(sX + canon_off(row, c, D)) = pack8(o);
+        for (int i = 0; i < 4; ++i) {
+            const float2 u = __fadd2_rn(p[gch * 4 + i], be[gch * 4 + i]);
+            o[2 * i] = u.x; o[2 * i + 1] = u.y;
+        }
+        *reinterpret_cast<uint4 *>(sX + canon_off(row, c0 + gch * 8, D)) = pack8(o);
     }
+    TP("l.st");
+}
+
+// one observation row (a token) of tile row r, zero beyond the batch
+__device__ __forceinline__ void load_obs_row(const float *__restrict__ obs, int s0, int nrows, int r, float *o) {
+    const bool valid = r < nrows;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] = (valid && j < F) ? __ldg(obs + ((size_t)s0 * S + r) * F + j) : 0.0f;
+}
+
+__device__ __forceinline__ void stage_vec(float *dst, const float *__restrict__ src, int n, int tid) {
+    for (int i = tid; i < n; i += kFusedThreads) dst[i] = __ldg(src + i);
+}
+__device__ __forceinline__ void stage_params(float *dst, const BlockW &w, const HeadW &head, int tid) {
+    stage_vec(dst + kPEmbB, w.emb_b, D, tid);
+    stage_vec(dst + kPPos, w.pos, S * D, tid);
+    for (int l = 0; l < w.layers; ++l) {
+        float *d = dst + kPLayer + l * kPLayerSize;
+        const LayerW &L = w.layer[l];
+        stage_vec(d + kPInB, L.in_b, 3 * D, tid); stage_vec(d + kPOutB, L.out_b, D, tid);
+        stage_vec(d + kPN1W, L.n1_w, D, tid); stage_vec(d + kPN1B, L.n1_b, D, tid);
+        stage_vec(d + kPL1B, L.l1_b, FF, tid); stage_vec(d + kPL2B, L.l2_b, D, tid);
+        stage_vec(d + kPN2W, L.n2_w, D, tid); stage_vec(d + kPN2B, L.n2_b, D, tid);
+    }
+    stage_vec(dst + kPLayer + w.layers * kPLayerSize, head.b1, HID, tid);
 }
 
 __global__ void __launch_bounds__(kFusedThreads, 1)
 fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW head_actor, __nv_bfloat16 *__restrict__ hh_actor,
                    BlockW w_critic, HeadW head_critic, __nv_bfloat16 *__restrict__ hh_critic, int *__restrict__ work_counter) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ uint64_t mbar, wbar;                       // MMA completion / weight staging (bulk TMA) barriers
+    __shared__ uint64_t mbar, mbar2, wbar;                // MMA completion (two in flight) / weight staging (bulk TMA)
     __shared__ uint32_t tmem_base_s;
-    __shared__ int s_item;
+    __shared__ int s_item[2];                             // this work item / the next one (fetched a whole item ahead)
     __shared__ uint8_t s_pad[128];
     unsigned char *sX = smem, *sQ = smem + kTileBytes, *sK = sQ + kTileBytes, *sV = sK + kTileBytes;
     unsigned char *sH = sQ;                               // [128 x 256] canonical, aliases sQ + sK after attention
     unsigned char *sW = smem + 4 * kTileBytes;
+    float *const sP = reinterpret_cast<float *>(sW + kWBytes);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    __shared__ float s_part[2][2][128];
-    const int row = tid & 127, half = warp >> 2;          // thread = (row, column half); TMEM lane = row
+#ifdef UAVP_FUSED_TIMING
+    TpLog tp; tp.k = 0;
+#endif
+    // LayerNorm partial sums {sum, sum of squares} per (column part, row): 4 KB at the start of sV, which is idle in both
+    // residual epilogues (after the attention has consumed V; before the next V epilogue rewrites it)
+    float2 (*s_part)[128] = reinterpret_cast<float2 (*)[128]>(sV);
+    const int row = tid & 127, part = warp >> 2;          // thread = (row, column quarter); TMEM lane = row
+    const int num_tiles = (B + kTileSamples - 1) / kTileSamples, num_items = 2 * num_tiles;
     if (warp == 0) tmem_alloc(&tmem_base_s, 512);
-    if (tid == 0) { mbar_init(&mbar, 1); mbar_init(&wbar, 1); fence_mbar_init(); }
+    if (tid == 0) {
+        mbar_init(&mbar, 1); mbar_init(&mbar2, 1); mbar_init(&wbar, 1); fence_mbar_init();
+        s_item[0] = atomicAdd(work_counter, 1);
+    }
+    stage_params(sP + kPActor, w_actor, head_actor, tid);
+    stage_params(sP + kPCritic, w_critic, head_critic, tid);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
     const uint32_t tmem_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    uint32_t parity = 0, wparity = 0;
-    const int num_tiles = (B + kTileSamples - 1) / kTileSamples;
+    uint32_t parity = 0, parity2 = 0, wparity = 0;
+    int cur = 0;
+    float o[16];                                          // this thread's observation row (tid < 128), fetched an item ahead
+    bool have_obs = false;
 
     // work items = (network, tile), handed out dynamically, the two-layer critic tiles first (longest first)
     for (;;) {
-        if (tid == 0) s_item = atomicAdd(work_counter, 1);
-        __syncthreads();
-        const int item = s_item;
-        if (item >= 2 * num_tiles) break;
+        const int item = s_item[cur];
+#ifdef UAVP_FUSED_TIMING
+        if (tid == 0 && blockIdx.x == 0 && tp.k > 1) {
+            printf("item: %d stamps, total %lld cycles\n", tp.k, tp.t[tp.k - 1] - tp.t[0]);
+            for (int i = 1; i < tp.k; ++i) printf("  %-5s %6lld\n", tp.n[i], tp.t[i] - tp.t[i - 1]);
+        }
+        tp.k = 0;
+        TP("start");
+#endif
+        if (item >= num_items) break;
+        if (tid == 0) s_item[cur ^ 1] = atomicAdd(work_counter, 1);   // read after the barriers of this item
         const bool is_critic = item < num_tiles;
         const BlockW &w = is_critic ? w_critic : w_actor;
         const HeadW &head = is_critic ? head_critic : head_actor;
+        const float *const pw = sP + (is_critic ? kPCritic : kPActor);
         __nv_bfloat16 *head_hidden = is_critic ? hh_critic : hh_actor;
         const int tile = is_critic ? item : item - num_tiles;
         const int s0 = tile * kTileSamples;
@@ -162,20 +270,17 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
         // ---- embedding: X = relu(obs W^T + b) + pos (transformer_net.py:24-30,57-59); key-padding mask (:52-54).
         //      On the tensor cores with K = 32: the fp32 observation row is split into bf16 hi + lo parts
         //      (columns 0..13 and 16..29) against the weight duplicated in both halves, so the product keeps ~16
-        //      mantissa bits of the input.  A operand staged in sQ, B operand in sK; Win of layer 0 streams into sW. ----
+        //      mantissa bits of the input.  A operand staged in sQ, B operand in sK; Wq|Wk of layer 0 streams into sW. ----
         if (tid == 0) {
             bulk_load(sK, w.emb_w2p, D * 32 * 2, &wbar);                  // embedding weights (B operand, K = 32)
         }
         if (tid < 128) {
             const int r = tid;
-            const bool valid = r < nrows;
-            float o[16], asum = 0.0f;
+            if (!have_obs) load_obs_row(obs, s0, nrows, r, o);
+            float asum = 0.0f;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                o[j] = (valid && j < F) ? obs[((size_t)s0 * S + r) * F + j] : 0.0f;
-                asum += fabsf(o[j]);
-            }
-            s_pad[r] = (valid && asum == 0.0f && r % S != S - 1) ? 1 : 0;
+            for (int j = 0; j < 16; ++j) asum += fabsf(o[j]);
+            s_pad[r] = (r < nrows && asum == 0.0f && r % S != S - 1) ? 1 : 0;
             float hi[16], lo[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -190,134 +295,207 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
+        TP("stage");
         tc_fence_after();
         mbar_wait(&wbar, wparity); wparity ^= 1;
+        TP("wbar");
         if (tid == 0) {
-            bulk_load(sW, w.layer[0].in_wp, 3 * D * D * 2, &wbar);       // Win of layer 0 streams in behind the embedding
+            bulk_load(sW, w.layer[0].in_wp, 2 * D * D * 2, &wbar);       // Wq|Wk of layer 0 streams in behind the embedding
             issue_gemm(tmem, sQ, sK, D, 32, &mbar);
         }
         mbar_wait(&mbar, parity); parity ^= 1;
+        TP("mma");
         tc_fence_after();
         {
             const bool valid = row < nrows;
-            const float *pos = w.pos + (row % S) * D;
-            for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
-                float v[32];
-                tmem_ld32(tmem_lane + c0, v);
+            const int c0 = part * 32;
+            float2 eb[16], ep[16];
+            load_cols32(pw + kPEmbB + c0, eb);
+            load_cols32(pw + kPPos + (row % S) * D + c0, ep);
+            float v[32];
+            tmem_ld32(tmem_lane + c0, v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    v[i] = valid ? fmaxf(v[i] + __ldg(w.emb_b + c0 + i), 0.0f) + __ldg(pos + c0 + i) : 0.0f;
-#pragma unroll
-                for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4 *>(sX + canon_off(row, c0 + g * 8, D)) = pack8(v + g * 8);
+            for (int i = 0; i < 16; ++i) {
+                float2 u = __fadd2_rn(make_float2(v[2 * i], v[2 * i + 1]), eb[i]);
+                u = __fadd2_rn(make_float2(fmaxf(u.x, 0.0f), fmaxf(u.y, 0.0f)), ep[i]);
+                v[2 * i] = valid ? u.x : 0.0f; v[2 * i + 1] = valid ? u.y : 0.0f;
             }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4 *>(sX + canon_off(row, c0 + g * 8, D)) = pack8(v + g * 8);
         }
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
+        TP("emb");
 
         for (int l = 0; l < w.layers; ++l) {
             const LayerW &L = w.layer[l];
-            // ---- QKV = X Win^T (N = 384) -> sQ | sK | sV; out-proj weights stream in behind the epilogue ----
+            const float *const pl = pw + kPLayer + l * kPLayerSize;
+            const bool last_layer = l + 1 == w.layers;    // only the newest token's output is consumed after it
+            // ---- Q|K = X [Wq|Wk]^T (N = 256), then V = X Wv^T (N = 128) under the Q / K epilogues -> sQ | sK | sV ----
             tc_fence_after();
-            mbar_wait(&wbar, wparity); wparity ^= 1;                      // Win has landed in sW
-            if (tid == 0) issue_gemm(tmem, sX, sW, 3 * D, D, &mbar);
+            mbar_wait(&wbar, wparity); wparity ^= 1;                      // Wq|Wk has landed in sW
+            TP("wbar");
+            if (tid == 0) issue_gemm(tmem, sX, sW, 2 * D, D, &mbar);
             mbar_wait(&mbar, parity); parity ^= 1;
+            TP("mmaQK");
             tc_fence_after();
-            if (tid == 0) bulk_load(sW, L.out_wp, D * D * 2, &wbar);
-            epilogue_bias_act(tmem_lane, row, L.in_b, half * 192, half * 192 + 192, false, sQ, D, D);
+            if (tid == 0) bulk_load(sW, L.in_wp + 2 * D * D, D * D * 2, &wbar);      // Wv (rows 256..383 of the packed Win)
+            epilogue_bias_act(tmem_lane, row, pl + kPInB, part * 32, part * 32 + 32, false, sQ, D, D TP_PASS);
+            mbar_wait(&wbar, wparity); wparity ^= 1;                      // Wv has landed
+            if (tid == 0) issue_gemm(tmem + 2 * D, sX, sW, D, D, &mbar);
+            epilogue_bias_act(tmem_lane, row, pl + kPInB, D + part * 32, D + part * 32 + 32, false, sQ, D, D TP_PASS);
+            mbar_wait(&mbar, parity); parity ^= 1;
+            TP("mmaV");
+            tc_fence_after();
+            if (tid == 0) bulk_load(sW, L.out_wp, D * D * 2, &wbar);      // out-proj weights stream in behind the rest
+            epilogue_bias_act(tmem_lane, row, pl + kPInB, 2 * D + part * 32, 2 * D + part * 32 + 32, false, sQ, D, D TP_PASS);
             tc_fence_before();
             __syncthreads();
-            // ---- attention over the 5-token window, per (sample, head, query); output overwrites the Q slice ----
-            for (int item = tid; item < nsamp * H * S; item += kFusedThreads) {
-                const int smp = item / (H * S), h = (item / S) % H, i = item % S;
-                const int r = smp * S + i;
-                float q[DH], sc[S], mx = -INFINITY;
-                unsigned char *pq = sQ + canon_off(r, h * DH, D);
-                unpack8(*reinterpret_cast<const uint4 *>(pq), q);
-                unpack8(*reinterpret_cast<const uint4 *>(pq + 128), q + 8);
+            TP("epiV");
+            // ---- attention over the 5-token window; output overwrites the Q slice.  A warp takes a (query, head) pair and its
+            //      lanes the samples: the 8 lanes of a quarter-warp then read 8 different rows (5 is odd: row & 7 distinct) of
+            //      the same 16-byte column chunk - conflict-free (one thread per (sample, head, query) in flat order put the
+            //      heads of a sample, 256 B apart, on the same banks: 8-way conflicts on every access) ----
+            {
+                const int npair = (last_layer ? 1 : S) * H;
+                for (int pair = warp; pair < npair; pair += kFusedThreads / 32) {
+                    const int h = pair % H, i = last_layer ? S - 1 : pair / H;
+                    if (lane < nsamp) {
+                        const int smp = lane, r = smp * S + i;
+                        unsigned char *pq = sQ + canon_off(r, h * DH, D);
+                        float2 q2[8];
+                        {
+                            float q[DH];
+                            unpack8(*reinterpret_cast<const uint4 *>(pq), q);
+                            unpack8(*reinterpret_cast<const uint4 *>(pq + 128), q + 8);
 #pragma unroll
-                for (int j = 0; j < S; ++j) {
-                    float kk[DH], sdot = 0.0f;
-                    const unsigned char *pk = sK + canon_off(smp * S + j, h * DH, D);
-                    unpack8(*reinterpret_cast<const uint4 *>(pk), kk);
-                    unpack8(*reinterpret_cast<const uint4 *>(pk + 128), kk + 8);
+                            for (int e = 0; e < 8; ++e) q2[e] = make_float2(q[2 * e], q[2 * e + 1]);
+                        }
+                        float sc[S], mx = -INFINITY;
 #pragma unroll
-                    for (int e = 0; e < DH; ++e) sdot = fmaf(q[e], kk[e], sdot);
-                    sc[j] = s_pad[smp * S + j] ? -INFINITY : sdot * 0.25f;
-                    mx = fmaxf(mx, sc[j]);
+                        for (int j = 0; j < S; ++j) {
+                            float kk[DH];
+                            const unsigned char *pk = sK + canon_off(smp * S + j, h * DH, D);
+                            unpack8(*reinterpret_cast<const uint4 *>(pk), kk);
+                            unpack8(*reinterpret_cast<const uint4 *>(pk + 128), kk + 8);
+                            float2 acc = make_float2(0.0f, 0.0f), acc1 = make_float2(0.0f, 0.0f);
+#pragma unroll
+                            for (int e = 0; e < 8; e += 2) {
+                                acc = __ffma2_rn(q2[e], make_float2(kk[2 * e], kk[2 * e + 1]), acc);
+                                acc1 = __ffma2_rn(q2[e + 1], make_float2(kk[2 * e + 2], kk[2 * e + 3]), acc1);
+                            }
+                            const float sdot = (acc.x + acc.y) + (acc1.x + acc1.y);
+                            sc[j] = s_pad[smp * S + j] ? -INFINITY : sdot * 0.25f;
+                            mx = fmaxf(mx, sc[j]);
+                        }
+                        float den = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < S; ++j) { sc[j] = __expf(sc[j] - mx); den += sc[j]; }
+                        const float inv = 1.0f / den;
+                        float2 o2[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o2[e] = make_float2(0.0f, 0.0f);
+#pragma unroll
+                        for (int j = 0; j < S; ++j) {
+                            float vv[DH];
+                            const unsigned char *pv = sV + canon_off(smp * S + j, h * DH, D);
+                            unpack8(*reinterpret_cast<const uint4 *>(pv), vv);
+                            unpack8(*reinterpret_cast<const uint4 *>(pv + 128), vv + 8);
+                            const float pj = sc[j] * inv;
+                            const float2 pj2 = make_float2(pj, pj);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) o2[e] = __ffma2_rn(pj2, make_float2(vv[2 * e], vv[2 * e + 1]), o2[e]);
+                        }
+                        float ov[DH];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) { ov[2 * e] = o2[e].x; ov[2 * e + 1] = o2[e].y; }
+                        *reinterpret_cast<uint4 *>(pq) = pack8(ov);
+                        *reinterpret_cast<uint4 *>(pq + 128) = pack8(ov + 8);
+                    }
                 }
-                float den = 0.0f, o[DH];
-#pragma unroll
-                for (int j = 0; j < S; ++j) { sc[j] = __expf(sc[j] - mx); den += sc[j]; }
-                const float inv = 1.0f / den;
-#pragma unroll
-                for (int e = 0; e < DH; ++e) o[e] = 0.0f;
-#pragma unroll
-                for (int j = 0; j < S; ++j) {
-                    float vv[DH];
-                    const unsigned char *pv = sV + canon_off(smp * S + j, h * DH, D);
-                    unpack8(*reinterpret_cast<const uint4 *>(pv), vv);
-                    unpack8(*reinterpret_cast<const uint4 *>(pv + 128), vv + 8);
-                    const float pj = sc[j] * inv;
-#pragma unroll
-                    for (int e = 0; e < DH; ++e) o[e] = fmaf(pj, vv[e], o[e]);
-                }
-                *reinterpret_cast<uint4 *>(pq) = pack8(o);
-                *reinterpret_cast<uint4 *>(pq + 128) = pack8(o + 8);
             }
             fence_async_smem();
             __syncthreads();
+            TP("attn");
             // ---- out-proj + residual + LayerNorm1 (in place in sX); FFN1 weights stream in ----
             tc_fence_after();
             mbar_wait(&wbar, wparity); wparity ^= 1;
             if (tid == 0) issue_gemm(tmem, sQ, sW, D, D, &mbar);
             mbar_wait(&mbar, parity); parity ^= 1;
+            TP("mmaO");
             tc_fence_after();
             if (tid == 0) bulk_load(sW, L.l1_wp, FF * D * 2, &wbar);
-            epilogue_residual_ln(tmem_lane, row, half, L.out_b, L.n1_w, L.n1_b, sX, s_part);
+            epilogue_residual_ln(tmem_lane, row, part, pl + kPOutB, pl + kPN1W, pl + kPN1B, sX, s_part TP_PASS);
             fence_async_smem();
             tc_fence_before();
             __syncthreads();
-            // ---- FFN1 + ReLU -> sH [128 x 256]; FFN2 weights ([128 x 256]) stream in ----
+            TP("ln1");
+            // ---- FFN1 + ReLU -> sH [128 x 256], as two column halves: the second half's MMAs run under the first half's
+            //      epilogue; FFN2 weights ([128 x 256]) stream in ----
             tc_fence_after();
             mbar_wait(&wbar, wparity); wparity ^= 1;
-            if (tid == 0) issue_gemm(tmem, sX, sW, FF, D, &mbar);
+            if (tid == 0) {
+                issue_gemm(tmem, sX, sW, FF / 2, D, &mbar);
+                issue_gemm(tmem + FF / 2, sX, sW + (FF / 2) * D * 2, FF / 2, D, &mbar2);
+            }
             mbar_wait(&mbar, parity); parity ^= 1;
+            TP("mmaF1a");
+            tc_fence_after();
+            epilogue_bias_act(tmem_lane, row, pl + kPL1B, part * 32, part * 32 + 32, true, sH, FF, FF TP_PASS);
+            mbar_wait(&mbar2, parity2); parity2 ^= 1;
             tc_fence_after();
             if (tid == 0) bulk_load(sW, L.l2_wp, D * FF * 2, &wbar);
-            epilogue_bias_act(tmem_lane, row, L.l1_b, half * 128, half * 128 + 128, true, sH, FF, FF);
+            epilogue_bias_act(tmem_lane, row, pl + kPL1B, FF / 2 + part * 32, FF / 2 + part * 32 + 32, true, sH, FF, FF TP_PASS);
             fence_async_smem();
             tc_fence_before();
             __syncthreads();
+            TP("ffn1");
             // ---- FFN2 + residual + LayerNorm2 (in place in sX); the next GEMM's weights stream in ----
             tc_fence_after();
             mbar_wait(&wbar, wparity); wparity ^= 1;
             if (tid == 0) issue_gemm(tmem, sH, sW, D, FF, &mbar);
             mbar_wait(&mbar, parity); parity ^= 1;
+            TP("mmaF2");
             tc_fence_after();
             if (tid == 0) {
-                if (l + 1 < w.layers) bulk_load(sW, w.layer[l + 1].in_wp, 3 * D * D * 2, &wbar);
+                if (!last_layer) bulk_load(sW, w.layer[l + 1].in_wp, 2 * D * D * 2, &wbar);
                 else bulk_load(sW, head.w1p, HID * D * 2, &wbar);        // last layer: the head's first layer
             }
-            epilogue_residual_ln(tmem_lane, row, half, L.l2_b, L.n2_w, L.n2_b, sX, s_part);
+            epilogue_residual_ln(tmem_lane, row, part, pl + kPL2B, pl + kPN2W, pl + kPN2B, sX, s_part TP_PASS);
             fence_async_smem();
             tc_fence_before();
             __syncthreads();
+            TP("ln2");
         }
         // ---- head first layer: relu(W1 z + b1) for the newest token of every sample (transformer_net.py:106-108) ----
         tc_fence_after();
         mbar_wait(&wbar, wparity); wparity ^= 1;
         if (tid == 0) issue_gemm(tmem, sX, sW, HID, D, &mbar);
+        {   // the next work item's observation rows arrive under the head GEMM and its epilogue
+            const int next = s_item[cur ^ 1];
+            have_obs = next < num_items;
+            if (have_obs && tid < 128) {
+                const int ns0 = (next < num_tiles ? next : next - num_tiles) * kTileSamples;
+                load_obs_row(obs, ns0, min(kTileSamples, B - ns0) * S, tid, o);
+            }
+        }
         mbar_wait(&mbar, parity); parity ^= 1;
+        TP("mmaH");
         tc_fence_after();
-        {   // tcgen05.ld is warp-collective: every lane loads, only the newest-token rows store (32 columns per half)
+        if (part < HID / 32) {   // tcgen05.ld is warp-collective: every lane loads, only the newest-token rows store
             const bool keep = row < nrows && row % S == S - 1;
             __nv_bfloat16 *dst = head_hidden + (size_t)(s0 + row / S) * HID;
-            const int c0 = half * 32;
+            const int c0 = part * 32;
+            float2 hb[16];
+            load_cols32(pw + kPLayer + w.layers * kPLayerSize + c0, hb);
             float v[32];
             tmem_ld32(tmem_lane + c0, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + __ldg(head.b1 + c0 + i), 0.0f);
+            for (int i = 0; i < 16; ++i) {
+                const float2 u = __fadd2_rn(make_float2(v[2 * i], v[2 * i + 1]), hb[i]);
+                v[2 * i] = fmaxf(u.x, 0.0f); v[2 * i + 1] = fmaxf(u.y, 0.0f);
+            }
             if (keep) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4 *>(dst + c0 + g * 8) = pack8(v + g * 8);
@@ -325,6 +503,8 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
         }
         tc_fence_before();
         __syncthreads();
+        TP("head");
+        cur ^= 1;
     }
     if (warp == 0) tmem_free(tmem, 512);
 }
