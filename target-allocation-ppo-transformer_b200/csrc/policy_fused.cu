@@ -2,7 +2,6 @@
 #include "uavpolicy_b200.h"
 
 #include <cstdint>
-#include <cstdio>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -81,17 +80,6 @@ __device__ __forceinline__ uint4 pack8(const float *v) {
 
 // Epilogues run on all 16 warps: warp w reads TMEM lanes 32*(w%4).. (its rows) and the column quarter w/4.
 
-// phase timing of CTA 0 (diagnostic build -DUAVP_FUSED_TIMING only): cycles between the waits / barriers of a work item
-#ifdef UAVP_FUSED_TIMING
-struct TpLog { long long t[128]; const char *n[128]; int k; };
-#define TP_ARG , TpLog &tp
-#define TP_PASS , tp
-#define TP(name) do { if (threadIdx.x == 0 && blockIdx.x == 0 && tp.k < 128) { tp.t[tp.k] = clock64(); tp.n[tp.k] = name; ++tp.k; } } while (0)
-#else
-#define TP_ARG
-#define TP_PASS
-#define TP(name) do { } while (0)
-#endif
 
 // Column parameters (bias, gamma, beta) are the same for every row: warp-uniform (broadcast) loads from the staged copy in
 // shared memory, issued BEFORE the TMEM load (or the barrier) an epilogue has to wait for anyway; packed fp32x2 arithmetic.
@@ -105,25 +93,22 @@ __device__ __forceinline__ void load_cols32(const float *p, float2 *o) {   // p:
 
 // plain layer: out = act(acc + bias) -> bf16; column c goes to tile (c / tile_cols) of dst, canonical row length Kout
 __device__ __forceinline__ void epilogue_bias_act(uint32_t tmem_lane, int row, const float *bias, int c_begin,
-                                                  int c_end, bool relu, unsigned char *dst, int Kout, int tile_cols TP_ARG) {
+                                                  int c_end, bool relu, unsigned char *dst, int Kout, int tile_cols) {
     for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         float2 b[16];
         load_cols32(bias + c0, b);
         float v[32];
         tmem_ld32(tmem_lane + c0, v);
-        TP("e.ld");
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             float2 u = __fadd2_rn(make_float2(v[2 * i], v[2 * i + 1]), b[i]);
             if (relu) { u.x = fmaxf(u.x, 0.0f); u.y = fmaxf(u.y, 0.0f); }
             v[2 * i] = u.x; v[2 * i + 1] = u.y;
         }
-        TP("e.ma");
         unsigned char *tile = dst + (c0 / tile_cols) * kTileBytes;
 #pragma unroll
         for (int g = 0; g < 4; ++g)
             *reinterpret_cast<uint4 *>(tile + canon_off(row, (c0 % tile_cols) + g * 8, Kout)) = pack8(v + g * 8);
-        TP("e.st");
     }
 }
 
@@ -131,7 +116,7 @@ __device__ __forceinline__ void epilogue_bias_act(uint32_t tmem_lane, int row, c
 // quarters of a row exchange their partial sums through shared memory (all threads call: contains a CTA barrier).
 __device__ __forceinline__ void epilogue_residual_ln(uint32_t tmem_lane, int row, int part, const float *bias,
                                                      const float *g, const float *beta,
-                                                     unsigned char *sX, float2 (*s_part)[128] TP_ARG) {
+                                                     unsigned char *sX, float2 (*s_part)[128]) {
     constexpr int W = D / kColParts;              // 32 columns per thread
     static_assert(W == 32, "one tcgen05.ld of 32 columns per thread");
     const int c0 = part * W;
@@ -142,7 +127,6 @@ __device__ __forceinline__ void epilogue_residual_ln(uint32_t tmem_lane, int row
     for (int gch = 0; gch < 4; ++gch) xr[gch] = *reinterpret_cast<const uint4 *>(sX + canon_off(row, c0 + gch * 8, D));
     float t[W];
     tmem_ld32(tmem_lane + c0, t);
-    TP("l.ld");
     float2 s2 = make_float2(0.0f, 0.0f), q2 = make_float2(0.0f, 0.0f);
 #pragma unroll
     for (int gch = 0; gch < 4; ++gch) {
@@ -157,10 +141,8 @@ __device__ __forceinline__ void epilogue_residual_ln(uint32_t tmem_lane, int row
         }
     }
     s_part[part][row] = make_float2(s2.x + s2.y, q2.x + q2.y);
-    TP("l.ma");
     load_cols32(g + c0, p);                        // gamma arrives while the CTA meets at the barrier
     __syncthreads();
-    TP("l.ba");
     float sum = 0.0f, sq = 0.0f;
 #pragma unroll
     for (int q = 0; q < kColParts; ++q) { const float2 p2 = s_part[q][row]; sum += p2.x; sq += p2.y; }
@@ -181,7 +163,6 @@ __device__ __forceinline__ void epilogue_residual_ln(uint32_t tmem_lane, int row
         }
         *reinterpret_cast<uint4 *>(sX + canon_off(row, c0 + gch * 8, D)) = pack8(o);
     }
-    TP("l.st");
 }
 
 // one observation row (a token) of tile row r, zero beyond the batch
@@ -220,10 +201,7 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
     unsigned char *sH = sQ;                               // [128 x 256] canonical, aliases sQ + sK after attention
     unsigned char *sW = smem + 4 * kTileBytes;
     float *const sP = reinterpret_cast<float *>(sW + kWBytes);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-#ifdef UAVP_FUSED_TIMING
-    TpLog tp; tp.k = 0;
-#endif
+    const int tid = threadIdx.x, warp = tid >> 5;
     // LayerNorm partial sums {sum, sum of squares} per (column part, row): 4 KB at the start of sV, which is idle in both
     // residual epilogues (after the attention has consumed V; before the next V epilogue rewrites it)
     float2 (*s_part)[128] = reinterpret_cast<float2 (*)[128]>(sV);
@@ -249,14 +227,6 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
     // work items = (network, tile), handed out dynamically, the two-layer critic tiles first (longest first)
     for (;;) {
         const int item = s_item[cur];
-#ifdef UAVP_FUSED_TIMING
-        if (tid == 0 && blockIdx.x == 0 && tp.k > 1) {
-            printf("item: %d stamps, total %lld cycles\n", tp.k, tp.t[tp.k - 1] - tp.t[0]);
-            for (int i = 1; i < tp.k; ++i) printf("  %-5s %6lld\n", tp.n[i], tp.t[i] - tp.t[i - 1]);
-        }
-        tp.k = 0;
-        TP("start");
-#endif
         if (item >= num_items) break;
         if (tid == 0) s_item[cur ^ 1] = atomicAdd(work_counter, 1);   // read after the barriers of this item
         const bool is_critic = item < num_tiles;
@@ -295,16 +265,13 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        TP("stage");
         tc_fence_after();
         mbar_wait(&wbar, wparity); wparity ^= 1;
-        TP("wbar");
         if (tid == 0) {
             bulk_load(sW, w.layer[0].in_wp, 2 * D * D * 2, &wbar);       // Wq|Wk of layer 0 streams in behind the embedding
             issue_gemm(tmem, sQ, sK, D, 32, &mbar);
         }
         mbar_wait(&mbar, parity); parity ^= 1;
-        TP("mma");
         tc_fence_after();
         {
             const bool valid = row < nrows;
@@ -326,7 +293,6 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        TP("emb");
 
         for (int l = 0; l < w.layers; ++l) {
             const LayerW &L = w.layer[l];
@@ -335,34 +301,31 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
             // ---- Q|K = X [Wq|Wk]^T (N = 256), then V = X Wv^T (N = 128) under the Q / K epilogues -> sQ | sK | sV ----
             tc_fence_after();
             mbar_wait(&wbar, wparity); wparity ^= 1;                      // Wq|Wk has landed in sW
-            TP("wbar");
             if (tid == 0) issue_gemm(tmem, sX, sW, 2 * D, D, &mbar);
             mbar_wait(&mbar, parity); parity ^= 1;
-            TP("mmaQK");
             tc_fence_after();
             if (tid == 0) bulk_load(sW, L.in_wp + 2 * D * D, D * D * 2, &wbar);      // Wv (rows 256..383 of the packed Win)
-            epilogue_bias_act(tmem_lane, row, pl + kPInB, part * 32, part * 32 + 32, false, sQ, D, D TP_PASS);
+            epilogue_bias_act(tmem_lane, row, pl + kPInB, part * 32, part * 32 + 32, false, sQ, D, D);
             mbar_wait(&wbar, wparity); wparity ^= 1;                      // Wv has landed
             if (tid == 0) issue_gemm(tmem + 2 * D, sX, sW, D, D, &mbar);
-            epilogue_bias_act(tmem_lane, row, pl + kPInB, D + part * 32, D + part * 32 + 32, false, sQ, D, D TP_PASS);
+            epilogue_bias_act(tmem_lane, row, pl + kPInB, D + part * 32, D + part * 32 + 32, false, sQ, D, D);
             mbar_wait(&mbar, parity); parity ^= 1;
-            TP("mmaV");
             tc_fence_after();
             if (tid == 0) bulk_load(sW, L.out_wp, D * D * 2, &wbar);      // out-proj weights stream in behind the rest
-            epilogue_bias_act(tmem_lane, row, pl + kPInB, 2 * D + part * 32, 2 * D + part * 32 + 32, false, sQ, D, D TP_PASS);
+            epilogue_bias_act(tmem_lane, row, pl + kPInB, 2 * D + part * 32, 2 * D + part * 32 + 32, false, sQ, D, D);
             tc_fence_before();
             __syncthreads();
-            TP("epiV");
             // ---- attention over the 5-token window; output overwrites the Q slice.  A warp takes a (query, head) pair and its
             //      lanes the samples: the 8 lanes of a quarter-warp then read 8 different rows (5 is odd: row & 7 distinct) of
-            //      the same 16-byte column chunk - conflict-free (one thread per (sample, head, query) in flat order put the
-            //      heads of a sample, 256 B apart, on the same banks: 8-way conflicts on every access) ----
+            //      the same 16-byte column chunk - conflict-free.  (One thread per (sample, head, query) in flat
+            //      order put the heads of a sample, 256 B apart, on the same banks: 8-way conflicts on every access.) ----
             {
-                const int npair = (last_layer ? 1 : S) * H;
-                for (int pair = warp; pair < npair; pair += kFusedThreads / 32) {
-                    const int h = pair % H, i = last_layer ? S - 1 : pair / H;
+                const int npair = (last_layer ? 1 : S) * H, lane = tid & 31;
+                for (int pair = warp; pair < npair; pair += kFusedThreads / 32) {   // (dense packing of the 1000 items over
+                    const int h = pair % H, i = last_layer ? S - 1 : pair / H;      //  the 512 threads measured slower)
                     if (lane < nsamp) {
-                        const int smp = lane, r = smp * S + i;
+                        const int smp = lane;
+                        const int r = smp * S + i;
                         unsigned char *pq = sQ + canon_off(r, h * DH, D);
                         float2 q2[8];
                         {
@@ -417,20 +380,17 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
             }
             fence_async_smem();
             __syncthreads();
-            TP("attn");
             // ---- out-proj + residual + LayerNorm1 (in place in sX); FFN1 weights stream in ----
             tc_fence_after();
             mbar_wait(&wbar, wparity); wparity ^= 1;
             if (tid == 0) issue_gemm(tmem, sQ, sW, D, D, &mbar);
             mbar_wait(&mbar, parity); parity ^= 1;
-            TP("mmaO");
             tc_fence_after();
             if (tid == 0) bulk_load(sW, L.l1_wp, FF * D * 2, &wbar);
-            epilogue_residual_ln(tmem_lane, row, part, pl + kPOutB, pl + kPN1W, pl + kPN1B, sX, s_part TP_PASS);
+            epilogue_residual_ln(tmem_lane, row, part, pl + kPOutB, pl + kPN1W, pl + kPN1B, sX, s_part);
             fence_async_smem();
             tc_fence_before();
             __syncthreads();
-            TP("ln1");
             // ---- FFN1 + ReLU -> sH [128 x 256], as two column halves: the second half's MMAs run under the first half's
             //      epilogue; FFN2 weights ([128 x 256]) stream in ----
             tc_fence_after();
@@ -440,33 +400,29 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
                 issue_gemm(tmem + FF / 2, sX, sW + (FF / 2) * D * 2, FF / 2, D, &mbar2);
             }
             mbar_wait(&mbar, parity); parity ^= 1;
-            TP("mmaF1a");
             tc_fence_after();
-            epilogue_bias_act(tmem_lane, row, pl + kPL1B, part * 32, part * 32 + 32, true, sH, FF, FF TP_PASS);
+            epilogue_bias_act(tmem_lane, row, pl + kPL1B, part * 32, part * 32 + 32, true, sH, FF, FF);
             mbar_wait(&mbar2, parity2); parity2 ^= 1;
             tc_fence_after();
             if (tid == 0) bulk_load(sW, L.l2_wp, D * FF * 2, &wbar);
-            epilogue_bias_act(tmem_lane, row, pl + kPL1B, FF / 2 + part * 32, FF / 2 + part * 32 + 32, true, sH, FF, FF TP_PASS);
+            epilogue_bias_act(tmem_lane, row, pl + kPL1B, FF / 2 + part * 32, FF / 2 + part * 32 + 32, true, sH, FF, FF);
             fence_async_smem();
             tc_fence_before();
             __syncthreads();
-            TP("ffn1");
             // ---- FFN2 + residual + LayerNorm2 (in place in sX); the next GEMM's weights stream in ----
             tc_fence_after();
             mbar_wait(&wbar, wparity); wparity ^= 1;
             if (tid == 0) issue_gemm(tmem, sH, sW, D, FF, &mbar);
             mbar_wait(&mbar, parity); parity ^= 1;
-            TP("mmaF2");
             tc_fence_after();
             if (tid == 0) {
                 if (!last_layer) bulk_load(sW, w.layer[l + 1].in_wp, 2 * D * D * 2, &wbar);
                 else bulk_load(sW, head.w1p, HID * D * 2, &wbar);        // last layer: the head's first layer
             }
-            epilogue_residual_ln(tmem_lane, row, part, pl + kPL2B, pl + kPN2W, pl + kPN2B, sX, s_part TP_PASS);
+            epilogue_residual_ln(tmem_lane, row, part, pl + kPL2B, pl + kPN2W, pl + kPN2B, sX, s_part);
             fence_async_smem();
             tc_fence_before();
             __syncthreads();
-            TP("ln2");
         }
         // ---- head first layer: relu(W1 z + b1) for the newest token of every sample (transformer_net.py:106-108) ----
         tc_fence_after();
@@ -481,7 +437,6 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
             }
         }
         mbar_wait(&mbar, parity); parity ^= 1;
-        TP("mmaH");
         tc_fence_after();
         if (part < HID / 32) {   // tcgen05.ld is warp-collective: every lane loads, only the newest-token rows store
             const bool keep = row < nrows && row % S == S - 1;
@@ -503,7 +458,6 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
         }
         tc_fence_before();
         __syncthreads();
-        TP("head");
         cur ^= 1;
     }
     if (warp == 0) tmem_free(tmem, 512);
