@@ -91,6 +91,7 @@ struct uavpolicy {
     __nv_bfloat16 *w16_critic = nullptr;  // that the block's first parameter is 16 B aligned (TMA needs aligned operands)
     __nv_bfloat16 *emb2_a = nullptr, *emb2_c = nullptr;   // [128 x 32] tensor-core form of the two embedding weights
     __nv_bfloat16 *wpk = nullptr;         // GEMM weights pre-packed in canonical order (same element offsets as w32)
+    __nv_bfloat16 *bpk = nullptr;         // their biases as [N x 16] B-operands (3 layers + 2 heads), fused kernel only
     BlockW actor, critic;
     HeadW actor_head, critic_head;
     // bf16 activation workspaces (R = 5 * max_batch rows)
@@ -194,6 +195,7 @@ extern "C" int uavpolicy_create(int32_t device, int32_t max_batch, uavpolicy_t *
     if (e == cudaSuccess) e = palloc(p, &p->pad, R);
     if (e == cudaSuccess) e = palloc(p, &p->work_counter, 1);
     if (e == cudaSuccess) e = palloc(p, &p->wpk, (size_t)UPK_SIZE);
+    if (e == cudaSuccess) e = palloc(p, &p->bpk, (size_t)3 * uavp::kLayerBiasElems + 2 * HID * uavp::kBiasK);
     if (e == cudaSuccess) e = palloc(p, &p->emb2_a, (size_t)D * 32);
     if (e == cudaSuccess) e = palloc(p, &p->emb2_c, (size_t)D * 32);
     if (e == cudaSuccess) { void *ws = nullptr; e = cudaMalloc(&ws, uavp::gemm_workspace_bytes()); if (e == cudaSuccess) { p->allocs.push_back(ws); p->gemm_ws = ws; } }
@@ -207,6 +209,20 @@ extern "C" int uavpolicy_create(int32_t device, int32_t max_batch, uavpolicy_t *
     off = map_block(p->critic, 2, p->w32, p->w16_critic, p->wpk, off);
     off = map_head(p->critic_head, 1, p->w32, p->w16_critic, p->wpk, off);   // 267520 elements later: still a multiple of 8
     p->actor.emb_w2p = p->emb2_a; p->critic.emb_w2p = p->emb2_c;
+    {   // bias operands: layers of the actor, then of the critic, then the two heads
+        __nv_bfloat16 *q = p->bpk;
+        BlockW *blocks[2] = {&p->actor, &p->critic};
+        for (BlockW *b : blocks)
+            for (int l = 0; l < b->layers; ++l) {
+                LayerW &L = b->layer[l];
+                L.in_bp = q; q += 3 * D * uavp::kBiasK;
+                L.out_bp = q; q += D * uavp::kBiasK;
+                L.l1_bp = q; q += FF * uavp::kBiasK;
+                L.l2_bp = q; q += D * uavp::kBiasK;
+            }
+        p->actor_head.b1p = q; q += HID * uavp::kBiasK;
+        p->critic_head.b1p = q;
+    }
     if (off != (size_t)UAVPOLICY_NUM_PARAMS) { pfail(p, -1, "internal: parameter layout mismatch"); return bail(-1); }
     *out = p;
     return 0;
@@ -242,9 +258,19 @@ extern "C" int uavpolicy_set_weights(uavpolicy_t *p, const float *d_flat_params,
             }
         packw(p->actor_head.w1p, p->actor_head.w1, HID, D);
         packw(p->critic_head.w1p, p->critic_head.w1, HID, D);
+        auto packb = [&](const __nv_bfloat16 *dst, const float *bias, int N) {
+            pack_bias_kernel<<<(N * 16 + 255) / 256, 256, 0, s>>>(bias, const_cast<__nv_bfloat16 *>(dst), N);
+        };
+        for (const BlockW *b : blocks)
+            for (int l = 0; l < b->layers; ++l) {
+                const LayerW &L = b->layer[l];
+                packb(L.in_bp, L.in_b, 3 * D); packb(L.out_bp, L.out_b, D); packb(L.l1_bp, L.l1_b, FF); packb(L.l2_bp, L.l2_b, D);
+            }
+        packb(p->actor_head.b1p, p->actor_head.b1, HID);
+        packb(p->critic_head.b1p, p->critic_head.b1, HID);
     }
-    emb_w2_kernel<<<(D * 32 + 255) / 256, 256, 0, s>>>(p->actor.emb_w, p->emb2_a);
-    emb_w2_kernel<<<(D * 32 + 255) / 256, 256, 0, s>>>(p->critic.emb_w, p->emb2_c);
+    emb_w2_kernel<<<(D * 32 + 255) / 256, 256, 0, s>>>(p->actor.emb_w, p->actor.emb_b, p->emb2_a);
+    emb_w2_kernel<<<(D * 32 + 255) / 256, 256, 0, s>>>(p->critic.emb_w, p->critic.emb_b, p->emb2_c);
     P_TRY(p, cudaGetLastError());
     p->have_weights = true;
     return 0;

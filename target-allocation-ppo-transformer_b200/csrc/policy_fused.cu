@@ -24,9 +24,13 @@ using namespace uavp;
 //
 //   shared memory (215 KB):  sX 32 KB | sQ sK sV 3 x 32 KB (attention output overwrites Q; the FFN hidden tile
 //                            [128 x 256] later aliases sQ+sK) | sW 64 KB (one weight matrix at a time; the QKV projection
-//                            arrives as Wq|Wk, then Wv) | 23 KB: every bias / LayerNorm / position vector of both networks,
-//                            staged once per CTA (they are warp-uniform operands of every epilogue: as global loads they
-//                            kept missing the 28 KB of L1 that is left and cost an L2 round trip per phase)
+//                            arrives as Wq|Wk, then Wv) | sB 8 KB + 4 KB: the bias of that matrix as a [N x 16] B operand and
+//                            a constant A operand of ones - ONE more k-step per GEMM adds the bias on the tensor core
+//                            (bf16 value + rounding remainder in two columns), so no epilogue loads or adds a bias |
+//                            11 KB: the LayerNorm / position vectors of both networks, staged once per CTA (warp-uniform
+//                            operands of the epilogues: as global loads they kept missing the little L1 that is left; a
+//                            broadcast load still costs a full 128 B/cycle pass of the shared-memory pipe per 32 lanes x 4 B,
+//                            which is why the biases went to the tensor core instead)
 //   TMEM: 512 columns; Q|K uses [0,256), V [256,384), the other GEMMs [0,256) / [0,128) / [0,64).  TMEM reads are
 //   64 B per cycle per SM, so reading a [128 x N] fp32 accumulator costs 8 N cycles - more than its MMAs (4.2 N): wherever
 //   a GEMM has independent column blocks (Q|K vs V, the two halves of the FFN hidden layer) the second block's MMAs run
@@ -34,31 +38,34 @@ using namespace uavp;
 constexpr int kTileSamples = 25;                                   // 125 valid token rows of the 128
 constexpr int kFusedThreads = 512, kColParts = kFusedThreads / 128;   // column parts per row
 constexpr uint32_t kTileBytes = 128 * D * 2;                       // a [128 x 128] bf16 canonical tile
-// parameter vectors in shared memory (float offsets).  per network: emb_b | pos | layers | head b1
-constexpr int kPEmbB = 0, kPPos = D, kPLayer = D + S * D, kPLayerSize = 9 * D + FF;
-constexpr int kPInB = 0, kPOutB = 3 * D, kPN1W = 4 * D, kPN1B = 5 * D, kPL1B = 6 * D, kPL2B = 6 * D + FF, kPN2W = 7 * D + FF,
-              kPN2B = 8 * D + FF;
-constexpr int kPActor = 0, kPActorSize = kPLayer + 1 * kPLayerSize + HID, kPCritic = kPActorSize,
-              kPCriticSize = kPLayer + 2 * kPLayerSize + HID;
+// parameter vectors in shared memory (float offsets).  per network: pos | per layer: LayerNorm gamma / beta x 2
+constexpr int kPPos = 0, kPLayer = S * D, kPLayerSize = 4 * D;
+constexpr int kPN1W = 0, kPN1B = D, kPN2W = 2 * D, kPN2B = 3 * D;
+constexpr int kPActor = 0, kPActorSize = kPLayer + 1 * kPLayerSize, kPCritic = kPActorSize, kPCriticSize = kPLayer + 2 * kPLayerSize;
 static_assert(kPActorSize % 4 == 0 && kPLayer % 4 == 0 && kPLayerSize % 4 == 0, "16-byte loads of the staged vectors");
 constexpr uint32_t kWBytes = 64 * 1024;                            // sW: the largest block staged at once (Wq|Wk, W1, W2)
-constexpr size_t kFusedSmem = 4 * (size_t)kTileBytes + kWBytes + (size_t)(kPActorSize + kPCriticSize) * 4;
+constexpr uint32_t kBBytes = 2 * D * kBiasK * 2;                   // sB: its bias operand, [<= 256 x 16] bf16 (8 KB)
+constexpr uint32_t kOnesBytes = 128 * kBiasK * 2;                  // the A operand of the bias k-step: ones in columns 0, 1
+constexpr size_t kFusedSmem = 4 * (size_t)kTileBytes + kWBytes + kBBytes + kOnesBytes + (size_t)(kPActorSize + kPCriticSize) * 4;
 
 struct Phase { uint32_t parity = 0; };
 
-// issue D[tmem cols 0..N) = A[128 x K] * W[N x K]^T as K/16 k-steps (N <= 384 split at 256); thread 0 only
+// issue D[tmem cols 0..N) = A[128 x K] * W[N x K]^T (+ 1 * bias^T) as K/16 (+ 1) k-steps, N <= 256; thread 0 only.
+// sBias: the [N x 16] bias operand (or NULL), sOnes: the [128 x 16] A operand with ones in columns 0 and 1
 __device__ __forceinline__ void issue_gemm(uint32_t tmem, const unsigned char *sA, const unsigned char *sWt, int N, int K,
-                                           uint64_t *mbar) {
-    const uint32_t sbo = (uint32_t)K * 16;
-    for (int j = 0; j < K / 16; ++j) {
-        const uint64_t ad = smem_desc(smem_u32(sA) + j * 256, 128, sbo);
-        for (int n0 = 0; n0 < N; n0 += 256) {
-            const int nn = min(256, N - n0);
-            const uint64_t bd = smem_desc(smem_u32(sWt) + (n0 >> 3) * sbo + j * 256, 128, sbo);
-            mma_bf16(tmem + n0, ad, bd, instr_desc_bf16(128, nn), j > 0);
-        }
-    }
+                                           uint64_t *mbar, const unsigned char *sBias = nullptr, const unsigned char *sOnes = nullptr) {
+    const uint32_t sbo = (uint32_t)K * 16, idesc = instr_desc_bf16(128, N);
+    for (int j = 0; j < K / 16; ++j)
+        mma_bf16(tmem, smem_desc(smem_u32(sA) + j * 256, 128, sbo), smem_desc(smem_u32(sWt) + j * 256, 128, sbo), idesc, j > 0);
+    if (sBias) mma_bf16(tmem, smem_desc(smem_u32(sOnes), 128, kBiasK * 16), smem_desc(smem_u32(sBias), 128, kBiasK * 16), idesc, 1);
     mma_commit(mbar);
+}
+
+// a weight matrix and its bias operand land on ONE mbarrier phase (one arrival, the sum of the bytes)
+__device__ __forceinline__ void bulk_load2(void *s0, const void *g0, uint32_t b0, void *s1, const void *g1, uint32_t b1, uint64_t *mbar) {
+    mbar_expect_tx(mbar, b0 + b1);
+    bulk_copy(s0, g0, b0, mbar);
+    bulk_copy(s1, g1, b1, mbar);
 }
 
 __device__ __forceinline__ void unpack8(const uint4 &q, float *o) {   // bf16 -> fp32 is a 16-bit shift
@@ -81,8 +88,9 @@ __device__ __forceinline__ uint4 pack8(const float *v) {
 // Epilogues run on all 16 warps: warp w reads TMEM lanes 32*(w%4).. (its rows) and the column quarter w/4.
 
 
-// Column parameters (bias, gamma, beta) are the same for every row: warp-uniform (broadcast) loads from the staged copy in
-// shared memory, issued BEFORE the TMEM load (or the barrier) an epilogue has to wait for anyway; packed fp32x2 arithmetic.
+// Column parameters (gamma, beta, positions) are the same for every row: warp-uniform (broadcast) loads from the staged copy
+// in shared memory, issued BEFORE the TMEM load (or the barrier) an epilogue has to wait for anyway; packed fp32x2 arithmetic.
+// The biases are already in the accumulators (bias k-step of issue_gemm).
 __device__ __forceinline__ void load_cols32(const float *p, float2 *o) {   // p: shared memory, 16 B aligned
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -91,19 +99,15 @@ __device__ __forceinline__ void load_cols32(const float *p, float2 *o) {   // p:
     }
 }
 
-// plain layer: out = act(acc + bias) -> bf16; column c goes to tile (c / tile_cols) of dst, canonical row length Kout
-__device__ __forceinline__ void epilogue_bias_act(uint32_t tmem_lane, int row, const float *bias, int c_begin,
-                                                  int c_end, bool relu, unsigned char *dst, int Kout, int tile_cols) {
+// plain layer: out = act(acc) -> bf16; column c goes to tile (c / tile_cols) of dst, canonical row length Kout
+__device__ __forceinline__ void epilogue_act(uint32_t tmem_lane, int row, int c_begin, int c_end, bool relu, unsigned char *dst,
+                                             int Kout, int tile_cols) {
     for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-        float2 b[16];
-        load_cols32(bias + c0, b);
         float v[32];
         tmem_ld32(tmem_lane + c0, v);
+        if (relu) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            float2 u = __fadd2_rn(make_float2(v[2 * i], v[2 * i + 1]), b[i]);
-            if (relu) { u.x = fmaxf(u.x, 0.0f); u.y = fmaxf(u.y, 0.0f); }
-            v[2 * i] = u.x; v[2 * i + 1] = u.y;
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
         }
         unsigned char *tile = dst + (c0 / tile_cols) * kTileBytes;
 #pragma unroll
@@ -112,16 +116,13 @@ __device__ __forceinline__ void epilogue_bias_act(uint32_t tmem_lane, int row, c
     }
 }
 
-// residual layer: X[row] <- LayerNorm(X[row] + acc + bias) * g + beta (post-LN, eps 1e-5), in place.  The four column
+// residual layer: X[row] <- LayerNorm(X[row] + acc) * g + beta (post-LN, eps 1e-5), in place.  The four column
 // quarters of a row exchange their partial sums through shared memory (all threads call: contains a CTA barrier).
-__device__ __forceinline__ void epilogue_residual_ln(uint32_t tmem_lane, int row, int part, const float *bias,
-                                                     const float *g, const float *beta,
+__device__ __forceinline__ void epilogue_residual_ln(uint32_t tmem_lane, int row, int part, const float *g, const float *beta,
                                                      unsigned char *sX, float2 (*s_part)[128]) {
     constexpr int W = D / kColParts;              // 32 columns per thread
     static_assert(W == 32, "one tcgen05.ld of 32 columns per thread");
     const int c0 = part * W;
-    float2 p[16];
-    load_cols32(bias + c0, p);
     uint4 xr[4];
 #pragma unroll
     for (int gch = 0; gch < 4; ++gch) xr[gch] = *reinterpret_cast<const uint4 *>(sX + canon_off(row, c0 + gch * 8, D));
@@ -135,12 +136,13 @@ __device__ __forceinline__ void epilogue_residual_ln(uint32_t tmem_lane, int row
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int c = gch * 8 + 2 * i;
-            const float2 u = __fadd2_rn(__fadd2_rn(make_float2(t[c], t[c + 1]), p[c / 2]), make_float2(x[2 * i], x[2 * i + 1]));
+            const float2 u = __fadd2_rn(make_float2(t[c], t[c + 1]), make_float2(x[2 * i], x[2 * i + 1]));
             t[c] = u.x; t[c + 1] = u.y;
             s2 = __fadd2_rn(s2, u); q2 = __ffma2_rn(u, u, q2);
         }
     }
     s_part[part][row] = make_float2(s2.x + s2.y, q2.x + q2.y);
+    float2 p[16];
     load_cols32(g + c0, p);                        // gamma arrives while the CTA meets at the barrier
     __syncthreads();
     float sum = 0.0f, sq = 0.0f;
@@ -175,18 +177,14 @@ __device__ __forceinline__ void load_obs_row(const float *__restrict__ obs, int 
 __device__ __forceinline__ void stage_vec(float *dst, const float *__restrict__ src, int n, int tid) {
     for (int i = tid; i < n; i += kFusedThreads) dst[i] = __ldg(src + i);
 }
-__device__ __forceinline__ void stage_params(float *dst, const BlockW &w, const HeadW &head, int tid) {
-    stage_vec(dst + kPEmbB, w.emb_b, D, tid);
+__device__ __forceinline__ void stage_params(float *dst, const BlockW &w, int tid) {
     stage_vec(dst + kPPos, w.pos, S * D, tid);
     for (int l = 0; l < w.layers; ++l) {
         float *d = dst + kPLayer + l * kPLayerSize;
         const LayerW &L = w.layer[l];
-        stage_vec(d + kPInB, L.in_b, 3 * D, tid); stage_vec(d + kPOutB, L.out_b, D, tid);
         stage_vec(d + kPN1W, L.n1_w, D, tid); stage_vec(d + kPN1B, L.n1_b, D, tid);
-        stage_vec(d + kPL1B, L.l1_b, FF, tid); stage_vec(d + kPL2B, L.l2_b, D, tid);
         stage_vec(d + kPN2W, L.n2_w, D, tid); stage_vec(d + kPN2B, L.n2_b, D, tid);
     }
-    stage_vec(dst + kPLayer + w.layers * kPLayerSize, head.b1, HID, tid);
 }
 
 __global__ void __launch_bounds__(kFusedThreads, 1)
@@ -200,7 +198,8 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
     unsigned char *sX = smem, *sQ = smem + kTileBytes, *sK = sQ + kTileBytes, *sV = sK + kTileBytes;
     unsigned char *sH = sQ;                               // [128 x 256] canonical, aliases sQ + sK after attention
     unsigned char *sW = smem + 4 * kTileBytes;
-    float *const sP = reinterpret_cast<float *>(sW + kWBytes);
+    unsigned char *sB = sW + kWBytes, *sOnes = sB + kBBytes;
+    float *const sP = reinterpret_cast<float *>(sOnes + kOnesBytes);
     const int tid = threadIdx.x, warp = tid >> 5;
     // LayerNorm partial sums {sum, sum of squares} per (column part, row): 4 KB at the start of sV, which is idle in both
     // residual epilogues (after the attention has consumed V; before the next V epilogue rewrites it)
@@ -212,8 +211,13 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
         mbar_init(&mbar, 1); mbar_init(&mbar2, 1); mbar_init(&wbar, 1); fence_mbar_init();
         s_item[0] = atomicAdd(work_counter, 1);
     }
-    stage_params(sP + kPActor, w_actor, head_actor, tid);
-    stage_params(sP + kPCritic, w_critic, head_critic, tid);
+    stage_params(sP + kPActor, w_actor, tid);
+    stage_params(sP + kPCritic, w_critic, tid);
+    if (tid < 256) {   // the ones operand, canonical [128 x 16]: 16-byte chunk = (8-row group, k half, row); 1.0 at k = 0, 1
+        const int kh = (tid >> 3) & 1;
+        *reinterpret_cast<uint4 *>(sOnes + (tid >> 4) * 256 + kh * 128 + (tid & 7) * 16) = make_uint4(kh ? 0u : 0x3F803F80u, 0u, 0u, 0u);
+    }
+    fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -257,6 +261,7 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
                 hi[j] = __bfloat162float(__float2bfloat16(o[j]));
                 lo[j] = o[j] - hi[j];
             }
+            hi[14] = 1.0f; hi[15] = 1.0f;            // against the bias columns of emb_w2p
             *reinterpret_cast<uint4 *>(sQ + canon_off(r, 0, 32)) = pack8(hi);
             *reinterpret_cast<uint4 *>(sQ + canon_off(r, 8, 32)) = pack8(hi + 8);
             *reinterpret_cast<uint4 *>(sQ + canon_off(r, 16, 32)) = pack8(lo);
@@ -268,7 +273,7 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
         tc_fence_after();
         mbar_wait(&wbar, wparity); wparity ^= 1;
         if (tid == 0) {
-            bulk_load(sW, w.layer[0].in_wp, 2 * D * D * 2, &wbar);       // Wq|Wk of layer 0 streams in behind the embedding
+            bulk_load2(sW, w.layer[0].in_wp, 2 * D * D * 2, sB, w.layer[0].in_bp, 2 * D * kBiasK * 2, &wbar);   // Wq|Wk of layer 0
             issue_gemm(tmem, sQ, sK, D, 32, &mbar);
         }
         mbar_wait(&mbar, parity); parity ^= 1;
@@ -276,15 +281,13 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
         {
             const bool valid = row < nrows;
             const int c0 = part * 32;
-            float2 eb[16], ep[16];
-            load_cols32(pw + kPEmbB + c0, eb);
+            float2 ep[16];
             load_cols32(pw + kPPos + (row % S) * D + c0, ep);
             float v[32];
             tmem_ld32(tmem_lane + c0, v);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-                float2 u = __fadd2_rn(make_float2(v[2 * i], v[2 * i + 1]), eb[i]);
-                u = __fadd2_rn(make_float2(fmaxf(u.x, 0.0f), fmaxf(u.y, 0.0f)), ep[i]);
+                const float2 u = __fadd2_rn(make_float2(fmaxf(v[2 * i], 0.0f), fmaxf(v[2 * i + 1], 0.0f)), ep[i]);
                 v[2 * i] = valid ? u.x : 0.0f; v[2 * i + 1] = valid ? u.y : 0.0f;
             }
 #pragma unroll
@@ -301,18 +304,18 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
             // ---- Q|K = X [Wq|Wk]^T (N = 256), then V = X Wv^T (N = 128) under the Q / K epilogues -> sQ | sK | sV ----
             tc_fence_after();
             mbar_wait(&wbar, wparity); wparity ^= 1;                      // Wq|Wk has landed in sW
-            if (tid == 0) issue_gemm(tmem, sX, sW, 2 * D, D, &mbar);
+            if (tid == 0) issue_gemm(tmem, sX, sW, 2 * D, D, &mbar, sB, sOnes);
             mbar_wait(&mbar, parity); parity ^= 1;
             tc_fence_after();
-            if (tid == 0) bulk_load(sW, L.in_wp + 2 * D * D, D * D * 2, &wbar);      // Wv (rows 256..383 of the packed Win)
-            epilogue_bias_act(tmem_lane, row, pl + kPInB, part * 32, part * 32 + 32, false, sQ, D, D);
+            if (tid == 0) bulk_load2(sW, L.in_wp + 2 * D * D, D * D * 2, sB, L.in_bp + 2 * D * kBiasK, D * kBiasK * 2, &wbar);   // Wv (rows 256..383)
+            epilogue_act(tmem_lane, row, part * 32, part * 32 + 32, false, sQ, D, D);
             mbar_wait(&wbar, wparity); wparity ^= 1;                      // Wv has landed
-            if (tid == 0) issue_gemm(tmem + 2 * D, sX, sW, D, D, &mbar);
-            epilogue_bias_act(tmem_lane, row, pl + kPInB, D + part * 32, D + part * 32 + 32, false, sQ, D, D);
+            if (tid == 0) issue_gemm(tmem + 2 * D, sX, sW, D, D, &mbar, sB, sOnes);
+            epilogue_act(tmem_lane, row, D + part * 32, D + part * 32 + 32, false, sQ, D, D);
             mbar_wait(&mbar, parity); parity ^= 1;
             tc_fence_after();
-            if (tid == 0) bulk_load(sW, L.out_wp, D * D * 2, &wbar);      // out-proj weights stream in behind the rest
-            epilogue_bias_act(tmem_lane, row, pl + kPInB, 2 * D + part * 32, 2 * D + part * 32 + 32, false, sQ, D, D);
+            if (tid == 0) bulk_load2(sW, L.out_wp, D * D * 2, sB, L.out_bp, D * kBiasK * 2, &wbar);   // out-proj weights stream in behind the rest
+            epilogue_act(tmem_lane, row, 2 * D + part * 32, 2 * D + part * 32 + 32, false, sQ, D, D);
             tc_fence_before();
             __syncthreads();
             // ---- attention over the 5-token window; output overwrites the Q slice.  A warp takes a (query, head) pair and its
@@ -383,11 +386,11 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
             // ---- out-proj + residual + LayerNorm1 (in place in sX); FFN1 weights stream in ----
             tc_fence_after();
             mbar_wait(&wbar, wparity); wparity ^= 1;
-            if (tid == 0) issue_gemm(tmem, sQ, sW, D, D, &mbar);
+            if (tid == 0) issue_gemm(tmem, sQ, sW, D, D, &mbar, sB, sOnes);
             mbar_wait(&mbar, parity); parity ^= 1;
             tc_fence_after();
-            if (tid == 0) bulk_load(sW, L.l1_wp, FF * D * 2, &wbar);
-            epilogue_residual_ln(tmem_lane, row, part, pl + kPOutB, pl + kPN1W, pl + kPN1B, sX, s_part);
+            if (tid == 0) bulk_load2(sW, L.l1_wp, FF * D * 2, sB, L.l1_bp, FF * kBiasK * 2, &wbar);
+            epilogue_residual_ln(tmem_lane, row, part, pl + kPN1W, pl + kPN1B, sX, s_part);
             fence_async_smem();
             tc_fence_before();
             __syncthreads();
@@ -396,30 +399,30 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
             tc_fence_after();
             mbar_wait(&wbar, wparity); wparity ^= 1;
             if (tid == 0) {
-                issue_gemm(tmem, sX, sW, FF / 2, D, &mbar);
-                issue_gemm(tmem + FF / 2, sX, sW + (FF / 2) * D * 2, FF / 2, D, &mbar2);
+                issue_gemm(tmem, sX, sW, FF / 2, D, &mbar, sB, sOnes);
+                issue_gemm(tmem + FF / 2, sX, sW + (FF / 2) * D * 2, FF / 2, D, &mbar2, sB + (FF / 2) * kBiasK * 2, sOnes);
             }
             mbar_wait(&mbar, parity); parity ^= 1;
             tc_fence_after();
-            epilogue_bias_act(tmem_lane, row, pl + kPL1B, part * 32, part * 32 + 32, true, sH, FF, FF);
+            epilogue_act(tmem_lane, row, part * 32, part * 32 + 32, true, sH, FF, FF);
             mbar_wait(&mbar2, parity2); parity2 ^= 1;
             tc_fence_after();
-            if (tid == 0) bulk_load(sW, L.l2_wp, D * FF * 2, &wbar);
-            epilogue_bias_act(tmem_lane, row, pl + kPL1B, FF / 2 + part * 32, FF / 2 + part * 32 + 32, true, sH, FF, FF);
+            if (tid == 0) bulk_load2(sW, L.l2_wp, D * FF * 2, sB, L.l2_bp, D * kBiasK * 2, &wbar);
+            epilogue_act(tmem_lane, row, FF / 2 + part * 32, FF / 2 + part * 32 + 32, true, sH, FF, FF);
             fence_async_smem();
             tc_fence_before();
             __syncthreads();
             // ---- FFN2 + residual + LayerNorm2 (in place in sX); the next GEMM's weights stream in ----
             tc_fence_after();
             mbar_wait(&wbar, wparity); wparity ^= 1;
-            if (tid == 0) issue_gemm(tmem, sH, sW, D, FF, &mbar);
+            if (tid == 0) issue_gemm(tmem, sH, sW, D, FF, &mbar, sB, sOnes);
             mbar_wait(&mbar, parity); parity ^= 1;
             tc_fence_after();
             if (tid == 0) {
-                if (!last_layer) bulk_load(sW, w.layer[l + 1].in_wp, 2 * D * D * 2, &wbar);
-                else bulk_load(sW, head.w1p, HID * D * 2, &wbar);        // last layer: the head's first layer
+                if (!last_layer) bulk_load2(sW, w.layer[l + 1].in_wp, 2 * D * D * 2, sB, w.layer[l + 1].in_bp, 2 * D * kBiasK * 2, &wbar);
+                else bulk_load2(sW, head.w1p, HID * D * 2, sB, head.b1p, HID * kBiasK * 2, &wbar);   // last layer: the head's first layer
             }
-            epilogue_residual_ln(tmem_lane, row, part, pl + kPL2B, pl + kPN2W, pl + kPN2B, sX, s_part);
+            epilogue_residual_ln(tmem_lane, row, part, pl + kPN2W, pl + kPN2B, sX, s_part);
             fence_async_smem();
             tc_fence_before();
             __syncthreads();
@@ -427,7 +430,7 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
         // ---- head first layer: relu(W1 z + b1) for the newest token of every sample (transformer_net.py:106-108) ----
         tc_fence_after();
         mbar_wait(&wbar, wparity); wparity ^= 1;
-        if (tid == 0) issue_gemm(tmem, sX, sW, HID, D, &mbar);
+        if (tid == 0) issue_gemm(tmem, sX, sW, HID, D, &mbar, sB, sOnes);
         {   // the next work item's observation rows arrive under the head GEMM and its epilogue
             const int next = s_item[cur ^ 1];
             have_obs = next < num_items;
@@ -442,15 +445,10 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
             const bool keep = row < nrows && row % S == S - 1;
             __nv_bfloat16 *dst = head_hidden + (size_t)(s0 + row / S) * HID;
             const int c0 = part * 32;
-            float2 hb[16];
-            load_cols32(pw + kPLayer + w.layers * kPLayerSize + c0, hb);
             float v[32];
             tmem_ld32(tmem_lane + c0, v);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float2 u = __fadd2_rn(make_float2(v[2 * i], v[2 * i + 1]), hb[i]);
-                v[2 * i] = fmaxf(u.x, 0.0f); v[2 * i + 1] = fmaxf(u.y, 0.0f);
-            }
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
             if (keep) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4 *>(dst + c0 + g * 8) = pack8(v + g * 8);

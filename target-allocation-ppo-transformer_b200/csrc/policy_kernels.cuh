@@ -15,11 +15,24 @@ using namespace uavp;
 __device__ __forceinline__ int canon_elem(int n, int k, int K) { return (n >> 3) * (K * 8) + (k >> 3) * 64 + (n & 7) * 8 + (k & 7); }
 
 // [128 x 14] fp32 embedding weight -> [128 x 32] bf16, canonical order, the 14 columns duplicated at 0.. and 16..
-__global__ void emb_w2_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ out) {
+// columns 14 / 15: the embedding bias as bf16 + rounding remainder (the A operand carries ones in these two columns)
+__global__ void emb_w2_kernel(const float *__restrict__ w, const float *__restrict__ b, __nv_bfloat16 *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= D * 32) return;
     const int d = i / 32, c = i % 32, j = c % 16;
-    out[canon_elem(d, c, 32)] = __float2bfloat16(j < F ? w[d * F + j] : 0.0f);
+    float v = j < F ? w[d * F + j] : 0.0f;
+    if (c == 14) v = b[d];
+    if (c == 15) v = b[d] - __bfloat162float(__float2bfloat16(b[d]));
+    out[canon_elem(d, c, 32)] = __float2bfloat16(v);
+}
+
+// bias [N] fp32 -> [N x 16] bf16 B-operand in canonical order: column 0 = bf16(b), column 1 = b - bf16(b), rest zero
+__global__ void pack_bias_kernel(const float *__restrict__ b, __nv_bfloat16 *__restrict__ out, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * 16) return;
+    const int n = i / 16, c = i % 16;
+    const float hi = __bfloat162float(__float2bfloat16(b[n]));
+    out[canon_elem(n, c, 16)] = __float2bfloat16(c == 0 ? hi : (c == 1 ? b[n] - hi : 0.0f));
 }
 
 // row-major fp32 [N x K] -> bf16 in canonical order (one bulk TMA copy then stages a whole B operand)

@@ -153,6 +153,12 @@ __device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, 
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
 }
 
+// the copy alone (the caller has posted the bytes of all the copies of this phase with ONE mbar_expect_tx)
+__device__ __forceinline__ void bulk_copy(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
+}
+
 // 2-D TMA tensor load (UTMALDG) of one box at element coordinates (c0 = innermost, c1) of the tensor map; completion is
 // signalled on the mbarrier as a transaction count (post the expected bytes with mbar_expect_tx first).  ONE thread.
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *mbar, uint32_t bytes) {
