@@ -29,6 +29,9 @@ typedef struct uavpolicy uavpolicy_t;
 int uavpolicy_create(int32_t device, int32_t max_batch, uavpolicy_t **out);
 int uavpolicy_destroy(uavpolicy_t *p);
 const char *uavpolicy_last_error(const uavpolicy_t *p);
+/* version of this ABI (struct layouts, argument lists); the Python binding refuses a library that reports another */
+#define UAVPOLICY_ABI_VERSION 2
+int uavpolicy_abi_version(void);
 
 /* Load the network weights from ONE flat fp32 device buffer holding every parameter in
  * `TransformerActorCritic.named_parameters()` order (== state_dict order of the reference network):

@@ -158,6 +158,9 @@ def load_policy():
             raise ImportError("libuavpolicy_b200.so is %s and could not be (re)built (%s)" % (
                 "stale" if os.path.isfile(path) else "missing", exc)) from exc
     L = C.CDLL(path)
+    L.uavpolicy_abi_version.restype = C.c_int
+    if L.uavpolicy_abi_version() != 2:
+        raise ImportError("libuavpolicy_b200.so ABI version mismatch")
     vp, i32, u64 = C.c_void_p, C.c_int32, C.c_uint64
     L.uavpolicy_create.argtypes = [i32, i32, C.POINTER(vp)]
     L.uavpolicy_destroy.argtypes = [vp]

@@ -167,6 +167,8 @@ static size_t map_head(HeadW &h, int outs, const float *w32, const __nv_bfloat16
     return off;
 }
 
+extern "C" int uavpolicy_abi_version(void) { return UAVPOLICY_ABI_VERSION; }
+
 extern "C" const char *uavpolicy_last_error(const uavpolicy_t *p) { return p ? p->err.c_str() : g_err.c_str(); }
 
 extern "C" int uavpolicy_create(int32_t device, int32_t max_batch, uavpolicy_t **out) {
