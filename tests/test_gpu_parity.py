@@ -221,10 +221,14 @@ def test_step_host_equals_device_step_and_non_binary_actions_skip():
         a = torch.randint(-2, 4, (B,), generator=g, dtype=torch.int64)   # anything but 1 is Skip (uav_env.py:344)
         a_bin = (a == 1).to(torch.int64)
         o1, r1, d1, _ = e1.step(a_bin.cuda())
-        if s % 3 == 0:
-            r2, d2 = e2.step_host(a.pin_memory())                 # pinned int64: in place over PCIe
-        elif s % 3 == 1:
-            r2, d2 = e2.step_host(a.to(torch.int8).pin_memory())  # one byte per action
+        if s % 4 == 0:
+            r2, d2 = e2.step_host(a.pin_memory())                 # pinned int64: in place over PCIe (a bulk copy per CTA)
+        elif s % 4 == 1:
+            r2, d2 = e2.step_host(a.to(torch.int8).pin_memory())  # one byte per action (the 44-env tail CTA: plain loads)
+        elif s % 4 == 2:
+            odd = torch.zeros(B + 1, dtype=torch.int8).pin_memory()   # a pinned buffer that is not 16 B aligned: plain loads
+            odd[1:] = a.to(torch.int8)
+            r2, d2 = e2.step_host(odd[1:])
         else:
             r2, d2 = e2.step_host(a.clone(), reward_out=torch.zeros(B), done_out=torch.zeros(B, dtype=torch.uint8))
         assert torch.equal(r1.cpu(), r2) and torch.equal(d1.cpu(), d2.bool())   # pageable: staging copies
