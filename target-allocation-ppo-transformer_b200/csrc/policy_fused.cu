@@ -17,7 +17,7 @@ using namespace uavp;
 // M = 128 of tcgen05.mma).  Activations never leave the SM: the layer input X lives in shared memory as a UMMA
 // A-operand (canonical K-major tile), each GEMM accumulates in TMEM, the epilogue threads (FOUR per row: TMEM lane =
 // row, each thread a quarter of the columns - a warp can only read the 32 TMEM lanes of its quadrant, so the way to
-// put more threads on an epilogue is more warps per quadrant) apply bias / ReLU / residual + LayerNorm and write the
+// put more threads on an epilogue is more warps per quadrant) apply ReLU / residual + LayerNorm and write the
 // next A-operand back to shared memory.  Weights stream L2 -> shared memory by bulk TMA behind the running epilogue.
 // In the LAST layer of a network only the newest token of a sample is consumed (transformer_net.py:106): its attention
 // is evaluated for that query alone (a fifth of the CUDA-core work of the layer).
@@ -28,9 +28,7 @@ using namespace uavp;
 //                            a constant A operand of ones - ONE more k-step per GEMM adds the bias on the tensor core
 //                            (bf16 value + rounding remainder in two columns), so no epilogue loads or adds a bias |
 //                            11 KB: the LayerNorm / position vectors of both networks, staged once per CTA (warp-uniform
-//                            operands of the epilogues: as global loads they kept missing the little L1 that is left; a
-//                            broadcast load still costs a full 128 B/cycle pass of the shared-memory pipe per 32 lanes x 4 B,
-//                            which is why the biases went to the tensor core instead)
+//                            operands of the epilogues: as global loads they kept missing the little L1 that is left)
 //   TMEM: 512 columns; Q|K uses [0,256), V [256,384), the other GEMMs [0,256) / [0,128) / [0,64).  TMEM reads are
 //   64 B per cycle per SM, so reading a [128 x N] fp32 accumulator costs 8 N cycles - more than its MMAs (4.2 N): wherever
 //   a GEMM has independent column blocks (Q|K vs V, the two halves of the FFN hidden layer) the second block's MMAs run
@@ -47,8 +45,6 @@ constexpr uint32_t kWBytes = 64 * 1024;                            // sW: the la
 constexpr uint32_t kBBytes = 2 * D * kBiasK * 2;                   // sB: its bias operand, [<= 256 x 16] bf16 (8 KB)
 constexpr uint32_t kOnesBytes = 128 * kBiasK * 2;                  // the A operand of the bias k-step: ones in columns 0, 1
 constexpr size_t kFusedSmem = 4 * (size_t)kTileBytes + kWBytes + kBBytes + kOnesBytes + (size_t)(kPActorSize + kPCriticSize) * 4;
-
-struct Phase { uint32_t parity = 0; };
 
 // issue D[tmem cols 0..N) = A[128 x K] * W[N x K]^T (+ 1 * bias^T) as K/16 (+ 1) k-steps, N <= 256; thread 0 only.
 // sBias: the [N x 16] bias operand (or NULL), sOnes: the [128 x 16] A operand with ones in columns 0 and 1

@@ -509,6 +509,7 @@ __global__ void __launch_bounds__(kStepThreads, 512 / kStepThreads) step_kernel(
                     TgtRec *tp = P.tgt + P.toff(slot, b) + m;
                     tp->nh = nh2; tp->nh_pure = c_nhp * (1.0 - c_pd);
                     tp->lock_cost = c_lock_cost + c_ucost; tp->lock_tag = make_tag(c_lock_cnt + 1, episode_new - 1);
+                    tp->id = c_tid;   // (unchanged value: the record's second 32 B sector is then written WHOLE - no fill read)
                     P.assigned[(size_t)b * N + k] = c_tid;                               // :308
                     rev = rev2; cost_sum = cost2;
                     if (c_lock_cnt == 0) { covered_val += c_value; n0 = n02; }
