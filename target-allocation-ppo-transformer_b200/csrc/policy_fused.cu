@@ -37,7 +37,10 @@ constexpr int kTileSamples = 25;                                   // 125 valid 
 constexpr int kFusedThreads = 512, kColParts = kFusedThreads / 128;   // column parts per row
 constexpr uint32_t kTileBytes = 128 * D * 2;                       // a [128 x 128] bf16 canonical tile
 // parameter vectors in shared memory (float offsets).  per network: pos | per layer: LayerNorm gamma / beta x 2
-constexpr int kPPos = 0, kPLayer = S * D, kPLayerSize = 4 * D;
+// (position rows are kPosStride floats apart: the lanes of a quarter-warp read up to 5 different position rows at the same
+// column, and rows a multiple of 128 B apart would put them on the same banks - a 5-way conflict on every 16-byte load)
+constexpr int kPosStride = D + 4;
+constexpr int kPPos = 0, kPLayer = S * kPosStride, kPLayerSize = 4 * D;
 constexpr int kPN1W = 0, kPN1B = D, kPN2W = 2 * D, kPN2B = 3 * D;
 constexpr int kPActor = 0, kPActorSize = kPLayer + 1 * kPLayerSize, kPCritic = kPActorSize, kPCriticSize = kPLayer + 2 * kPLayerSize;
 static_assert(kPActorSize % 4 == 0 && kPLayer % 4 == 0 && kPLayerSize % 4 == 0, "16-byte loads of the staged vectors");
@@ -174,7 +177,7 @@ __device__ __forceinline__ void stage_vec(float *dst, const float *__restrict__ 
     for (int i = tid; i < n; i += kFusedThreads) dst[i] = __ldg(src + i);
 }
 __device__ __forceinline__ void stage_params(float *dst, const BlockW &w, int tid) {
-    stage_vec(dst + kPPos, w.pos, S * D, tid);
+    for (int i = tid; i < S * D; i += kFusedThreads) dst[kPPos + (i / D) * kPosStride + i % D] = __ldg(w.pos + i);
     for (int l = 0; l < w.layers; ++l) {
         float *d = dst + kPLayer + l * kPLayerSize;
         const LayerW &L = w.layer[l];
@@ -278,7 +281,7 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
             const bool valid = row < nrows;
             const int c0 = part * 32;
             float2 ep[16];
-            load_cols32(pw + kPPos + (row % S) * D + c0, ep);
+            load_cols32(pw + kPPos + (row % S) * kPosStride + c0, ep);
             float v[32];
             tmem_ld32(tmem_lane + c0, v);
 #pragma unroll
