@@ -83,6 +83,26 @@ def test_padding_rows_and_batch_tails(fused_kernel):
     fused.close()
 
 
+def test_fused_forward_is_bit_reproducible():
+    """Work items are handed out dynamically and shared memory is re-used across phases and items: any race or stale read
+    would show up as run-to-run differences.  Ten forwards of the same 3000 windows must agree bit for bit."""
+    from target_allocation_ppo_transformer_b200.networks.fused_forward import FusedPolicyForward
+    net, _ = _net()
+    B = 3000
+    fused = FusedPolicyForward(B, "cuda")
+    fused.sync(net)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    obs = torch.rand(B, 5, 14, device="cuda", generator=g)
+    obs[::3, :2] = 0.0
+    fused.get_action(obs, step=1)
+    ref_logits, ref_v = fused.logits[:B].clone(), fused.values[:B].clone() if hasattr(fused, "values") else None
+    v0 = fused.get_action(obs, step=1)[2].clone()
+    for _ in range(10):
+        v = fused.get_action(obs, step=1)[2]
+        assert torch.equal(fused.logits[:B], ref_logits) and torch.equal(v, v0)
+    fused.close()
+
+
 def test_sampling_is_counter_based_and_follows_the_probabilities():
     from target_allocation_ppo_transformer_b200.networks.fused_forward import FusedPolicyForward
     net, _ = _net()
