@@ -98,9 +98,11 @@ __device__ __forceinline__ void load_cols32(const float *p, float2 *o) {   // p:
     }
 }
 
-// plain layer: out = act(acc) -> bf16; column c goes to tile (c / tile_cols) of dst, canonical row length Kout
-__device__ __forceinline__ void epilogue_act(uint32_t tmem_lane, int row, int c_begin, int c_end, bool relu, unsigned char *dst,
-                                             int Kout, int tile_cols) {
+// plain layer: out = act(acc) -> bf16; column c goes to tile (c / tile_cols) of dst, canonical row length Kout.  The thread's
+// accumulator row lands in row dst_row of the tile (its own row, or a compacted one); `store` = false only loads (tcgen05.ld
+// is warp-collective)
+__device__ __forceinline__ void epilogue_act(uint32_t tmem_lane, int dst_row, bool store, int c_begin, int c_end, bool relu,
+                                             unsigned char *dst, int Kout, int tile_cols) {
     for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         float v[32];
         tmem_ld32(tmem_lane + c0, v);
@@ -109,9 +111,11 @@ __device__ __forceinline__ void epilogue_act(uint32_t tmem_lane, int row, int c_
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
         }
         unsigned char *tile = dst + (c0 / tile_cols) * kTileBytes;
+        if (store) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-            *reinterpret_cast<uint4 *>(tile + canon_off(row, (c0 % tile_cols) + g * 8, Kout)) = pack8(v + g * 8);
+            for (int g = 0; g < 4; ++g)
+                *reinterpret_cast<uint4 *>(tile + canon_off(dst_row, (c0 % tile_cols) + g * 8, Kout)) = pack8(v + g * 8);
+        }
     }
 }
 
@@ -173,6 +177,13 @@ __device__ __forceinline__ void load_obs_row(const float *__restrict__ obs, int 
     for (int j = 0; j < 16; ++j) o[j] = (valid && j < F) ? __ldg(obs + ((size_t)s0 * S + r) * F + j) : 0.0f;
 }
 
+// the newest token (position S - 1) of sample s0 + r, zero beyond nsamp samples
+__device__ __forceinline__ void load_newest_obs_row(const float *__restrict__ obs, int s0, int nsamp, int r, float *o) {
+    const bool valid = r < nsamp;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] = (valid && j < F) ? __ldg(obs + ((size_t)(s0 + r) * S + (S - 1)) * F + j) : 0.0f;
+}
+
 __device__ __forceinline__ void stage_vec(float *dst, const float *__restrict__ src, int n, int tid) {
     for (int i = tid; i < n; i += kFusedThreads) dst[i] = __ldg(src + i);
 }
@@ -186,11 +197,16 @@ __device__ __forceinline__ void stage_params(float *dst, const BlockW &w, int ti
     }
 }
 
+constexpr int kMaxGroupTiles = 5;   // an actor work item: up to 5 tiles = 125 samples (the rows of one compact tile)
+
 __global__ void __launch_bounds__(kFusedThreads, 1)
 fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW head_actor, __nv_bfloat16 *__restrict__ hh_actor,
-                   BlockW w_critic, HeadW head_critic, __nv_bfloat16 *__restrict__ hh_critic, int *__restrict__ work_counter) {
+                   BlockW w_critic, HeadW head_critic, __nv_bfloat16 *__restrict__ hh_critic, int *__restrict__ work_counter,
+                   int group_tiles /* tiles per actor work item, 1..5 */) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ uint64_t mbar, mbar2, wbar;                // MMA completion (two in flight) / weight staging (bulk TMA)
+    // MMA completion (two in flight) / weight staging by bulk TMA (wbar: the matrix in sW; ebar: the embedding operand in sK,
+    // which is in flight together with the first Wq|Wk)
+    __shared__ uint64_t mbar, mbar2, wbar, ebar;
     __shared__ uint32_t tmem_base_s;
     __shared__ int s_item[2];                             // this work item / the next one (fetched a whole item ahead)
     __shared__ uint8_t s_pad[128];
@@ -199,15 +215,17 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
     unsigned char *sW = smem + 4 * kTileBytes;
     unsigned char *sB = sW + kWBytes, *sOnes = sB + kBBytes;
     float *const sP = reinterpret_cast<float *>(sOnes + kOnesBytes);
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // LayerNorm partial sums {sum, sum of squares} per (column part, row): 4 KB at the start of sV, which is idle in both
     // residual epilogues (after the attention has consumed V; before the next V epilogue rewrites it)
     float2 (*s_part)[128] = reinterpret_cast<float2 (*)[128]>(sV);
     const int row = tid & 127, part = warp >> 2;          // thread = (row, column quarter); TMEM lane = row
-    const int num_tiles = (B + kTileSamples - 1) / kTileSamples, num_items = 2 * num_tiles;
+    const int num_tiles = (B + kTileSamples - 1) / kTileSamples, num_groups = (num_tiles + group_tiles - 1) / group_tiles;
+    const int group_samples = group_tiles * kTileSamples;
+    const int num_items = num_groups + num_tiles;
     if (warp == 0) tmem_alloc(&tmem_base_s, 512);
     if (tid == 0) {
-        mbar_init(&mbar, 1); mbar_init(&mbar2, 1); mbar_init(&wbar, 1); fence_mbar_init();
+        mbar_init(&mbar, 1); mbar_init(&mbar2, 1); mbar_init(&wbar, 1); mbar_init(&ebar, 1); fence_mbar_init();
         s_item[0] = atomicAdd(work_counter, 1);
     }
     stage_params(sP + kPActor, w_actor, tid);
@@ -222,38 +240,21 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
     const uint32_t tmem_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    uint32_t parity = 0, parity2 = 0, wparity = 0;
+    uint32_t parity = 0, parity2 = 0, wparity = 0, eparity = 0;
     int cur = 0;
-    float o[16];                                          // this thread's observation row (tid < 128), fetched an item ahead
+    float o[16];                                          // this thread's observation row (tid < 128), fetched ahead of its use
     bool have_obs = false;
 
-    // work items = (network, tile), handed out dynamically, the two-layer critic tiles first (longest first)
-    for (;;) {
-        const int item = s_item[cur];
-        if (item >= num_items) break;
-        if (tid == 0) s_item[cur ^ 1] = atomicAdd(work_counter, 1);   // read after the barriers of this item
-        const bool is_critic = item < num_tiles;
-        const BlockW &w = is_critic ? w_critic : w_actor;
-        const HeadW &head = is_critic ? head_critic : head_actor;
-        const float *const pw = sP + (is_critic ? kPCritic : kPActor);
-        __nv_bfloat16 *head_hidden = is_critic ? hh_critic : hh_actor;
-        const int tile = is_critic ? item : item - num_tiles;
-        const int s0 = tile * kTileSamples;
-        const int nsamp = min(kTileSamples, B - s0), nrows = nsamp * S;
-        // ---- embedding: X = relu(obs W^T + b) + pos (transformer_net.py:24-30,57-59); key-padding mask (:52-54).
-        //      On the tensor cores with K = 32: the fp32 observation row is split into bf16 hi + lo parts
-        //      (columns 0..13 and 16..29) against the weight duplicated in both halves, so the product keeps ~16
-        //      mantissa bits of the input.  A operand staged in sQ, B operand in sK; Wq|Wk of layer 0 streams into sW. ----
-        if (tid == 0) {
-            bulk_load(sK, w.emb_w2p, D * 32 * 2, &wbar);                  // embedding weights (B operand, K = 32)
-        }
+    // first sample of work item `it`: actor groups come first (the longest items), then the critic tiles
+    auto item_first_sample = [&](int it) { return it < num_groups ? it * group_samples : (it - num_groups) * kTileSamples; };
+
+    // ---- embedding of the 128 staged rows: X = relu(obs W^T + b) + pos (transformer_net.py:24-30,57-59) -> sX.
+    //      On the tensor cores with K = 32: the fp32 observation row is split into bf16 hi + lo parts (columns 0..13 and
+    //      16..29) against the weight duplicated in both halves, so the product keeps ~16 mantissa bits of the input; columns
+    //      14 / 15 are ones against the bias.  A operand: this thread's row o[] -> sV; B operand: emb_w2p -> sK (bulk TMA).
+    //      position < 0: token r sits at position r % S of its window ----
+    auto embed_rows = [&](const BlockW &w, const float *pw, int nvalid, int position) {
         if (tid < 128) {
-            const int r = tid;
-            if (!have_obs) load_obs_row(obs, s0, nrows, r, o);
-            float asum = 0.0f;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) asum += fabsf(o[j]);
-            s_pad[r] = (r < nrows && asum == 0.0f && r % S != S - 1) ? 1 : 0;
             float hi[16], lo[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -261,27 +262,24 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
                 lo[j] = o[j] - hi[j];
             }
             hi[14] = 1.0f; hi[15] = 1.0f;            // against the bias columns of emb_w2p
-            *reinterpret_cast<uint4 *>(sQ + canon_off(r, 0, 32)) = pack8(hi);
-            *reinterpret_cast<uint4 *>(sQ + canon_off(r, 8, 32)) = pack8(hi + 8);
-            *reinterpret_cast<uint4 *>(sQ + canon_off(r, 16, 32)) = pack8(lo);
-            *reinterpret_cast<uint4 *>(sQ + canon_off(r, 24, 32)) = pack8(lo + 8);
+            *reinterpret_cast<uint4 *>(sV + canon_off(tid, 0, 32)) = pack8(hi);
+            *reinterpret_cast<uint4 *>(sV + canon_off(tid, 8, 32)) = pack8(hi + 8);
+            *reinterpret_cast<uint4 *>(sV + canon_off(tid, 16, 32)) = pack8(lo);
+            *reinterpret_cast<uint4 *>(sV + canon_off(tid, 24, 32)) = pack8(lo + 8);
         }
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
-        mbar_wait(&wbar, wparity); wparity ^= 1;
-        if (tid == 0) {
-            bulk_load2(sW, w.layer[0].in_wp, 2 * D * D * 2, sB, w.layer[0].in_bp, 2 * D * kBiasK * 2, &wbar);   // Wq|Wk of layer 0
-            issue_gemm(tmem, sQ, sK, D, 32, &mbar);
-        }
+        mbar_wait(&ebar, eparity); eparity ^= 1;
+        if (tid == 0) issue_gemm(tmem, sV, sK, D, 32, &mbar);
         mbar_wait(&mbar, parity); parity ^= 1;
         tc_fence_after();
         {
-            const bool valid = row < nrows;
+            const bool valid = row < nvalid;
             const int c0 = part * 32;
             float2 ep[16];
-            load_cols32(pw + kPPos + (row % S) * kPosStride + c0, ep);
+            load_cols32(pw + kPPos + (position < 0 ? row % S : position) * kPosStride + c0, ep);
             float v[32];
             tmem_ld32(tmem_lane + c0, v);
 #pragma unroll
@@ -295,154 +293,214 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
+    };
 
-        for (int l = 0; l < w.layers; ++l) {
-            const LayerW &L = w.layer[l];
-            const float *const pl = pw + kPLayer + l * kPLayerSize;
-            const bool last_layer = l + 1 == w.layers;    // only the newest token's output is consumed after it
-            // ---- Q|K = X [Wq|Wk]^T (N = 256), then V = X Wv^T (N = 128) under the Q / K epilogues -> sQ | sK | sV ----
-            tc_fence_after();
-            mbar_wait(&wbar, wparity); wparity ^= 1;                      // Wq|Wk has landed in sW
-            if (tid == 0) issue_gemm(tmem, sX, sW, 2 * D, D, &mbar, sB, sOnes);
-            mbar_wait(&mbar, parity); parity ^= 1;
-            tc_fence_after();
-            if (tid == 0) bulk_load2(sW, L.in_wp + 2 * D * D, D * D * 2, sB, L.in_bp + 2 * D * kBiasK, D * kBiasK * 2, &wbar);   // Wv (rows 256..383)
-            epilogue_act(tmem_lane, row, part * 32, part * 32 + 32, false, sQ, D, D);
-            mbar_wait(&wbar, wparity); wparity ^= 1;                      // Wv has landed
-            if (tid == 0) issue_gemm(tmem + 2 * D, sX, sW, D, D, &mbar, sB, sOnes);
-            epilogue_act(tmem_lane, row, D + part * 32, D + part * 32 + 32, false, sQ, D, D);
-            mbar_wait(&mbar, parity); parity ^= 1;
-            tc_fence_after();
-            if (tid == 0) bulk_load2(sW, L.out_wp, D * D * 2, sB, L.out_bp, D * kBiasK * 2, &wbar);   // out-proj weights stream in behind the rest
-            epilogue_act(tmem_lane, row, 2 * D + part * 32, 2 * D + part * 32 + 32, false, sQ, D, D);
-            tc_fence_before();
-            __syncthreads();
-            // ---- attention over the 5-token window; output overwrites the Q slice.  A warp takes a (query, head) pair and its
-            //      lanes the samples: the 8 lanes of a quarter-warp then read 8 different rows (5 is odd: row & 7 distinct) of
-            //      the same 16-byte column chunk - conflict-free.  (One thread per (sample, head, query) in flat
-            //      order put the heads of a sample, 256 B apart, on the same banks: 8-way conflicts on every access.) ----
-            {
-                const int npair = (last_layer ? 1 : S) * H, lane = tid & 31;
-                for (int pair = warp; pair < npair; pair += kFusedThreads / 32) {   // (dense packing of the 1000 items over
-                    const int h = pair % H, i = last_layer ? S - 1 : pair / H;      //  the 512 threads measured slower)
-                    if (lane < nsamp) {
-                        const int smp = lane;
-                        const int r = smp * S + i;
-                        unsigned char *pq = sQ + canon_off(r, h * DH, D);
-                        float2 q2[8];
-                        {
-                            float q[DH];
-                            unpack8(*reinterpret_cast<const uint4 *>(pq), q);
-                            unpack8(*reinterpret_cast<const uint4 *>(pq + 128), q + 8);
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) q2[e] = make_float2(q[2 * e], q[2 * e + 1]);
-                        }
-                        float sc[S], mx = -INFINITY;
-#pragma unroll
-                        for (int j = 0; j < S; ++j) {
-                            float kk[DH];
-                            const unsigned char *pk = sK + canon_off(smp * S + j, h * DH, D);
-                            unpack8(*reinterpret_cast<const uint4 *>(pk), kk);
-                            unpack8(*reinterpret_cast<const uint4 *>(pk + 128), kk + 8);
-                            float2 acc = make_float2(0.0f, 0.0f), acc1 = make_float2(0.0f, 0.0f);
-#pragma unroll
-                            for (int e = 0; e < 8; e += 2) {
-                                acc = __ffma2_rn(q2[e], make_float2(kk[2 * e], kk[2 * e + 1]), acc);
-                                acc1 = __ffma2_rn(q2[e + 1], make_float2(kk[2 * e + 2], kk[2 * e + 3]), acc1);
-                            }
-                            const float sdot = (acc.x + acc.y) + (acc1.x + acc1.y);
-                            sc[j] = s_pad[smp * S + j] ? -INFINITY : sdot * 0.25f;
-                            mx = fmaxf(mx, sc[j]);
-                        }
-                        float den = 0.0f;
-#pragma unroll
-                        for (int j = 0; j < S; ++j) { sc[j] = __expf(sc[j] - mx); den += sc[j]; }
-                        const float inv = 1.0f / den;
-                        float2 o2[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) o2[e] = make_float2(0.0f, 0.0f);
-#pragma unroll
-                        for (int j = 0; j < S; ++j) {
-                            float vv[DH];
-                            const unsigned char *pv = sV + canon_off(smp * S + j, h * DH, D);
-                            unpack8(*reinterpret_cast<const uint4 *>(pv), vv);
-                            unpack8(*reinterpret_cast<const uint4 *>(pv + 128), vv + 8);
-                            const float pj = sc[j] * inv;
-                            const float2 pj2 = make_float2(pj, pj);
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) o2[e] = __ffma2_rn(pj2, make_float2(vv[2 * e], vv[2 * e + 1]), o2[e]);
-                        }
-                        float ov[DH];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) { ov[2 * e] = o2[e].x; ov[2 * e + 1] = o2[e].y; }
-                        *reinterpret_cast<uint4 *>(pq) = pack8(ov);
-                        *reinterpret_cast<uint4 *>(pq + 128) = pack8(ov + 8);
-                    }
-                }
-            }
-            fence_async_smem();
-            __syncthreads();
-            // ---- out-proj + residual + LayerNorm1 (in place in sX); FFN1 weights stream in ----
-            tc_fence_after();
-            mbar_wait(&wbar, wparity); wparity ^= 1;
-            if (tid == 0) issue_gemm(tmem, sQ, sW, D, D, &mbar, sB, sOnes);
-            mbar_wait(&mbar, parity); parity ^= 1;
-            tc_fence_after();
-            if (tid == 0) bulk_load2(sW, L.l1_wp, FF * D * 2, sB, L.l1_bp, FF * kBiasK * 2, &wbar);
-            epilogue_residual_ln(tmem_lane, row, part, pl + kPN1W, pl + kPN1B, sX, s_part);
-            fence_async_smem();
-            tc_fence_before();
-            __syncthreads();
-            // ---- FFN1 + ReLU -> sH [128 x 256], as two column halves: the second half's MMAs run under the first half's
-            //      epilogue; FFN2 weights ([128 x 256]) stream in ----
-            tc_fence_after();
-            mbar_wait(&wbar, wparity); wparity ^= 1;
-            if (tid == 0) {
-                issue_gemm(tmem, sX, sW, FF / 2, D, &mbar, sB, sOnes);
-                issue_gemm(tmem + FF / 2, sX, sW + (FF / 2) * D * 2, FF / 2, D, &mbar2, sB + (FF / 2) * kBiasK * 2, sOnes);
-            }
-            mbar_wait(&mbar, parity); parity ^= 1;
-            tc_fence_after();
-            epilogue_act(tmem_lane, row, part * 32, part * 32 + 32, true, sH, FF, FF);
-            mbar_wait(&mbar2, parity2); parity2 ^= 1;
-            tc_fence_after();
-            if (tid == 0) bulk_load2(sW, L.l2_wp, D * FF * 2, sB, L.l2_bp, D * kBiasK * 2, &wbar);
-            epilogue_act(tmem_lane, row, FF / 2 + part * 32, FF / 2 + part * 32 + 32, true, sH, FF, FF);
-            fence_async_smem();
-            tc_fence_before();
-            __syncthreads();
-            // ---- FFN2 + residual + LayerNorm2 (in place in sX); the next GEMM's weights stream in ----
-            tc_fence_after();
-            mbar_wait(&wbar, wparity); wparity ^= 1;
-            if (tid == 0) issue_gemm(tmem, sH, sW, D, FF, &mbar, sB, sOnes);
-            mbar_wait(&mbar, parity); parity ^= 1;
-            tc_fence_after();
-            if (tid == 0) {
-                if (!last_layer) bulk_load2(sW, w.layer[l + 1].in_wp, 2 * D * D * 2, sB, w.layer[l + 1].in_bp, 2 * D * kBiasK * 2, &wbar);
-                else bulk_load2(sW, head.w1p, HID * D * 2, sB, head.b1p, HID * kBiasK * 2, &wbar);   // last layer: the head's first layer
-            }
-            epilogue_residual_ln(tmem_lane, row, part, pl + kPN2W, pl + kPN2B, sX, s_part);
-            fence_async_smem();
-            tc_fence_before();
-            __syncthreads();
+    // ---- Q|K = X [Wq|Wk]^T (N = 256), then V = X Wv^T (N = 128) under the K epilogue -> sQ | sK | sV, and the attention over the
+    //      5-token window (its output overwrites the Q rows).  all_queries: every token is a query (an inner layer); otherwise
+    //      only the newest token of a sample (transformer_net.py:106), and with qbase >= 0 its Q row / attention output live
+    //      in COMPACT row qbase + sample of sQ (the actor collects the newest tokens of 5 tiles there).  next_w / next_b: the
+    //      matrix (and bias operand) to stream into sW once V's MMAs have retired ----
+    auto qkv_attention = [&](const LayerW &L, int nsamp, bool all_queries, int qbase, const __nv_bfloat16 *next_w, uint32_t next_w_bytes,
+                             const __nv_bfloat16 *next_b, uint32_t next_b_bytes) {
+        tc_fence_after();
+        mbar_wait(&wbar, wparity); wparity ^= 1;                      // Wq|Wk has landed in sW
+        if (tid == 0) issue_gemm(tmem, sX, sW, 2 * D, D, &mbar, sB, sOnes);
+        mbar_wait(&mbar, parity); parity ^= 1;
+        tc_fence_after();
+        if (tid == 0) bulk_load2(sW, L.in_wp + 2 * D * D, D * D * 2, sB, L.in_bp + 2 * D * kBiasK, D * kBiasK * 2, &wbar);   // Wv (rows 256..383)
+        {
+            const bool newest = row % S == S - 1 && row < nsamp * S;
+            epilogue_act(tmem_lane, qbase >= 0 ? qbase + row / S : row, qbase < 0 || newest, part * 32, part * 32 + 32, false, sQ, D, D);
         }
+        mbar_wait(&wbar, wparity); wparity ^= 1;                      // Wv has landed
+        if (tid == 0) issue_gemm(tmem + 2 * D, sX, sW, D, D, &mbar, sB, sOnes);
+        epilogue_act(tmem_lane, row, true, D + part * 32, D + part * 32 + 32, false, sQ, D, D);
+        mbar_wait(&mbar, parity); parity ^= 1;
+        tc_fence_after();
+        if (tid == 0) bulk_load2(sW, next_w, next_w_bytes, sB, next_b, next_b_bytes, &wbar);
+        epilogue_act(tmem_lane, row, true, 2 * D + part * 32, 2 * D + part * 32 + 32, false, sQ, D, D);
+        tc_fence_before();
+        __syncthreads();
+        // A warp takes a (query, head) pair and its lanes the samples: the 8 lanes of a quarter-warp then read 8 different rows
+        // (5 is odd: row & 7 distinct) of the same 16-byte column chunk - conflict-free.  (One thread per (sample, head, query)
+        // in flat order put the heads of a sample, 256 B apart, on the same banks: 8-way conflicts on every access; dense
+        // packing of the 1000 items of an inner layer over the 512 threads measured slower than the three rounds here.)
+        const int npair = (all_queries ? S : 1) * H;
+        for (int pair = warp; pair < npair; pair += kFusedThreads / 32) {
+            const int h = pair % H, i = all_queries ? pair / H : S - 1;
+            if (lane < nsamp) {
+                const int smp = lane, r = qbase >= 0 ? qbase + smp : smp * S + i;
+                unsigned char *pq = sQ + canon_off(r, h * DH, D);
+                float2 q2[8];
+                {
+                    float q[DH];
+                    unpack8(*reinterpret_cast<const uint4 *>(pq), q);
+                    unpack8(*reinterpret_cast<const uint4 *>(pq + 128), q + 8);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) q2[e] = make_float2(q[2 * e], q[2 * e + 1]);
+                }
+                float sc[S], mx = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < S; ++j) {
+                    float kk[DH];
+                    const unsigned char *pk = sK + canon_off(smp * S + j, h * DH, D);
+                    unpack8(*reinterpret_cast<const uint4 *>(pk), kk);
+                    unpack8(*reinterpret_cast<const uint4 *>(pk + 128), kk + 8);
+                    float2 acc = make_float2(0.0f, 0.0f), acc1 = make_float2(0.0f, 0.0f);
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) {
+                        acc = __ffma2_rn(q2[e], make_float2(kk[2 * e], kk[2 * e + 1]), acc);
+                        acc1 = __ffma2_rn(q2[e + 1], make_float2(kk[2 * e + 2], kk[2 * e + 3]), acc1);
+                    }
+                    const float sdot = (acc.x + acc.y) + (acc1.x + acc1.y);
+                    sc[j] = s_pad[smp * S + j] ? -INFINITY : sdot * 0.25f;
+                    mx = fmaxf(mx, sc[j]);
+                }
+                float den = 0.0f;
+#pragma unroll
+                for (int j = 0; j < S; ++j) { sc[j] = __expf(sc[j] - mx); den += sc[j]; }
+                const float inv = 1.0f / den;
+                float2 o2[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o2[e] = make_float2(0.0f, 0.0f);
+#pragma unroll
+                for (int j = 0; j < S; ++j) {
+                    float vv[DH];
+                    const unsigned char *pv = sV + canon_off(smp * S + j, h * DH, D);
+                    unpack8(*reinterpret_cast<const uint4 *>(pv), vv);
+                    unpack8(*reinterpret_cast<const uint4 *>(pv + 128), vv + 8);
+                    const float pj = sc[j] * inv;
+                    const float2 pj2 = make_float2(pj, pj);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o2[e] = __ffma2_rn(pj2, make_float2(vv[2 * e], vv[2 * e + 1]), o2[e]);
+                }
+                float ov[DH];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { ov[2 * e] = o2[e].x; ov[2 * e + 1] = o2[e].y; }
+                *reinterpret_cast<uint4 *>(pq) = pack8(ov);
+                *reinterpret_cast<uint4 *>(pq + 128) = pack8(ov + 8);
+            }
+        }
+        fence_async_smem();
+        __syncthreads();
+    };
+
+    // ---- the rest of an encoder layer on the rows of sQ (attention output) and sX (layer input = residual): out-proj +
+    //      LayerNorm1, FFN (hidden layer as two column halves: the second half's MMAs run under the first half's epilogue),
+    //      LayerNorm2 - in place in sX.  Out-proj weights are in flight on wbar; next_w / next_b follow W2 ----
+    auto post_attention = [&](const LayerW &L, const float *pl, const __nv_bfloat16 *next_w, uint32_t next_w_bytes,
+                              const __nv_bfloat16 *next_b, uint32_t next_b_bytes) {
+        tc_fence_after();
+        mbar_wait(&wbar, wparity); wparity ^= 1;
+        if (tid == 0) issue_gemm(tmem, sQ, sW, D, D, &mbar, sB, sOnes);
+        mbar_wait(&mbar, parity); parity ^= 1;
+        tc_fence_after();
+        if (tid == 0) bulk_load2(sW, L.l1_wp, FF * D * 2, sB, L.l1_bp, FF * kBiasK * 2, &wbar);
+        epilogue_residual_ln(tmem_lane, row, part, pl + kPN1W, pl + kPN1B, sX, s_part);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        mbar_wait(&wbar, wparity); wparity ^= 1;
+        if (tid == 0) {
+            issue_gemm(tmem, sX, sW, FF / 2, D, &mbar, sB, sOnes);
+            issue_gemm(tmem + FF / 2, sX, sW + (FF / 2) * D * 2, FF / 2, D, &mbar2, sB + (FF / 2) * kBiasK * 2, sOnes);
+        }
+        mbar_wait(&mbar, parity); parity ^= 1;
+        tc_fence_after();
+        epilogue_act(tmem_lane, row, true, part * 32, part * 32 + 32, true, sH, FF, FF);
+        mbar_wait(&mbar2, parity2); parity2 ^= 1;
+        tc_fence_after();
+        if (tid == 0) bulk_load2(sW, L.l2_wp, D * FF * 2, sB, L.l2_bp, D * kBiasK * 2, &wbar);
+        epilogue_act(tmem_lane, row, true, FF / 2 + part * 32, FF / 2 + part * 32 + 32, true, sH, FF, FF);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        mbar_wait(&wbar, wparity); wparity ^= 1;
+        if (tid == 0) issue_gemm(tmem, sH, sW, D, FF, &mbar, sB, sOnes);
+        mbar_wait(&mbar, parity); parity ^= 1;
+        tc_fence_after();
+        if (tid == 0) bulk_load2(sW, next_w, next_w_bytes, sB, next_b, next_b_bytes, &wbar);
+        epilogue_residual_ln(tmem_lane, row, part, pl + kPN2W, pl + kPN2B, sX, s_part);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+    };
+
+    // Work items, handed out dynamically, longest first:
+    //   actor group  = up to 5 tiles of 25 samples (fewer when the batch is too small to give every SM several items).  The actor's only layer is a LAST layer: per tile it needs the embedding, the QKV
+    //                  projection and the attention of the newest token - whose 25 output rows are collected in COMPACT rows
+    //                  of sQ, so that out-proj, FFN, both LayerNorms and the head run ONCE per 125 samples on a full M = 128
+    //                  tile instead of five times on tiles with 25 useful rows (their residual input, X of the newest tokens,
+    //                  is embedded again: one K = 32 product);
+    //   critic tile  = 25 samples = 125 token rows through the inner layer, then the same last-layer scheme on its own rows.
+    for (;;) {
+        const int item = s_item[cur];
+        if (item >= num_items) break;
+        if (tid == 0) s_item[cur ^ 1] = atomicAdd(work_counter, 1);   // read after the barriers of this item
+        const bool is_actor = item < num_groups;
+        const BlockW &w = is_actor ? w_actor : w_critic;
+        const HeadW &head = is_actor ? head_actor : head_critic;
+        const float *const pw = sP + (is_actor ? kPActor : kPCritic);
+        __nv_bfloat16 *head_hidden = is_actor ? hh_actor : hh_critic;
+        const int g0 = item_first_sample(item);                       // first sample of the item
+        const int item_samples = min(is_actor ? group_samples : kTileSamples, B - g0);
+        const int ntiles = (item_samples + kTileSamples - 1) / kTileSamples;
+        const LayerW &LL = w.layer[w.layers - 1];                     // the last layer
+        const float *const pll = pw + kPLayer + (w.layers - 1) * kPLayerSize;
+        if (tid == 0)   // sW / sB are free since the previous item's head GEMM retired: the first Wq|Wk has the whole embedding to land
+            bulk_load2(sW, w.layer[0].in_wp, 2 * D * D * 2, sB, w.layer[0].in_bp, 2 * D * kBiasK * 2, &wbar);
+        for (int tl = 0; tl < ntiles; ++tl) {
+            const int s0 = g0 + tl * kTileSamples;
+            const int nsamp = min(kTileSamples, B - s0), nrows = nsamp * S;
+            if (tid == 0) bulk_load(sK, w.emb_w2p, D * 32 * 2, &ebar);    // embedding weights (B operand, K = 32)
+            if (tid < 128) {   // this tile's token rows (fetched ahead, normally) and the key-padding mask (transformer_net.py:52-54)
+                if (!have_obs) load_obs_row(obs, s0, nrows, tid, o);
+                float asum = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) asum += fabsf(o[j]);
+                s_pad[tid] = (tid < nrows && asum == 0.0f && tid % S != S - 1) ? 1 : 0;
+            }
+            have_obs = false;
+            embed_rows(w, pw, nrows, -1);
+            if (!is_actor) {   // the critic's inner layer: every token is a query; Wq|Wk of the last layer follows W2
+                qkv_attention(w.layer[0], nsamp, true, -1, w.layer[0].out_wp, D * D * 2, w.layer[0].out_bp, D * kBiasK * 2);
+                post_attention(w.layer[0], pw + kPLayer, LL.in_wp, 2 * D * D * 2, LL.in_bp, 2 * D * kBiasK * 2);
+            }
+            // last layer: the newest token's attention.  Behind V's MMAs: the next tile's Wq|Wk, or the out-proj weights
+            const bool more = tl + 1 < ntiles;
+            if (more && tid < 128) {   // the next tile's token rows arrive under this tile's projections and attention
+                const int ns0 = s0 + kTileSamples;
+                load_obs_row(obs, ns0, min(kTileSamples, B - ns0) * S, tid, o);
+            }
+            qkv_attention(LL, nsamp, false, is_actor ? tl * kTileSamples : -1, more ? LL.in_wp : LL.out_wp,
+                          more ? 2 * D * D * 2 : D * D * 2, more ? LL.in_bp : LL.out_bp, more ? 2 * D * kBiasK * 2 : D * kBiasK * 2);
+            have_obs = more;
+        }
+        if (is_actor) {   // X of the newest tokens again: the residual input of what follows, one row per sample
+            if (tid == 0) bulk_load(sK, w.emb_w2p, D * 32 * 2, &ebar);
+            if (tid < 128) load_newest_obs_row(obs, g0, item_samples, tid, o);
+            embed_rows(w, pw, item_samples, S - 1);
+        }
+        post_attention(LL, pll, head.w1p, HID * D * 2, head.b1p, HID * kBiasK * 2);
         // ---- head first layer: relu(W1 z + b1) for the newest token of every sample (transformer_net.py:106-108) ----
         tc_fence_after();
         mbar_wait(&wbar, wparity); wparity ^= 1;
         if (tid == 0) issue_gemm(tmem, sX, sW, HID, D, &mbar, sB, sOnes);
-        {   // the next work item's observation rows arrive under the head GEMM and its epilogue
+        {   // the next work item's first token rows arrive under the head GEMM and its epilogue
             const int next = s_item[cur ^ 1];
             have_obs = next < num_items;
             if (have_obs && tid < 128) {
-                const int ns0 = (next < num_tiles ? next : next - num_tiles) * kTileSamples;
+                const int ns0 = item_first_sample(next);
                 load_obs_row(obs, ns0, min(kTileSamples, B - ns0) * S, tid, o);
             }
         }
         mbar_wait(&mbar, parity); parity ^= 1;
         tc_fence_after();
-        if (part < HID / 32) {   // tcgen05.ld is warp-collective: every lane loads, only the newest-token rows store
-            const bool keep = row < nrows && row % S == S - 1;
-            __nv_bfloat16 *dst = head_hidden + (size_t)(s0 + row / S) * HID;
+        if (part < HID / 32) {   // tcgen05.ld is warp-collective: every lane loads, only the rows of newest tokens store
+            const bool keep = is_actor ? row < item_samples : (row < item_samples * S && row % S == S - 1);
+            __nv_bfloat16 *dst = head_hidden + (size_t)(g0 + (is_actor ? row : row / S)) * HID;
             const int c0 = part * 32;
             float v[32];
             tmem_ld32(tmem_lane + c0, v);
@@ -511,15 +569,19 @@ int fused_block_prepare() {
 int launch_fused_blocks(const float *d_obs, int B, const BlockW &actor, const HeadW &actor_head, __nv_bfloat16 *hh_actor,
                         const BlockW &critic, const HeadW &critic_head, __nv_bfloat16 *hh_critic, int *d_work_counter,
                         cudaStream_t stream) {
-    const int items = 2 * ((B + kTileSamples - 1) / kTileSamples);
+    const int tiles = (B + kTileSamples - 1) / kTileSamples;
     static int num_sms = 0;                       // one persistent CTA per SM of the device
     if (num_sms == 0) {
         int dev = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -2;
     }
+    if (actor.layers != 1 || critic.layers != 2) return -1;   // the kernel's item structure (and its staged parameter layout)
+    // tiles per actor work item: as many as a compact tile holds once every SM still gets several items
+    const int group_tiles = tiles >= 4 * num_sms ? kMaxGroupTiles : (tiles >= 2 * num_sms ? 3 : (tiles >= num_sms ? 2 : 1));
+    const int items = tiles + (tiles + group_tiles - 1) / group_tiles;
     if (cudaMemsetAsync(d_work_counter, 0, sizeof(int), stream) != cudaSuccess) return -2;
     fused_block_kernel<<<items < num_sms ? items : num_sms, kFusedThreads, kFusedSmem, stream>>>(
-        d_obs, B, actor, actor_head, hh_actor, critic, critic_head, hh_critic, d_work_counter);
+        d_obs, B, actor, actor_head, hh_actor, critic, critic_head, hh_critic, d_work_counter, group_tiles);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 }  // namespace uavp

@@ -83,20 +83,40 @@ def test_padding_rows_and_batch_tails(fused_kernel):
     fused.close()
 
 
-def test_fused_forward_is_bit_reproducible():
-    """Work items are handed out dynamically and shared memory is re-used across phases and items: any race or stale read
-    would show up as run-to-run differences.  Ten forwards of the same 3000 windows must agree bit for bit."""
+def test_actor_work_items_of_several_tiles_at_large_batches():
+    """From about 3700 windows on, an actor work item covers 2, 3 or 5 tiles whose newest-token rows share one compact
+    tile (csrc/policy_fused.cu): sizes around every switch, with ragged last tiles and last groups."""
     from target_allocation_ppo_transformer_b200.networks.fused_forward import FusedPolicyForward
     net, _ = _net()
-    B = 3000
+    fused = FusedPolicyForward(16500, "cuda")
+    fused.sync(net)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    for B in (3699, 3700, 3751, 7399, 7437, 14799, 14800 + 13, 16384, 16500):
+        obs = torch.rand(B, 5, 14, device="cuda", generator=g)
+        obs[:, :, 13] = 1.0
+        lead = torch.arange(B, device="cuda") % 5                    # episode starts: 0..4 leading zero rows
+        obs[torch.arange(5, device="cuda")[None, :] < lead[:, None]] = 0.0
+        _, _, v, _ = fused.get_action(obs, step=3)
+        with torch.no_grad():
+            ref_logits, ref_v = net.logits_and_value(obs)
+        assert float((fused.logits[:B] - ref_logits).abs().max()) < 3e-2, B
+        assert float((v - ref_v).abs().max()) < 3e-2 * max(1.0, float(ref_v.abs().max())), B
+    fused.close()
+
+
+def test_fused_forward_is_bit_reproducible():
+    """Work items are handed out dynamically and shared memory is re-used across phases and items: any race or stale read
+    would show up as run-to-run differences.  Ten forwards of the same 15013 windows must agree bit for bit."""
+    from target_allocation_ppo_transformer_b200.networks.fused_forward import FusedPolicyForward
+    net, _ = _net()
+    B = 15013
     fused = FusedPolicyForward(B, "cuda")
     fused.sync(net)
     g = torch.Generator(device="cuda").manual_seed(5)
     obs = torch.rand(B, 5, 14, device="cuda", generator=g)
     obs[::3, :2] = 0.0
-    fused.get_action(obs, step=1)
-    ref_logits, ref_v = fused.logits[:B].clone(), fused.values[:B].clone() if hasattr(fused, "values") else None
     v0 = fused.get_action(obs, step=1)[2].clone()
+    ref_logits = fused.logits[:B].clone()
     for _ in range(10):
         v = fused.get_action(obs, step=1)[2]
         assert torch.equal(fused.logits[:B], ref_logits) and torch.equal(v, v0)
