@@ -363,7 +363,11 @@ def main():
         # lead-in: ~0.25 ms of untimed flush work queued ahead of the first bracket, so that the host (which comes out of
         # the barrier late under torchrun) is enqueueing ahead of the GPU when bracket 0 opens - a bracket only measures
         # the kernel if its launch is already waiting in the stream (without this, bracket 0 read 40-120 us at N > 1)
-        flush_l2(0); flush_l2(1)
+        # (two untimed steps ride along: at N > 1 the first step after the barrier's NCCL kernel read ~30 us against 18.5 for
+        # every later one - one cold bracket in 20 is 0.6 us on the mean)
+        for j in range(2):
+            flush_l2(j)
+            step_fn(n_warm + j)
         for i in range(n_timed):
             flush_l2(i)
             ev[i][0].record(stream)
