@@ -244,11 +244,15 @@ __device__ __forceinline__ double penetration_prob(const Params &P, const NfzRec
     return p;
 }
 
-// derived fields of a UAV record from its velocity and the scene's obstacles Z[K1], I[K2] (any address space)
-__device__ __forceinline__ void finish_uav(const Params &P, const NfzRec *Z, const IntRec *I, UavRec &u, double vx, double vy) {
+// derived fields of a UAV record from its velocity (unit heading, 1/speed) ...
+__device__ __forceinline__ void finish_uav_kinematics(UavRec &u, double vx, double vy) {
     const double speed = sqrt(vx * vx + vy * vy);
     if (speed < 1e-6) { u.wx = 1.0; u.wy = 0.0; u.inv_speed = -1.0; }
     else { u.wx = vx / speed; u.wy = vy / speed; u.inv_speed = 1.0 / speed; }
+}
+// ... and from the scene's obstacles Z[K1], I[K2] (any address space)
+__device__ __forceinline__ void finish_uav(const Params &P, const NfzRec *Z, const IntRec *I, UavRec &u, double vx, double vy) {
+    finish_uav_kinematics(u, vx, vy);
     u.p_pen = penetration_prob(P, Z, I, u);
 }
 __device__ __forceinline__ void finish_uav(const Params &P, int slot, int b, UavRec &u, double vx, double vy) {

@@ -117,9 +117,11 @@ __device__ __forceinline__ void warp_generate_obstacles(const Params &P, int b, 
 }
 
 // entities [32*c, 32*c+32) of chunk c: target chunks first, then UAV chunks; Z / I: the scene's obstacles, already
-// visible to this warp (the UAV chunks need them for p_pen)
+// visible to this warp (the UAV chunks need them for p_pen).  A UAV chunk can be produced in two stages (the pre-generation
+// service runs them in different launches: p_pen - two acos, four exp - is as long as everything else of the chunk):
+// stage 0 = the whole record, 1 = everything but p_pen, 2 = p_pen of the records stage 1 has written
 __device__ void warp_generate_chunk(const Params &P, int slot, int b, uint32_t scene, int chunk, uint32_t *s_keys,
-                                    const NfzRec *Z, const IntRec *I) {
+                                    const NfzRec *Z, const IntRec *I, int stage = 0) {
     const int lane = threadIdx.x & 31;
     const uint32_t k0 = P.seed_lo, k1 = P.seed_hi, env = P.env_id_base + (uint32_t)b;
     const int N = P.N, M = P.M, tchunks = (M + 31) / 32;
@@ -156,6 +158,15 @@ __device__ void warp_generate_chunk(const Params &P, int slot, int b, uint32_t s
     } else {
         // UAVs [32*c, 32*c+32): N//4 of type 2, uniformly permuted (uav_env.py:81-84); kinematics (:88-111)
         const int i = (chunk - tchunks) * 32 + lane;
+        if (stage == 2) {
+            if (i < N) {
+                UavRec *up = P.uav + P.uoff(slot, b) + i;
+                const UavRec u = *up;
+                up->p_pen = penetration_prob(P, Z, I, u);
+            }
+            __syncwarp();
+            return;
+        }
         for (int j = lane; j < N; j += 32) s_keys[j] = philox4x32(k0, k1, j, S_UAV_TYPE, scene, env).x;
         __syncwarp();
         if (i < N) {
@@ -172,7 +183,8 @@ __device__ void warp_generate_chunk(const Params &P, int slot, int b, uint32_t s
             u.load = base_load * P.weather_load;                                      // :107
             const double ang = (-15.0 + (15.0 - (-15.0)) * u53(d.z, d.w)) * (3.141592653589793 / 180.0);  // :110
             const double vx = cos(ang) * real_speed, vy = sin(ang) * real_speed;      // :111
-            finish_uav(P, Z, I, u, vx, vy);
+            if (stage == 0) finish_uav(P, Z, I, u, vx, vy);
+            else { finish_uav_kinematics(u, vx, vy); u.p_pen = 1.0; }
             P.uav[P.uoff(slot, b) + i] = u;
             P.uav_vel[P.uoff(slot, b) + i] = make_double2(vx, vy);
             P.uav_type[P.uoff(slot, b) + i] = type;
@@ -205,7 +217,9 @@ __device__ __noinline__ void warp_generate_scene(const Params &P, int slot, int 
 //   launches 1..P-2     PROCESS  job j = (queue entry, chunk of 32 entities) -> warp j of the round; a warp re-generates the
 //                                few obstacles in its own shared-memory scratch, so jobs are independent and a whole batch
 //                                of scenes costs ONE chunk latency, hidden behind the step's main CTAs; jobs whose env has
-//                                moved on since the scan (I_GEN changed, or the scene was delivered by reset()) are dropped
+//                                moved on since the scan (I_GEN changed, or the scene was delivered by reset()) are dropped.
+//                                A UAV chunk is two jobs in different launches - the record without p_pen, then p_pen: as one
+//                                job it outlasted the main CTAs by ~9 us (every 16th step read 27-29 us instead of 18.5)
 //   launch P-1          PUBLISH  entries with all chunks in: I_NEXT_TAG = scene index (I_GEN still unchanged)
 // Single writer per word: owner -> I_GEN; service -> I_NEXT_TAG, the queues and the other slot's records.  An owner that
 // sees the tag flips; its record reads are ordered after the service's writes by >= 1 kernel boundary.  Whatever is not
@@ -229,7 +243,9 @@ __device__ __noinline__ void pregen_service(const Params &P, int service_cta, in
     const int q = (int)((s_tick / (uint32_t)kServicePeriod) & 1u);
     int32_t *const q_env = P.q_env + (size_t)q * P.B, *const q_gen = P.q_gen + (size_t)q * P.B;
     int32_t *const q_done = P.q_done + (size_t)q * P.B;
-    const int nchunks = scene_chunks(P);
+    // jobs of a queue entry: its target chunks, its UAV chunks without p_pen (space A), then p_pen of its UAV chunks (space B,
+    // in launches AFTER the last launch of space A: stage 2 reads what stage 1 wrote)
+    const int tchunks = (P.M + 31) / 32, uchunks = (P.N + 31) / 32, chunks_a = tchunks + uchunks, nchunks = chunks_a + uchunks;
     if (phase == 0u) {
         // ---- SCAN: 8 consecutive envs per thread = one 32 B run of the I_GEN row and of the I_NEXT_TAG row of a tile
         if (service_cta == 0 && tid == 0) P.q_count[q ^ 1] = 0u;   // the other queue is idle during this whole period
@@ -272,25 +288,37 @@ __device__ __noinline__ void pregen_service(const Params &P, int service_cta, in
         }
         return;
     }
-    // ---- PROCESS, round phase-1: one (entry, chunk) job per warp
-    const long long job = (long long)(phase - 1u) * n_service * kWarpsPerCta + service_cta * kWarpsPerCta + warp;
-    if (job >= (long long)count * nchunks) return;
-    const int entry = (int)(job / nchunks), chunk = (int)(job % nchunks);
+    // ---- PROCESS, round phase-1: one job per warp
+    const long long cap = (long long)n_service * kWarpsPerCta, jobs_a = (long long)count * chunks_a, jobs_b = (long long)count * uchunks;
+    const long long rounds_a = (jobs_a + cap - 1) / cap, widx = (long long)service_cta * kWarpsPerCta + warp;
+    long long round = (long long)phase - 1;
+    int entry, chunk, stage;
+    if (round < rounds_a) {
+        const long long job = round * cap + widx;
+        if (job >= jobs_a) return;
+        entry = (int)(job / chunks_a); chunk = (int)(job % chunks_a); stage = 1;
+    } else {
+        const long long job = (round - rounds_a) * cap + widx;
+        if (job >= jobs_b) return;
+        entry = (int)(job / uchunks); chunk = tchunks + (int)(job % uchunks); stage = 2;
+    }
     const int eb = q_env[entry], gen = q_gen[entry];
     const Hdr h = P.header(eb);
     if (*(volatile int32_t *)&h.n(I_GEN) != gen || *(volatile int32_t *)&h.n(I_NEXT_TAG) == (gen >> 1)) return;  // stale
     const int scene = gen >> 1, slot = (gen & 1) ^ 1;
     NfzRec *Z = reinterpret_cast<NfzRec *>(s_scratch + (size_t)warp * kServiceScratchPerWarp);
     IntRec *I = reinterpret_cast<IntRec *>(Z + P.K1);
-    warp_generate_obstacles(P, eb, (uint32_t)scene, Z, I);
-    __syncwarp();
+    if (chunk == 0 || stage == 2) {   // (only the obstacle records themselves and p_pen need them)
+        warp_generate_obstacles(P, eb, (uint32_t)scene, Z, I);
+        __syncwarp();
+    }
     if (chunk == 0) {  // the records proper (scene readback)
         NfzRec *Zg = P.nfz + ((size_t)slot * P.B + eb) * P.K1;
         IntRec *Ig = P.intc + ((size_t)slot * P.B + eb) * P.K2;
         for (int i = lane; i < P.K1; i += 32) Zg[i] = Z[i];
         for (int i = lane; i < P.K2; i += 32) Ig[i] = I[i];
     }
-    warp_generate_chunk(P, slot, eb, (uint32_t)scene, chunk, s_keys, Z, I);
+    warp_generate_chunk(P, slot, eb, (uint32_t)scene, chunk, s_keys, Z, I, stage);
     if (lane == 0) atomicAdd(&q_done[entry], 1);
 }
 
