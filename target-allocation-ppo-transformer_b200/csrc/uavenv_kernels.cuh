@@ -306,17 +306,19 @@ __device__ __noinline__ void pregen_service(const Params &P, int service_cta, in
     const Hdr h = P.header(eb);
     if (*(volatile int32_t *)&h.n(I_GEN) != gen || *(volatile int32_t *)&h.n(I_NEXT_TAG) == (gen >> 1)) return;  // stale
     const int scene = gen >> 1, slot = (gen & 1) ^ 1;
-    NfzRec *Z = reinterpret_cast<NfzRec *>(s_scratch + (size_t)warp * kServiceScratchPerWarp);
-    IntRec *I = reinterpret_cast<IntRec *>(Z + P.K1);
-    if (chunk == 0 || stage == 2) {   // (only the obstacle records themselves and p_pen need them)
-        warp_generate_obstacles(P, eb, (uint32_t)scene, Z, I);
+    // the obstacles: chunk 0 generates them (in its shared-memory scratch) and writes the records; the p_pen jobs run in a
+    // later launch and read those records - nobody else needs them
+    NfzRec *Zg = P.nfz + ((size_t)slot * P.B + eb) * P.K1;
+    IntRec *Ig = P.intc + ((size_t)slot * P.B + eb) * P.K2;
+    const NfzRec *Z = Zg;
+    const IntRec *I = Ig;
+    if (chunk == 0) {
+        NfzRec *Zs = reinterpret_cast<NfzRec *>(s_scratch + (size_t)warp * kServiceScratchPerWarp);
+        IntRec *Is = reinterpret_cast<IntRec *>(Zs + P.K1);
+        warp_generate_obstacles(P, eb, (uint32_t)scene, Zs, Is);
         __syncwarp();
-    }
-    if (chunk == 0) {  // the records proper (scene readback)
-        NfzRec *Zg = P.nfz + ((size_t)slot * P.B + eb) * P.K1;
-        IntRec *Ig = P.intc + ((size_t)slot * P.B + eb) * P.K2;
-        for (int i = lane; i < P.K1; i += 32) Zg[i] = Z[i];
-        for (int i = lane; i < P.K2; i += 32) Ig[i] = I[i];
+        for (int i = lane; i < P.K1; i += 32) Zg[i] = Zs[i];
+        for (int i = lane; i < P.K2; i += 32) Ig[i] = Is[i];
     }
     warp_generate_chunk(P, slot, eb, (uint32_t)scene, chunk, s_keys, Z, I, stage);
     if (lane == 0) atomicAdd(&q_done[entry], 1);
