@@ -214,12 +214,12 @@ __device__ __noinline__ void warp_generate_scene(const Params &P, int slot, int 
 //   a period = kServicePeriod launches, counted by every service CTA on its own (all counters are equal)
 //   launch 0            SCAN     each CTA reads I_GEN / I_NEXT_TAG of its 1024 envs; an env whose other slot does not hold
 //                                scene I_GEN >> 1 yet is appended to the period's queue (its I_GEN word is captured)
-//   launches 1..P-2     PROCESS  job j = (queue entry, chunk of 32 entities) -> warp j of the round; a warp re-generates the
-//                                few obstacles in its own shared-memory scratch, so jobs are independent and a whole batch
-//                                of scenes costs ONE chunk latency, hidden behind the step's main CTAs; jobs whose env has
-//                                moved on since the scan (I_GEN changed, or the scene was delivered by reset()) are dropped.
-//                                A UAV chunk is two jobs in different launches - the record without p_pen, then p_pen: as one
-//                                job it outlasted the main CTAs by ~9 us (every 16th step read 27-29 us instead of 18.5)
+//   launches 1..P-2     PROCESS  job j = (queue entry, chunk of 32 entities) -> warp j of the round; jobs are independent, so a
+//                                whole batch of scenes costs ONE job latency per stage, hidden behind the step's main CTAs;
+//                                jobs whose env has moved on since the scan (I_GEN changed, or the scene was delivered by
+//                                reset()) are dropped.  A UAV chunk is two jobs in different launches - the record without
+//                                p_pen, then p_pen (from the obstacle records the scene's first job wrote): as one job it
+//                                outlasted the main CTAs by ~9 us (every 16th step read 27-29 us instead of 18.5)
 //   launch P-1          PUBLISH  entries with all chunks in: I_NEXT_TAG = scene index (I_GEN still unchanged)
 // Single writer per word: owner -> I_GEN; service -> I_NEXT_TAG, the queues and the other slot's records.  An owner that
 // sees the tag flips; its record reads are ordered after the service's writes by >= 1 kernel boundary.  Whatever is not
