@@ -97,7 +97,8 @@ struct uavpolicy {
     // bf16 activation workspaces (R = 5 * max_batch rows)
     __nv_bfloat16 *Ea, *Ec, *QKV, *ATT, *T, *Y, *Hf, *X1, *Q, *AL, *T1, *Y1, *Hs, *T2, *Za, *Zc;
     uint8_t *pad = nullptr;
-    int *work_counter = nullptr;          // dynamic work-item counter of the fused launch
+    int *work_counter = nullptr;          // dynamic work-item counters of the two fused launches
+    unsigned char *fused_scratch = nullptr;   // newest-token rows handed from the first fused launch to the second
     void *gemm_ws = nullptr;
     std::vector<void *> allocs;
     bool have_weights = false;
@@ -195,7 +196,9 @@ extern "C" int uavpolicy_create(int32_t device, int32_t max_batch, uavpolicy_t *
     for (auto b : small) if (e == cudaSuccess) e = palloc(p, b, B * D);
     if (e == cudaSuccess) e = palloc(p, &p->Hs, B * FF);
     if (e == cudaSuccess) e = palloc(p, &p->pad, R);
-    if (e == cudaSuccess) e = palloc(p, &p->work_counter, 1);
+    if (e == cudaSuccess) e = palloc(p, &p->work_counter, 2);
+    if (e == cudaSuccess) e = palloc(p, &p->fused_scratch, uavp::fused_scratch_bytes(max_batch));
+    if (e == cudaSuccess) e = cudaMemset(p->fused_scratch, 0, uavp::fused_scratch_bytes(max_batch));
     if (e == cudaSuccess) e = palloc(p, &p->wpk, (size_t)UPK_SIZE);
     if (e == cudaSuccess) e = palloc(p, &p->bpk, (size_t)3 * uavp::kLayerBiasElems + 2 * HID * uavp::kBiasK);
     if (e == cudaSuccess) e = palloc(p, &p->emb2_a, (size_t)D * 32);
@@ -331,7 +334,7 @@ extern "C" int uavpolicy_get_action(uavpolicy_t *p, const float *d_obs, int32_t 
     if (p->fused) {
         // two fused launches (actor block + head layer 1, critic block + head layer 1), then the per-sample outputs
         if (uavp::launch_fused_blocks(d_obs, B, p->actor, p->actor_head, p->T1, p->critic, p->critic_head, p->T2,
-                                      p->work_counter, c.s))
+                                      p->work_counter, p->fused_scratch, c.s))
             return pfail(p, -2, "fused block launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         heads_out_kernel<<<(B + 255) / 256, 256, 0, c.s>>>(p->T1, p->T2, p->actor_head, p->critic_head, B, (uint32_t)seed,
                                                            (uint32_t)(seed >> 32), step, env_id_base, d_action, d_logp, d_value,

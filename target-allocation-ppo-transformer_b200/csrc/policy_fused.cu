@@ -13,14 +13,13 @@ using namespace tc;
 using namespace uavp;
 
 // ------------------------------------------------------------------------------------------------------------
-// Fused encoder block.  One CTA (16 warps) owns a tile of 25 samples = 125 token rows (3 rows of padding make the
-// M = 128 of tcgen05.mma).  Activations never leave the SM: the layer input X lives in shared memory as a UMMA
-// A-operand (canonical K-major tile), each GEMM accumulates in TMEM, the epilogue threads (FOUR per row: TMEM lane =
+// Fused encoder blocks, two kernels (fused_body below).  One CTA (16 warps) owns a tile of 128 rows at a time: 25 samples =
+// 125 token rows (3 rows of padding make the M = 128 of tcgen05.mma) in the first kernel, the newest-token rows of 128
+// samples in the second.  Activations never leave the SM inside a kernel: the layer input X lives in shared memory as a
+// UMMA A-operand (canonical K-major tile), each GEMM accumulates in TMEM, the epilogue threads (FOUR per row: TMEM lane =
 // row, each thread a quarter of the columns - a warp can only read the 32 TMEM lanes of its quadrant, so the way to
 // put more threads on an epilogue is more warps per quadrant) apply ReLU / residual + LayerNorm and write the
 // next A-operand back to shared memory.  Weights stream L2 -> shared memory by bulk TMA behind the running epilogue.
-// In the LAST layer of a network only the newest token of a sample is consumed (transformer_net.py:106): its attention
-// is evaluated for that query alone (a fifth of the CUDA-core work of the layer).
 //
 //   shared memory (215 KB):  sX 32 KB | sQ sK sV 3 x 32 KB (attention output overwrites Q; the FFN hidden tile
 //                            [128 x 256] later aliases sQ+sK) | sW 64 KB (one weight matrix at a time; the QKV projection
@@ -177,13 +176,6 @@ __device__ __forceinline__ void load_obs_row(const float *__restrict__ obs, int 
     for (int j = 0; j < 16; ++j) o[j] = (valid && j < F) ? __ldg(obs + ((size_t)s0 * S + r) * F + j) : 0.0f;
 }
 
-// the newest token (position S - 1) of sample s0 + r, zero beyond nsamp samples
-__device__ __forceinline__ void load_newest_obs_row(const float *__restrict__ obs, int s0, int nsamp, int r, float *o) {
-    const bool valid = r < nsamp;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) o[j] = (valid && j < F) ? __ldg(obs + ((size_t)(s0 + r) * S + (S - 1)) * F + j) : 0.0f;
-}
-
 __device__ __forceinline__ void stage_vec(float *dst, const float *__restrict__ src, int n, int tid) {
     for (int i = tid; i < n; i += kFusedThreads) dst[i] = __ldg(src + i);
 }
@@ -197,15 +189,25 @@ __device__ __forceinline__ void stage_params(float *dst, const BlockW &w, int ti
     }
 }
 
-constexpr int kMaxGroupTiles = 5;   // an actor work item: up to 5 tiles = 125 samples (the rows of one compact tile)
+constexpr int kGroupRows = 128;   // samples per work item of the second kernel (one full M = 128 tile of newest-token rows)
 
-__global__ void __launch_bounds__(kFusedThreads, 1)
-fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW head_actor, __nv_bfloat16 *__restrict__ hh_actor,
-                   BlockW w_critic, HeadW head_critic, __nv_bfloat16 *__restrict__ hh_critic, int *__restrict__ work_counter,
-                   int group_tiles /* tiles per actor work item, 1..5 */) {
+// Both kernels of the forward share this body (kPhase picks the work loop):
+//   phase 0 (fused_tiles_kernel)  work item = (network, tile of 25 samples = 125 token rows): embedding, the critic's inner
+//            layer, and of the LAST layer the QKV projection and the attention of the newest token of each sample - all that
+//            is consumed of it (transformer_net.py:106).  The 25 newest-token rows (attention output, and the layer input =
+//            residual) go to a compact [samples x 128] bf16 scratch in canonical tile order (L2-resident).
+//   phase 1 (fused_heads_kernel)  work item = (network, 128 samples): the rest of the last layer - out-proj, LayerNorm1, FFN,
+//            LayerNorm2 - and the head's first layer, on FULL M = 128 tiles of those rows, bulk-copied from the scratch.
+// So the four fifths of a last layer that a tile-at-a-time kernel spends on rows nobody reads are not computed, every
+// product of phase 1 runs on a full tile, and its weights stream once per 128 samples instead of once per 25.
+template <int kPhase>
+__device__ __forceinline__ void fused_body(const float *__restrict__ obs, int B, const BlockW &w_actor, const HeadW &head_actor,
+                                           __nv_bfloat16 *__restrict__ hh_actor, const BlockW &w_critic, const HeadW &head_critic,
+                                           __nv_bfloat16 *__restrict__ hh_critic, int *__restrict__ work_counter,
+                                           unsigned char *__restrict__ scratch) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    // MMA completion (two in flight) / weight staging by bulk TMA (wbar: the matrix in sW; ebar: the embedding operand in sK,
-    // which is in flight together with the first Wq|Wk)
+    // MMA completion (two in flight) / weight staging by bulk TMA (wbar: the matrix in sW; ebar: the embedding operand in sK
+    // resp. the compact tiles of phase 1, in flight together with the first matrix)
     __shared__ uint64_t mbar, mbar2, wbar, ebar;
     __shared__ uint32_t tmem_base_s;
     __shared__ int s_item[2];                             // this work item / the next one (fetched a whole item ahead)
@@ -220,9 +222,10 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
     // residual epilogues (after the attention has consumed V; before the next V epilogue rewrites it)
     float2 (*s_part)[128] = reinterpret_cast<float2 (*)[128]>(sV);
     const int row = tid & 127, part = warp >> 2;          // thread = (row, column quarter); TMEM lane = row
-    const int num_tiles = (B + kTileSamples - 1) / kTileSamples, num_groups = (num_tiles + group_tiles - 1) / group_tiles;
-    const int group_samples = group_tiles * kTileSamples;
-    const int num_items = num_groups + num_tiles;
+    const int num_tiles = (B + kTileSamples - 1) / kTileSamples, num_groups = (B + kGroupRows - 1) / kGroupRows;
+    const int num_items = 2 * (kPhase == 0 ? num_tiles : num_groups);
+    // compact scratch: per network the attention outputs, then the residual rows, of every 128 samples as one canonical tile
+    unsigned char *const scr_critic = scratch, *const scr_actor = scratch + (size_t)2 * num_groups * kTileBytes;
     if (warp == 0) tmem_alloc(&tmem_base_s, 512);
     if (tid == 0) {
         mbar_init(&mbar, 1); mbar_init(&mbar2, 1); mbar_init(&wbar, 1); mbar_init(&ebar, 1); fence_mbar_init();
@@ -244,9 +247,6 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
     int cur = 0;
     float o[16];                                          // this thread's observation row (tid < 128), fetched ahead of its use
     bool have_obs = false;
-
-    // first sample of work item `it`: actor groups come first (the longest items), then the critic tiles
-    auto item_first_sample = [&](int it) { return it < num_groups ? it * group_samples : (it - num_groups) * kTileSamples; };
 
     // ---- embedding of the 128 staged rows: X = relu(obs W^T + b) + pos (transformer_net.py:24-30,57-59) -> sX.
     //      On the tensor cores with K = 32: the fp32 observation row is split into bf16 hi + lo parts (columns 0..13 and
@@ -317,7 +317,7 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
         epilogue_act(tmem_lane, row, true, D + part * 32, D + part * 32 + 32, false, sQ, D, D);
         mbar_wait(&mbar, parity); parity ^= 1;
         tc_fence_after();
-        if (tid == 0) bulk_load2(sW, next_w, next_w_bytes, sB, next_b, next_b_bytes, &wbar);
+        if (tid == 0 && next_w) bulk_load2(sW, next_w, next_w_bytes, sB, next_b, next_b_bytes, &wbar);
         epilogue_act(tmem_lane, row, true, 2 * D + part * 32, 2 * D + part * 32 + 32, false, sQ, D, D);
         tc_fence_before();
         __syncthreads();
@@ -428,33 +428,25 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
         __syncthreads();
     };
 
-    // Work items, handed out dynamically, longest first:
-    //   actor group  = up to 5 tiles of 25 samples (fewer when the batch is too small to give every SM several items).  The actor's only layer is a LAST layer: per tile it needs the embedding, the QKV
-    //                  projection and the attention of the newest token - whose 25 output rows are collected in COMPACT rows
-    //                  of sQ, so that out-proj, FFN, both LayerNorms and the head run ONCE per 125 samples on a full M = 128
-    //                  tile instead of five times on tiles with 25 useful rows (their residual input, X of the newest tokens,
-    //                  is embedded again: one K = 32 product);
-    //   critic tile  = 25 samples = 125 token rows through the inner layer, then the same last-layer scheme on its own rows.
+    // Work items are handed out dynamically; the two-layer critic items come first (longest first)
     for (;;) {
         const int item = s_item[cur];
         if (item >= num_items) break;
         if (tid == 0) s_item[cur ^ 1] = atomicAdd(work_counter, 1);   // read after the barriers of this item
-        const bool is_actor = item < num_groups;
-        const BlockW &w = is_actor ? w_actor : w_critic;
-        const HeadW &head = is_actor ? head_actor : head_critic;
-        const float *const pw = sP + (is_actor ? kPActor : kPCritic);
-        __nv_bfloat16 *head_hidden = is_actor ? hh_actor : hh_critic;
-        const int g0 = item_first_sample(item);                       // first sample of the item
-        const int item_samples = min(is_actor ? group_samples : kTileSamples, B - g0);
-        const int ntiles = (item_samples + kTileSamples - 1) / kTileSamples;
+        const bool is_critic = item < num_items / 2;
+        const BlockW &w = is_critic ? w_critic : w_actor;
+        const HeadW &head = is_critic ? head_critic : head_actor;
+        const float *const pw = sP + (is_critic ? kPCritic : kPActor);
         const LayerW &LL = w.layer[w.layers - 1];                     // the last layer
-        const float *const pll = pw + kPLayer + (w.layers - 1) * kPLayerSize;
-        if (tid == 0)   // sW / sB are free since the previous item's head GEMM retired: the first Wq|Wk has the whole embedding to land
-            bulk_load2(sW, w.layer[0].in_wp, 2 * D * D * 2, sB, w.layer[0].in_bp, 2 * D * kBiasK * 2, &wbar);
-        for (int tl = 0; tl < ntiles; ++tl) {
-            const int s0 = g0 + tl * kTileSamples;
+        unsigned char *const scr_attn = is_critic ? scr_critic : scr_actor, *const scr_res = scr_attn + (size_t)num_groups * kTileBytes;
+        if constexpr (kPhase == 0) {
+            const int tile = is_critic ? item : item - num_tiles;
+            const int s0 = tile * kTileSamples;
             const int nsamp = min(kTileSamples, B - s0), nrows = nsamp * S;
-            if (tid == 0) bulk_load(sK, w.emb_w2p, D * 32 * 2, &ebar);    // embedding weights (B operand, K = 32)
+            if (tid == 0) {   // sW / sB are free since the previous item's last MMAs retired: Wq|Wk has the whole embedding to land
+                bulk_load(sK, w.emb_w2p, D * 32 * 2, &ebar);              // embedding weights (B operand, K = 32)
+                bulk_load2(sW, w.layer[0].in_wp, 2 * D * D * 2, sB, w.layer[0].in_bp, 2 * D * kBiasK * 2, &wbar);
+            }
             if (tid < 128) {   // this tile's token rows (fetched ahead, normally) and the key-padding mask (transformer_net.py:52-54)
                 if (!have_obs) load_obs_row(obs, s0, nrows, tid, o);
                 float asum = 0.0f;
@@ -462,60 +454,80 @@ fused_block_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW h
                 for (int j = 0; j < 16; ++j) asum += fabsf(o[j]);
                 s_pad[tid] = (tid < nrows && asum == 0.0f && tid % S != S - 1) ? 1 : 0;
             }
-            have_obs = false;
             embed_rows(w, pw, nrows, -1);
-            if (!is_actor) {   // the critic's inner layer: every token is a query; Wq|Wk of the last layer follows W2
+            {   // the next work item's token rows arrive under this item's layers
+                const int next = s_item[cur ^ 1];
+                have_obs = next < num_items;
+                if (have_obs && tid < 128) {
+                    const int ns0 = (next < num_tiles ? next : next - num_tiles) * kTileSamples;
+                    load_obs_row(obs, ns0, min(kTileSamples, B - ns0) * S, tid, o);
+                }
+            }
+            if (is_critic) {   // the critic's inner layer: every token is a query; Wq|Wk of the last layer follows W2
                 qkv_attention(w.layer[0], nsamp, true, -1, w.layer[0].out_wp, D * D * 2, w.layer[0].out_bp, D * kBiasK * 2);
                 post_attention(w.layer[0], pw + kPLayer, LL.in_wp, 2 * D * D * 2, LL.in_bp, 2 * D * kBiasK * 2);
             }
-            // last layer: the newest token's attention.  Behind V's MMAs: the next tile's Wq|Wk, or the out-proj weights
-            const bool more = tl + 1 < ntiles;
-            if (more && tid < 128) {   // the next tile's token rows arrive under this tile's projections and attention
-                const int ns0 = s0 + kTileSamples;
-                load_obs_row(obs, ns0, min(kTileSamples, B - ns0) * S, tid, o);
-            }
-            qkv_attention(LL, nsamp, false, is_actor ? tl * kTileSamples : -1, more ? LL.in_wp : LL.out_wp,
-                          more ? 2 * D * D * 2 : D * D * 2, more ? LL.in_bp : LL.out_bp, more ? 2 * D * kBiasK * 2 : D * kBiasK * 2);
-            have_obs = more;
-        }
-        if (is_actor) {   // X of the newest tokens again: the residual input of what follows, one row per sample
-            if (tid == 0) bulk_load(sK, w.emb_w2p, D * 32 * 2, &ebar);
-            if (tid < 128) load_newest_obs_row(obs, g0, item_samples, tid, o);
-            embed_rows(w, pw, item_samples, S - 1);
-        }
-        post_attention(LL, pll, head.w1p, HID * D * 2, head.b1p, HID * kBiasK * 2);
-        // ---- head first layer: relu(W1 z + b1) for the newest token of every sample (transformer_net.py:106-108) ----
-        tc_fence_after();
-        mbar_wait(&wbar, wparity); wparity ^= 1;
-        if (tid == 0) issue_gemm(tmem, sX, sW, HID, D, &mbar, sB, sOnes);
-        {   // the next work item's first token rows arrive under the head GEMM and its epilogue
-            const int next = s_item[cur ^ 1];
-            have_obs = next < num_items;
-            if (have_obs && tid < 128) {
-                const int ns0 = item_first_sample(next);
-                load_obs_row(obs, ns0, min(kTileSamples, B - ns0) * S, tid, o);
-            }
-        }
-        mbar_wait(&mbar, parity); parity ^= 1;
-        tc_fence_after();
-        if (part < HID / 32) {   // tcgen05.ld is warp-collective: every lane loads, only the rows of newest tokens store
-            const bool keep = is_actor ? row < item_samples : (row < item_samples * S && row % S == S - 1);
-            __nv_bfloat16 *dst = head_hidden + (size_t)(g0 + (is_actor ? row : row / S)) * HID;
-            const int c0 = part * 32;
-            float v[32];
-            tmem_ld32(tmem_lane + c0, v);
+            qkv_attention(LL, nsamp, false, -1, nullptr, 0, nullptr, 0);
+            // the newest-token rows of this tile -> compact scratch (canonical order inside the 128-sample tile they belong to)
+            if (row < nrows && row % S == S - 1) {
+                const int gs = s0 + row / S, cr = gs & (kGroupRows - 1);
+                unsigned char *ga = scr_attn + (size_t)(gs / kGroupRows) * kTileBytes, *gr = scr_res + (size_t)(gs / kGroupRows) * kTileBytes;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
-            if (keep) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4 *>(dst + c0 + g * 8) = pack8(v + g * 8);
+                for (int g = 0; g < 4; ++g) {
+                    const int c = part * 32 + g * 8;
+                    *reinterpret_cast<uint4 *>(ga + canon_off(cr, c, D)) = *reinterpret_cast<const uint4 *>(sQ + canon_off(row, c, D));
+                    *reinterpret_cast<uint4 *>(gr + canon_off(cr, c, D)) = *reinterpret_cast<const uint4 *>(sX + canon_off(row, c, D));
+                }
             }
+            __syncthreads();   // sX / sQ / sK are rewritten by the next item's staging
+        } else {
+            const int group = is_critic ? item : item - num_groups;
+            const int g0 = group * kGroupRows, nvalid = min(kGroupRows, B - g0);
+            const float *const pll = pw + kPLayer + (w.layers - 1) * kPLayerSize;
+            __nv_bfloat16 *head_hidden = is_critic ? hh_critic : hh_actor;
+            if (tid == 0) {   // the 128 attention-output rows -> sQ (A operand of the out-proj), their residual rows -> sX
+                bulk_load2(sQ, scr_attn + (size_t)group * kTileBytes, kTileBytes, sX, scr_res + (size_t)group * kTileBytes, kTileBytes, &ebar);
+                bulk_load2(sW, LL.out_wp, D * D * 2, sB, LL.out_bp, D * kBiasK * 2, &wbar);
+            }
+            mbar_wait(&ebar, eparity); eparity ^= 1;
+            post_attention(LL, pll, head.w1p, HID * D * 2, head.b1p, HID * kBiasK * 2);
+            // ---- head first layer: relu(W1 z + b1) (transformer_net.py:106-108) ----
+            tc_fence_after();
+            mbar_wait(&wbar, wparity); wparity ^= 1;
+            if (tid == 0) issue_gemm(tmem, sX, sW, HID, D, &mbar, sB, sOnes);
+            mbar_wait(&mbar, parity); parity ^= 1;
+            tc_fence_after();
+            if (part < HID / 32) {
+                __nv_bfloat16 *dst = head_hidden + (size_t)(g0 + row) * HID;
+                const int c0 = part * 32;
+                float v[32];
+                tmem_ld32(tmem_lane + c0, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+                if (row < nvalid) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4 *>(dst + c0 + g * 8) = pack8(v + g * 8);
+                }
+            }
+            tc_fence_before();
+            __syncthreads();
         }
-        tc_fence_before();
-        __syncthreads();
         cur ^= 1;
     }
     if (warp == 0) tmem_free(tmem, 512);
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 1)
+fused_tiles_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW head_actor, __nv_bfloat16 *__restrict__ hh_actor,
+                   BlockW w_critic, HeadW head_critic, __nv_bfloat16 *__restrict__ hh_critic, int *__restrict__ work_counter,
+                   unsigned char *__restrict__ scratch) {
+    fused_body<0>(obs, B, w_actor, head_actor, hh_actor, w_critic, head_critic, hh_critic, work_counter, scratch);
+}
+__global__ void __launch_bounds__(kFusedThreads, 1)
+fused_heads_kernel(const float *__restrict__ obs, int B, BlockW w_actor, HeadW head_actor, __nv_bfloat16 *__restrict__ hh_actor,
+                   BlockW w_critic, HeadW head_critic, __nv_bfloat16 *__restrict__ hh_critic, int *__restrict__ work_counter,
+                   unsigned char *__restrict__ scratch) {
+    fused_body<1>(obs, B, w_actor, head_actor, hh_actor, w_critic, head_critic, hh_critic, work_counter, scratch);
 }
 
 // self-test: D[128,N] (fp32) = A[128,K] W[N,K]^T with one CTA: canonical smem operands, K/16 tcgen05.mma steps
@@ -564,24 +576,26 @@ __global__ void __launch_bounds__(128) gemm_tile_selftest_kernel(const __nv_bflo
 
 namespace uavp {
 int fused_block_prepare() {
-    return cudaFuncSetAttribute(fused_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem) == cudaSuccess ? 0 : -2;
+    return cudaFuncSetAttribute(fused_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem) == cudaSuccess &&
+                   cudaFuncSetAttribute(fused_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem) == cudaSuccess
+               ? 0 : -2;
 }
+size_t fused_scratch_bytes(int max_batch) { return (size_t)4 * ((max_batch + kGroupRows - 1) / kGroupRows) * kTileBytes; }
 int launch_fused_blocks(const float *d_obs, int B, const BlockW &actor, const HeadW &actor_head, __nv_bfloat16 *hh_actor,
-                        const BlockW &critic, const HeadW &critic_head, __nv_bfloat16 *hh_critic, int *d_work_counter,
-                        cudaStream_t stream) {
-    const int tiles = (B + kTileSamples - 1) / kTileSamples;
+                        const BlockW &critic, const HeadW &critic_head, __nv_bfloat16 *hh_critic, int *d_work_counters,
+                        unsigned char *d_scratch, cudaStream_t stream) {
     static int num_sms = 0;                       // one persistent CTA per SM of the device
     if (num_sms == 0) {
         int dev = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -2;
     }
-    if (actor.layers != 1 || critic.layers != 2) return -1;   // the kernel's item structure (and its staged parameter layout)
-    // tiles per actor work item: as many as a compact tile holds once every SM still gets several items
-    const int group_tiles = tiles >= 4 * num_sms ? kMaxGroupTiles : (tiles >= 2 * num_sms ? 3 : (tiles >= num_sms ? 2 : 1));
-    const int items = tiles + (tiles + group_tiles - 1) / group_tiles;
-    if (cudaMemsetAsync(d_work_counter, 0, sizeof(int), stream) != cudaSuccess) return -2;
-    fused_block_kernel<<<items < num_sms ? items : num_sms, kFusedThreads, kFusedSmem, stream>>>(
-        d_obs, B, actor, actor_head, hh_actor, critic, critic_head, hh_critic, d_work_counter, group_tiles);
+    if (actor.layers != 1 || critic.layers != 2) return -1;   // the kernels' item structure (and their staged parameter layout)
+    const int items0 = 2 * ((B + kTileSamples - 1) / kTileSamples), items1 = 2 * ((B + kGroupRows - 1) / kGroupRows);
+    if (cudaMemsetAsync(d_work_counters, 0, 2 * sizeof(int), stream) != cudaSuccess) return -2;
+    fused_tiles_kernel<<<items0 < num_sms ? items0 : num_sms, kFusedThreads, kFusedSmem, stream>>>(
+        d_obs, B, actor, actor_head, hh_actor, critic, critic_head, hh_critic, d_work_counters, d_scratch);
+    fused_heads_kernel<<<items1 < num_sms ? items1 : num_sms, kFusedThreads, kFusedSmem, stream>>>(
+        d_obs, B, actor, actor_head, hh_actor, critic, critic_head, hh_critic, d_work_counters + 1, d_scratch);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 }  // namespace uavp
