@@ -251,7 +251,7 @@ def measure_ppo(rank, local_rank, world, dev, B, T, K, W, with_clocks=True):
             "e2e": {"value": samples / (ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 24,
                     "note": "the whole loop is device-resident; only the three mean losses leave the GPU per update"},
             # own kernels per iteration: T x (fused policy blocks + heads + env step) + 2 GAE + the minibatch steps
-            "gpu_launches": K * (T * 3 + 2 + launches_mb * n_mb),
+            "gpu_launches": K * (T * 4 + 2 + launches_mb * n_mb),   # per rollout step: env step, two fused forward kernels, heads / sampling
             "clocks": clocks}
     agent.close()       # drop the captured graph before the communicator it references goes away
     env.close()

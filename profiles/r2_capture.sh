@@ -18,7 +18,7 @@ CMD="python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-ppo"
 $CMD > $O/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 600 -c 400 --csv --log-file $O/r2_launches_bench_c3.csv $CMD > $O/ncu1.log 2>&1
 $CMD > $O/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 310 -c 3 -f -o $O/r2_step_kernel_c3 $CMD > $O/ncu2.log 2>&1
 POL="python profiles/measure_policy.py 16384"
-$POL > $O/plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:fused_block -s 2 -c 1 -f -o $O/r2_fused_block $POL > $O/ncu3.log 2>&1
+$POL > $O/plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:fused_ -s 4 -c 2 -f -o $O/r2_fused_block $POL > $O/ncu3.log 2>&1
 $POL > $O/plain2.log 2>&1 && ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active --clock-control none -c 200 --csv --log-file $O/r2_launches_policy_forward_B16384.csv $POL > $O/ncu3b.log 2>&1
 UPD="python profiles/measure_update.py 131072 fused"
 $UPD > $O/plain3.log 2>&1 && ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__throughput.avg.pct_of_peak_sustained_elapsed --clock-control none --launch-skip 500 -c 220 --csv --log-file $O/r2_launches_ppo_update_step.csv $UPD > $O/ncu4.log 2>&1

@@ -97,11 +97,9 @@ __device__ __forceinline__ void load_cols32(const float *p, float2 *o) {   // p:
     }
 }
 
-// plain layer: out = act(acc) -> bf16; column c goes to tile (c / tile_cols) of dst, canonical row length Kout.  The thread's
-// accumulator row lands in row dst_row of the tile (its own row, or a compacted one); `store` = false only loads (tcgen05.ld
-// is warp-collective)
-__device__ __forceinline__ void epilogue_act(uint32_t tmem_lane, int dst_row, bool store, int c_begin, int c_end, bool relu,
-                                             unsigned char *dst, int Kout, int tile_cols) {
+// plain layer: out = act(acc) -> bf16; column c goes to tile (c / tile_cols) of dst, canonical row length Kout
+__device__ __forceinline__ void epilogue_act(uint32_t tmem_lane, int row, int c_begin, int c_end, bool relu, unsigned char *dst,
+                                             int Kout, int tile_cols) {
     for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         float v[32];
         tmem_ld32(tmem_lane + c0, v);
@@ -110,11 +108,9 @@ __device__ __forceinline__ void epilogue_act(uint32_t tmem_lane, int dst_row, bo
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
         }
         unsigned char *tile = dst + (c0 / tile_cols) * kTileBytes;
-        if (store) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-                *reinterpret_cast<uint4 *>(tile + canon_off(dst_row, (c0 % tile_cols) + g * 8, Kout)) = pack8(v + g * 8);
-        }
+        for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4 *>(tile + canon_off(row, (c0 % tile_cols) + g * 8, Kout)) = pack8(v + g * 8);
     }
 }
 
@@ -297,10 +293,9 @@ __device__ __forceinline__ void fused_body(const float *__restrict__ obs, int B,
 
     // ---- Q|K = X [Wq|Wk]^T (N = 256), then V = X Wv^T (N = 128) under the K epilogue -> sQ | sK | sV, and the attention over the
     //      5-token window (its output overwrites the Q rows).  all_queries: every token is a query (an inner layer); otherwise
-    //      only the newest token of a sample (transformer_net.py:106), and with qbase >= 0 its Q row / attention output live
-    //      in COMPACT row qbase + sample of sQ (the actor collects the newest tokens of 5 tiles there).  next_w / next_b: the
-    //      matrix (and bias operand) to stream into sW once V's MMAs have retired ----
-    auto qkv_attention = [&](const LayerW &L, int nsamp, bool all_queries, int qbase, const __nv_bfloat16 *next_w, uint32_t next_w_bytes,
+    //      only the newest token of a sample (transformer_net.py:106).  next_w / next_b: the matrix (and bias operand) to stream
+    //      into sW once V's MMAs have retired, or NULL ----
+    auto qkv_attention = [&](const LayerW &L, int nsamp, bool all_queries, const __nv_bfloat16 *next_w, uint32_t next_w_bytes,
                              const __nv_bfloat16 *next_b, uint32_t next_b_bytes) {
         tc_fence_after();
         mbar_wait(&wbar, wparity); wparity ^= 1;                      // Wq|Wk has landed in sW
@@ -308,17 +303,14 @@ __device__ __forceinline__ void fused_body(const float *__restrict__ obs, int B,
         mbar_wait(&mbar, parity); parity ^= 1;
         tc_fence_after();
         if (tid == 0) bulk_load2(sW, L.in_wp + 2 * D * D, D * D * 2, sB, L.in_bp + 2 * D * kBiasK, D * kBiasK * 2, &wbar);   // Wv (rows 256..383)
-        {
-            const bool newest = row % S == S - 1 && row < nsamp * S;
-            epilogue_act(tmem_lane, qbase >= 0 ? qbase + row / S : row, qbase < 0 || newest, part * 32, part * 32 + 32, false, sQ, D, D);
-        }
+        epilogue_act(tmem_lane, row, part * 32, part * 32 + 32, false, sQ, D, D);
         mbar_wait(&wbar, wparity); wparity ^= 1;                      // Wv has landed
         if (tid == 0) issue_gemm(tmem + 2 * D, sX, sW, D, D, &mbar, sB, sOnes);
-        epilogue_act(tmem_lane, row, true, D + part * 32, D + part * 32 + 32, false, sQ, D, D);
+        epilogue_act(tmem_lane, row, D + part * 32, D + part * 32 + 32, false, sQ, D, D);
         mbar_wait(&mbar, parity); parity ^= 1;
         tc_fence_after();
         if (tid == 0 && next_w) bulk_load2(sW, next_w, next_w_bytes, sB, next_b, next_b_bytes, &wbar);
-        epilogue_act(tmem_lane, row, true, 2 * D + part * 32, 2 * D + part * 32 + 32, false, sQ, D, D);
+        epilogue_act(tmem_lane, row, 2 * D + part * 32, 2 * D + part * 32 + 32, false, sQ, D, D);
         tc_fence_before();
         __syncthreads();
         // A warp takes a (query, head) pair and its lanes the samples: the 8 lanes of a quarter-warp then read 8 different rows
@@ -329,7 +321,7 @@ __device__ __forceinline__ void fused_body(const float *__restrict__ obs, int B,
         for (int pair = warp; pair < npair; pair += kFusedThreads / 32) {
             const int h = pair % H, i = all_queries ? pair / H : S - 1;
             if (lane < nsamp) {
-                const int smp = lane, r = qbase >= 0 ? qbase + smp : smp * S + i;
+                const int smp = lane, r = smp * S + i;
                 unsigned char *pq = sQ + canon_off(r, h * DH, D);
                 float2 q2[8];
                 {
@@ -408,11 +400,11 @@ __device__ __forceinline__ void fused_body(const float *__restrict__ obs, int B,
         }
         mbar_wait(&mbar, parity); parity ^= 1;
         tc_fence_after();
-        epilogue_act(tmem_lane, row, true, part * 32, part * 32 + 32, true, sH, FF, FF);
+        epilogue_act(tmem_lane, row, part * 32, part * 32 + 32, true, sH, FF, FF);
         mbar_wait(&mbar2, parity2); parity2 ^= 1;
         tc_fence_after();
         if (tid == 0) bulk_load2(sW, L.l2_wp, D * FF * 2, sB, L.l2_bp, D * kBiasK * 2, &wbar);
-        epilogue_act(tmem_lane, row, true, FF / 2 + part * 32, FF / 2 + part * 32 + 32, true, sH, FF, FF);
+        epilogue_act(tmem_lane, row, FF / 2 + part * 32, FF / 2 + part * 32 + 32, true, sH, FF, FF);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -464,10 +456,10 @@ __device__ __forceinline__ void fused_body(const float *__restrict__ obs, int B,
                 }
             }
             if (is_critic) {   // the critic's inner layer: every token is a query; Wq|Wk of the last layer follows W2
-                qkv_attention(w.layer[0], nsamp, true, -1, w.layer[0].out_wp, D * D * 2, w.layer[0].out_bp, D * kBiasK * 2);
+                qkv_attention(w.layer[0], nsamp, true, w.layer[0].out_wp, D * D * 2, w.layer[0].out_bp, D * kBiasK * 2);
                 post_attention(w.layer[0], pw + kPLayer, LL.in_wp, 2 * D * D * 2, LL.in_bp, 2 * D * kBiasK * 2);
             }
-            qkv_attention(LL, nsamp, false, -1, nullptr, 0, nullptr, 0);
+            qkv_attention(LL, nsamp, false, nullptr, 0, nullptr, 0);
             // the newest-token rows of this tile -> compact scratch (canonical order inside the 128-sample tile they belong to)
             if (row < nrows && row % S == S - 1) {
                 const int gs = s0 + row / S, cr = gs & (kGroupRows - 1);
