@@ -239,6 +239,11 @@ __device__ __forceinline__ void fused_body(const float *__restrict__ obs, int B,
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
     const uint32_t tmem_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    // programmatic dependent launch: the second kernel's CTAs may start (on SMs the first kernel has left) and run the
+    // prologue above while the first kernel's last work items are still running; they wait HERE for its completion and the
+    // visibility of its scratch writes
+    if constexpr (kPhase == 0) asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+    else asm volatile("griddepcontrol.wait;\n" ::: "memory");
     uint32_t parity = 0, parity2 = 0, wparity = 0, eparity = 0;
     int cur = 0;
     float o[16];                                          // this thread's observation row (tid < 128), fetched ahead of its use
@@ -586,8 +591,18 @@ int launch_fused_blocks(const float *d_obs, int B, const BlockW &actor, const He
     if (cudaMemsetAsync(d_work_counters, 0, 2 * sizeof(int), stream) != cudaSuccess) return -2;
     fused_tiles_kernel<<<items0 < num_sms ? items0 : num_sms, kFusedThreads, kFusedSmem, stream>>>(
         d_obs, B, actor, actor_head, hh_actor, critic, critic_head, hh_critic, d_work_counters, d_scratch);
-    fused_heads_kernel<<<items1 < num_sms ? items1 : num_sms, kFusedThreads, kFusedSmem, stream>>>(
-        d_obs, B, actor, actor_head, hh_actor, critic, critic_head, hh_critic, d_work_counters + 1, d_scratch);
+    {   // launched as a programmatic dependent of the first kernel (griddepcontrol.wait in its prologue)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(items1 < num_sms ? items1 : num_sms); cfg.blockDim = dim3(kFusedThreads);
+        cfg.dynamicSmemBytes = kFusedSmem; cfg.stream = stream;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        int *ctr = d_work_counters + 1;
+        if (cudaLaunchKernelEx(&cfg, fused_heads_kernel, d_obs, B, actor, actor_head, hh_actor, critic, critic_head, hh_critic, ctr,
+                               d_scratch) != cudaSuccess) return -2;
+    }
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 }  // namespace uavp
